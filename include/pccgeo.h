@@ -1,0 +1,154 @@
+/*
+ * pccgeo.h -- C ABI of libpccgeo.so, the B200 (sm_100a) implementation of the pcc_geo_cnn_v2 hot path.
+ *
+ * The reference (mauriceqch/pcc_geo_cnn_v2) has no FFI for this path: it reaches the arithmetic through
+ * Python call signatures (Keras layers, tfc entropy models) that bottom out in TensorFlow 1.15 / cuDNN and
+ * tensorflow-compression 1.3 kernels.  Each entry point below names the reference interface it replaces
+ * (file:line relative to the reference repo).  The Python host shim (pcc_geo_cnn_v2_b200/) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all `const T* x` / `T* y` below are DEVICE pointers unless the name
+ *     ends in `_host`; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - the caller owns every buffer; the library never allocates device memory behind the caller's back
+ *     (workspaces are passed in) and never synchronises the device.
+ *   - return value: 0 on success, negative PCCGEO_E* on failure; pccgeo_last_error() gives the text.
+ *   - re-entrant per stream.
+ *   - tensors are channels_first, contiguous: (N, C, D, H, W) -- the reference's only working layout
+ *     (src/model_types.py:180).
+ */
+#ifndef PCCGEO_H_
+#define PCCGEO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCCGEO_OK 0
+#define PCCGEO_EINVAL (-1)   /* bad argument / unsupported shape */
+#define PCCGEO_ECUDA (-2)    /* CUDA runtime error (text in pccgeo_last_error) */
+#define PCCGEO_ENOSPC (-3)   /* output buffer / workspace too small */
+#define PCCGEO_EDATA (-4)    /* corrupt bitstream */
+
+/* ---- library ------------------------------------------------------------------------------------ */
+const char* pccgeo_last_error(void);
+int pccgeo_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+long long pccgeo_launch_count(void);
+/* debug / tuning knobs ("umma_swap_lbo_sbo", "umma_max_ctas"); unknown names return PCCGEO_EINVAL */
+int pccgeo_set_option(const char* name, long long value);
+
+/* ---- 3D convolutions, fp32 CUDA-core path ---------------------------------------------------------
+ * Replaces tf.keras.layers.Conv3D / Conv3DTranspose with padding='same' as instantiated at
+ * src/model_transforms.py:45-47,56-58,67-69,78-80,93,107,121,135,144-146,155-157 (TF Conv3D /
+ * Conv3DBackpropInputV2 + BiasAdd + Relu), plus the ResidualLayer add (src/model_transforms.py:35-36).
+ *
+ *   y = [residual +] [relu]( conv(x, w) [+ bias] )
+ *
+ * x (N,Cin,D,H,W) fp32; y (N,Cout,D',H',W'): D' = ceil(D/stride) (conv) or D*stride (transposed).
+ * w is in the library's tap-major layout (k^3, Cin, Cout) -- i.e. the Keras Conv3D kernel as is, and the
+ * Keras Conv3DTranspose kernel (k,k,k,Cout,Cin) with its last two axes swapped.
+ * bias (Cout) or NULL; residual (shape of y) or NULL. */
+int pccgeo_conv3d_f32(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                      int n, int cin, int d, int h, int wd, int cout, int k, int stride, int transposed,
+                      int relu, void* stream);
+
+/* ---- 3D convolutions, tcgen05 tensor-core path (3x3x3 kernels) ------------------------------------
+ * Same reference call sites as above, for the 3x3x3 layers of the V2 / progressive / hyper transforms
+ * (src/model_transforms.py:62-158).  Activations live in a blocked channels layout
+ *   (N, C/8, D, H, W, 8) bf16   [one "plane set" per precision term]
+ * with `terms` = 1 (bf16 operands) or 2 (hi + lo bf16 split; products a_hi*w_hi + a_hi*w_lo + a_lo*w_hi
+ * accumulated in fp32 -- "bf16x3", fp32-class accuracy).  Term t of a tensor starts at element offset
+ * t * N*C*D*H*W.  Channel counts are padded up to a multiple of 16 by the pack/convert kernels. */
+
+/* fp32 (N,C,D,H,W) -> blocked bf16 (terms, N, Cp/8, D, H, W, 8), Cp = round_up(C,16), zero padded */
+int pccgeo_f32_to_blocked(const float* x, void* xb, int n, int c, int d, int h, int wd, int terms, void* stream);
+/* blocked bf16 -> fp32 (N,C,D,H,W) (sums the terms) */
+int pccgeo_blocked_to_f32(const void* xb, float* x, int n, int c, int d, int h, int wd, int terms, void* stream);
+
+/* Pack tap-major fp32 weights (27, Cin, Cout) into the UMMA B-operand image used by pccgeo_conv3d_umma.
+ * Returns the image size in bytes when wpacked == NULL.  `transposed`, `stride` select the layer type
+ * (they change which taps are stacked together); HOST pointers in, HOST image out. */
+long long pccgeo_umma_pack_weights_host(const float* w_host, void* wpacked_host, int cin, int cout,
+                                        int stride, int transposed, int terms);
+
+/* y = [residual +] [relu](conv(x,w) [+bias]) on blocked tensors, stride 1 or 2, conv or transposed conv.
+ * bias: fp32 (Cout) or NULL.  residual: blocked like y or NULL.  Spatial dims must be multiples of 8
+ * (16 for H when stride==1). */
+int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, const void* residual_b,
+                       void* yb, int n, int cin, int d, int h, int wd, int cout, int stride, int transposed,
+                       int relu, int terms, void* stream);
+
+/* ---- entropy models ------------------------------------------------------------------------------
+ * tfc.EntropyBottleneck (factorized prior; used at src/model_types.py:254,258,287,291-292,300,306,333,338,
+ * 377,382-383,397,404).  `eb_params` is the packed per-channel parameter block, C x 58 floats:
+ *   [0:3]  softplus(matrix_0) (3x1)   [3:12] softplus(matrix_1) (3x3 row-major)   [12:21] softplus(matrix_2)
+ *   [21:24] softplus(matrix_3) (1x3)  [24:27] bias_0  [27:30] bias_1  [30:33] bias_2  [33] bias_3
+ *   [34:37] tanh(factor_0) [37:40] tanh(factor_1) [40:43] tanh(factor_2)  [43] median  [44:58] reserved */
+#define PCCGEO_EB_PARAM_STRIDE 58
+
+/* symbols = floor(x + .5 - median[c]) (int32), x_hat = symbols + median[c]; either output may be NULL */
+int pccgeo_eb_quantize(const float* x, const float* eb_params, int32_t* symbols, float* x_hat,
+                       int n, int c, int spatial, void* stream);
+/* x_hat = symbols + median[c] (decoder side of EntropyBottleneck.decompress) */
+int pccgeo_eb_dequantize(const int32_t* symbols, const float* eb_params, float* x_hat,
+                         int n, int c, int spatial, void* stream);
+/* likelihood = max(|sigmoid(s*u) - sigmoid(s*l)|, 1e-9) of `values` (already noised or dequantised).
+ * sum_log (device double[1], may be NULL) receives sum(ln likelihood), reduced in a fixed order
+ * (deterministic); partials: device workspace of >= pccgeo_reduce_ws_doubles() doubles. */
+int pccgeo_eb_likelihood(const float* values, const float* eb_params, float* likelihood, double* sum_log,
+                         double* partials, int n, int c, int spatial, void* stream);
+
+/* tfc.GaussianConditional + the reference patch (src/utils/patch_gaussian_conditional.py:49-125; used at
+ * src/model_types.py:340-341,385-387,406-407).  scale_table: device fp32 (levels).
+ * symbols = rint(y) (int32), y_hat = float(symbols), indexes = (levels-1) - #{t in table[:-1]: max(sigma,table[0]) <= t}
+ * any of y/symbols/y_hat may be NULL (decoder calls it with only sigma -> indexes). */
+int pccgeo_gc_quantize(const float* y, const float* sigma, const float* scale_table, int levels,
+                       int32_t* symbols, float* y_hat, int32_t* indexes, long long count, void* stream);
+/* likelihood = max(Phi((.5-|v|)/s) - Phi((-.5-|v|)/s), 1e-9), s = max(sigma, scale_min) */
+int pccgeo_gc_likelihood(const float* values, const float* sigma, float scale_min, float* likelihood,
+                         double* sum_log, double* partials, long long count, void* stream);
+/* int32 symbols -> fp32 (GaussianConditional.decompress dequantise, mean=None) */
+int pccgeo_i32_to_f32(const int32_t* symbols, float* out, long long count, void* stream);
+size_t pccgeo_reduce_ws_doubles(void);
+
+/* ---- voxel-grid helpers ---------------------------------------------------------------------------
+ * sparse_to_dense (src/model_types.py:108-114): scatter 1.0f at integer coords.  coords: int16 (npts,4) =
+ * (block, z, y, x); x must be zero-initialised by the caller (cudaMemsetAsync). */
+int pccgeo_densify(const int16_t* coords, long long npts, float* x, int n, int d, int h, int wd, void* stream);
+/* decompress_blocks / compress_blocks thresholding (src/model_types.py:201-202,209,233-234):
+ * bit = min(x_hat,1) > threshold[block]; packed little-endian, 32 voxels per uint32 word in C order;
+ * counts[block] = number of set bits.  voxels per block must be a multiple of 32. */
+int pccgeo_threshold_pack(const float* x_hat, const float* thresholds, uint32_t* bits, int32_t* counts,
+                          int n, long long voxels_per_block, void* stream);
+/* focal_loss (src/utils/focal_loss.py:5-12), sum-reduced, deterministic order; out: device double[1] */
+int pccgeo_focal_loss(const float* x_true, const float* x_pred, float gamma, float alpha, double* out,
+                      double* partials, long long count, void* stream);
+
+/* ---- range coder (HOST) ---------------------------------------------------------------------------
+ * Replaces tfc's range_coding_ops.unbounded_index_range_encode / _decode (precision 16, overflow_width 4;
+ * src/utils/patch_gaussian_conditional.py:27-31 and EntropyBottleneck/GaussianConditional.compress/.decompress).
+ * All pointers are HOST memory.  Streams are independent; `threads` worker threads split them.
+ *   symbols/indexes: concatenated per-stream arrays, stream i covers [sym_offsets[i], sym_offsets[i+1])
+ *   cdf: (rows, cdf_stride) int32, cdf_length (rows), offset (rows)
+ *   encode: out_bytes capacity out_capacity; out_offsets (nstreams+1) receives the byte ranges.
+ *   index_mode 0: indexes given per symbol; 1: index = (position / channel_stride) % rows (per-channel
+ *   tables, EntropyBottleneck) -- `indexes` may then be NULL. */
+int pccgeo_range_encode_host(const int32_t* symbols, const int32_t* indexes, const long long* sym_offsets,
+                             int nstreams, const int32_t* cdf, int cdf_stride, const int32_t* cdf_length,
+                             const int32_t* offset, int rows, int index_mode, long long channel_stride,
+                             uint8_t* out_bytes, long long out_capacity, long long* out_offsets, int threads);
+int pccgeo_range_decode_host(const uint8_t* bytes, const long long* byte_offsets, const int32_t* indexes,
+                             const long long* sym_offsets, int nstreams, const int32_t* cdf, int cdf_stride,
+                             const int32_t* cdf_length, const int32_t* offset, int rows, int index_mode,
+                             long long channel_stride, int32_t* symbols_out, int threads);
+/* tfc pmf_to_quantized_cdf (precision 16): pmf (len) doubles -> cdf (len+1) int32, HOST */
+int pccgeo_pmf_to_quantized_cdf_host(const double* pmf, int len, int precision, int32_t* cdf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCCGEO_H_ */

@@ -1,0 +1,87 @@
+"""ctypes binding of libpccgeo.so (the C ABI declared in include/pccgeo.h).
+
+The product path has no CPU fallback: if the library cannot be loaded, or a device entry point is called
+without a CUDA device, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpccgeo.so')
+
+_lib = None
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> (restype, argtypes); mirrors include/pccgeo.h one to one (tests/test_abi.py checks the header against this)
+SIGNATURES = {
+    'pccgeo_last_error': (C.c_char_p, []),
+    'pccgeo_version': (i32, []),
+    'pccgeo_launch_count': (i64, []),
+    'pccgeo_set_option': (i32, [C.c_char_p, i64]),
+    'pccgeo_conv3d_f32': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_f32_to_blocked': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_blocked_to_f32': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_umma_pack_weights_host': (i64, [vp, vp, i32, i32, i32, i32, i32]),
+    'pccgeo_conv3d_umma': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_eb_quantize': (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    'pccgeo_eb_dequantize': (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    'pccgeo_eb_likelihood': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    'pccgeo_gc_quantize': (i32, [vp, vp, vp, i32, vp, vp, vp, i64, vp]),
+    'pccgeo_gc_likelihood': (i32, [vp, vp, f32, vp, vp, vp, i64, vp]),
+    'pccgeo_i32_to_f32': (i32, [vp, vp, i64, vp]),
+    'pccgeo_reduce_ws_doubles': (C.c_size_t, []),
+    'pccgeo_densify': (i32, [vp, i64, vp, i32, i32, i32, i32, vp]),
+    'pccgeo_threshold_pack': (i32, [vp, vp, vp, vp, i32, i64, vp]),
+    'pccgeo_focal_loss': (i32, [vp, vp, f32, f32, vp, vp, i64, vp]),
+    'pccgeo_range_encode_host': (i32, [vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, vp, i64, vp, i32]),
+    'pccgeo_range_decode_host': (i32, [vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, vp, i32]),
+    'pccgeo_pmf_to_quantized_cdf_host': (i32, [vp, i32, i32, vp]),
+}
+
+
+class PccGeoError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (building first if the .so is absent and nvcc is available) and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    h = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(h, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = h
+    return h
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().pccgeo_last_error().decode('utf-8', 'replace')
+        raise PccGeoError(f'{what} failed (code {rc}): {msg}')
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, 'data_ptr'):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise PccGeoError('pcc_geo_cnn_v2_b200 needs a CUDA device (sm_100a); there is no CPU fallback')

@@ -1,0 +1,571 @@
+// tcgen05 / TMEM / TMA implicit-GEMM 3x3x3 convolution for sm_100a.
+//
+// Replaces Keras Conv3D / Conv3DTranspose (3,3,3) 'same' + BiasAdd + Relu + ResidualLayer add for the layers of
+// AnalysisBlock / SynthesisBlock / the V2, progressive and hyper transforms
+// (reference src/model_transforms.py:62-81,84-158).
+//
+// Data layout ("blocked"): activations are bf16 (term, N, C/8, D, H, W, 8): eight channels of one voxel are 16
+// contiguous bytes, voxels along W follow at a 16-byte pitch.  That is exactly the UMMA *no-swizzle K-major*
+// core-matrix layout (8 rows x 16 bytes, rows 16 B apart), so an A operand of 128 output voxels (16 y x 8 x)
+// for ANY filter tap is just a different 16-byte-aligned start address into one halo'd input plane in shared
+// memory: start = plane + (dy+1)*row_pitch + (dx+1)*16,  SBO = row_pitch (next y),  LBO = channel-group pitch.
+// No im2col copy, no swizzle phase to keep consistent.
+//
+// Pipeline (one CTA, persistent over work items = (n, y-tile, x-tile) columns, streamed along z):
+//   warp 0      TMA producer: one 5-D box load {8ch, 10 x, 18 y, 1 z, C/8 groups} per input plane and precision
+//               term into a ring of stages; out-of-bounds coordinates are zero-filled = TF 'SAME' padding.
+//   warp 1      MMA issuer (one elected thread): for input plane z and each (ky,kx,k-chunk) ONE tcgen05.mma with
+//               N = 3*Cout whose B operand stacks the three z-taps, accumulating into three neighbouring output
+//               planes that live side by side in a TMEM ring (columns = plane slot x Cout).  This cuts the
+//               A-operand shared-memory reads -- the bound for small Cout -- by 3x.
+//   warps 2..9  epilogue: two groups of four warps (one per TMEM lane quadrant) alternate over finished planes:
+//               tcgen05.ld -> +bias -> ReLU -> +residual -> bf16 (hi[/lo]) -> 16-byte coalesced global stores.
+// Precision terms: terms=1 plain bf16 operands; terms=2 splits activations and weights into hi+lo bf16 and
+// issues a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into the same fp32 accumulator (fp32-class accuracy, 3x MMA work).
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pccgeo {
+
+// --------------------------------------------------------------------------------------------------------
+// debug / tuning options (pccgeo_set_option)
+// --------------------------------------------------------------------------------------------------------
+static int g_opt_swap_lbo_sbo = 0;
+static int g_opt_max_ctas = 0;
+
+// --------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, no swizzle, K-major (SM100 version bit set).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset = 0, lbo_mode = 0, layout_type = 0 (SWIZZLE_NONE / interleave)
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// kernel
+// --------------------------------------------------------------------------------------------------------
+constexpr int TY = 16, TX = 8;                 // output rows of one MMA: 16 y x 8 x = 128 voxels
+constexpr int PY = TY + 2, PX = TX + 2;        // halo'd plane
+constexpr int PLANE_CG_BYTES = PY * PX * 16;   // one channel group of one input plane: 2880 B
+constexpr int ROW_PITCH = PX * 16;             // 160 B between y rows  (SBO of A)
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int MAX_STAGES = 8, MAX_SLOTS = 32;
+
+struct UmmaConvParams {
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+  const uint8_t* wimg;   // packed B-operand image (global)
+  int N, D, H, W;
+  int CGi, CGo;          // channel groups (of 8) in / out
+  int terms, relu, cout_real;
+  int ytiles, xtiles, items;
+  int nstage, nslots;
+  int wbytes_term;       // bytes of one precision term of the weight image
+  int swap;              // debug: swap LBO/SBO roles
+  long long term_stride_out;  // elements between precision terms of y / res
+};
+
+struct __align__(8) SmemHeader {
+  uint64_t in_full[MAX_STAGES], in_empty[MAX_STAGES];
+  uint64_t acc_full[MAX_SLOTS], acc_empty[MAX_SLOTS];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+constexpr int HEADER_BYTES = 1024;
+static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "header too large");
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack_bf16x8_add(const int4& q, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] += f.x;
+    v[2 * i + 1] += f.y;
+  }
+}
+
+template <int COUT>  // padded output channels: 16, 32 or 64
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = p.CGi >> 1;                                  // 16-channel K chunks
+  const int wbytes_all = p.wbytes_term * p.terms;
+  uint8_t* wsm = smem + HEADER_BYTES;
+  const int stage_bytes = p.terms * p.CGi * PLANE_CG_BYTES;
+  uint8_t* stages = wsm + ((wbytes_all + 127) & ~127);
+  const int tmem_cols = p.nslots * COUT;                      // power of two >= 32 (host guarantees)
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&hdr->in_full[i]), 1); mbar_init(smem_u32(&hdr->in_empty[i]), 1); }
+    for (int i = 0; i < p.nslots; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&hdr->tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weights: global -> shared with plain 16-byte copies, then make them visible to the async (UMMA) proxy
+  for (int i = threadIdx.x * 16; i < wbytes_all; i += NUM_THREADS * 16)
+    *reinterpret_cast<int4*>(wsm + i) = __ldg(reinterpret_cast<const int4*>(p.wimg + i));
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  const int D = p.D;
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t q = 0;  // running input-plane counter
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int xt = item % p.xtiles, yt = (item / p.xtiles) % p.ytiles, n = item / (p.xtiles * p.ytiles);
+        for (int z = 0; z < D; ++z, ++q) {
+          const int s = q % p.nstage;
+          const uint32_t use = q / p.nstage;
+          mbar_wait(smem_u32(&hdr->in_empty[s]), (use & 1) ^ 1);
+          const uint32_t full = smem_u32(&hdr->in_full[s]);
+          mbar_expect_tx(full, (uint32_t)stage_bytes);
+          for (int t = 0; t < p.terms; ++t)
+            tma_load_5d(smem_u32(stages + (size_t)s * stage_bytes + (size_t)t * p.CGi * PLANE_CG_BYTES), &tmap_x, full, 0,
+                        xt * TX - 1, yt * TY - 1, z, (t * p.N + n) * p.CGi);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t lbo_a = p.swap ? ROW_PITCH : PLANE_CG_BYTES, sbo_a = p.swap ? PLANE_CG_BYTES : ROW_PITCH;
+      const uint32_t b_kcore = 3 * (COUT / 8) * 128;  // bytes between the two K core matrices of a B tile
+      const uint32_t lbo_b = p.swap ? 128 : b_kcore, sbo_b = p.swap ? b_kcore : 128;
+      const uint32_t b_tile = 2 * b_kcore;            // one (ky,kx,kc) tile: [2 kcore][3*COUT/8 groups][8][8] bf16
+      const int npairs = p.terms == 2 ? 3 : 1;
+      uint32_t q = 0;   // running input-plane counter
+      uint32_t g0 = 0;  // running output-plane counter at the start of this item
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += D) {
+        for (int z = 0; z < D; ++z, ++q) {
+          const int s = q % p.nstage;
+          mbar_wait(smem_u32(&hdr->in_full[s]), (q / p.nstage) & 1);
+          tc_fence_after();
+          const uint32_t a_stage = smem_u32(stages + (size_t)s * stage_bytes);
+          const int pa = z > 0 ? z - 1 : 0, pb = z + 1 < D ? z + 1 : D - 1;  // output planes touched
+          // planes touched for the first time by this input plane: z+1 (if any), and plane 0 when z == 0
+          for (int pl = pa; pl <= pb; ++pl) {
+            const bool first = (pl == z + 1) || (z == 0 && pl == 0);
+            if (first) {
+              const uint32_t g = g0 + pl;
+              mbar_wait(smem_u32(&hdr->acc_empty[g % p.nslots]), ((g / p.nslots) & 1) ^ 1);
+            }
+          }
+          tc_fence_after();
+          int combo = 0;
+          for (int kyx = 0; kyx < 9; ++kyx) {
+            const int ky = kyx / 3, kx = kyx % 3;
+            for (int kc = 0; kc < KC; ++kc, ++combo) {
+              for (int pr = 0; pr < npairs; ++pr) {
+                const int ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+                const uint32_t a_addr = a_stage + ta * p.CGi * PLANE_CG_BYTES + (2 * kc) * PLANE_CG_BYTES + ky * ROW_PITCH + kx * 16;
+                const uint64_t adesc = make_smem_desc(a_addr, lbo_a, sbo_a);
+                const uint32_t b_base = smem_u32(wsm) + tb * p.wbytes_term + (uint32_t)(kyx * KC + kc) * b_tile;
+                const bool very_first = (combo == 0 && pr == 0);
+                // emit maximal runs of planes that are contiguous in the TMEM ring and share the accumulate flag
+                int pl = pa;
+                while (pl <= pb) {
+                  const uint32_t g = g0 + pl;
+                  const int slot = g % p.nslots;
+                  const bool first = very_first && ((pl == z + 1) || (z == 0 && pl == 0));
+                  int run = 1;
+                  while (pl + run <= pb && slot + run < p.nslots) {
+                    const bool f2 = very_first && ((pl + run == z + 1) || (z == 0 && pl + run == 0));
+                    if (f2 != first) break;
+                    ++run;
+                  }
+                  // B rows: plane pl <-> stacked tap index j = pl - (z-1)  (j=0: kz=2, j=1: kz=1, j=2: kz=0)
+                  const int j = pl - (z - 1);
+                  const uint64_t bdesc = make_smem_desc(b_base + (uint32_t)j * (COUT / 8) * 128, lbo_b, sbo_b);
+                  umma_bf16(tmem_base + (uint32_t)slot * COUT, adesc, bdesc, make_idesc(run * COUT), first ? 0u : 1u);
+                  pl += run;
+                }
+              }
+            }
+          }
+          umma_commit(smem_u32(&hdr->in_empty[s]));  // input stage may be refilled once these MMAs retire
+          if (z >= 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z - 1) % p.nslots]));
+          if (z == D - 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z) % p.nslots]));
+        }
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int ew = warp - 2;          // 0..7
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access (warp id % 4)
+    const int grp = ew >> 2;          // planes with (g & 1) == grp
+    const int row = quad * 32 + lane; // M row = TMEM lane
+    const int yl = row >> 3, xl = row & 7;
+    float bias_r[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) bias_r[c] = (p.bias && c < p.cout_real) ? __ldg(p.bias + c) : 0.f;
+    const long long HW = (long long)p.H * p.W, DHW = HW * D;
+    uint32_t g0 = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += D) {
+      const int xt = item % p.xtiles, yt = (item / p.xtiles) % p.ytiles, n = item / (p.xtiles * p.ytiles);
+      const long long vox0 = (long long)(yt * TY + yl) * p.W + (xt * TX + xl);
+      for (int pl = 0; pl < D; ++pl) {
+        const uint32_t g = g0 + pl;
+        if ((int)(g & 1) != grp) continue;
+        const int slot = g % p.nslots;
+        mbar_wait(smem_u32(&hdr->acc_full[slot]), (g / p.nslots) & 1);
+        tc_fence_after();
+        uint32_t r[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; c += 16) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * COUT + c, r + c);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[slot]));  // accumulator slot is free again
+        float v[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          v[c] = __uint_as_float(r[c]) + bias_r[c];
+          if (p.relu) v[c] = fmaxf(v[c], 0.f);
+        }
+        const long long vox = (long long)pl * HW + vox0;
+        if (p.res) {
+          for (int t = 0; t < p.terms; ++t)
+#pragma unroll
+            for (int cg = 0; cg < COUT / 8; ++cg) {
+              const long long e = t * p.term_stride_out + (((long long)n * p.CGo + cg) * DHW + vox) * 8;
+              const int4 qv = __ldg(reinterpret_cast<const int4*>(p.res + e));
+              unpack_bf16x8_add(qv, v + cg * 8);
+            }
+        }
+#pragma unroll
+        for (int cg = 0; cg < COUT / 8; ++cg) {
+          const long long e = (((long long)n * p.CGo + cg) * DHW + vox) * 8;
+          float* vv = v + cg * 8;
+          __nv_bfloat16 hi[8];
+          int4 qh;
+          uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hi[i] = __float2bfloat16_rn(vv[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 t2 = __halves2bfloat162(hi[2 * i], hi[2 * i + 1]);
+            qh32[i] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          *reinterpret_cast<int4*>(p.y + e) = qh;
+          if (p.terms == 2) {
+            int4 ql;
+            uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              ql32[i] = pack_bf16x2(vv[2 * i] - __bfloat162float(hi[2 * i]), vv[2 * i + 1] - __bfloat162float(hi[2 * i + 1]));
+            *reinterpret_cast<int4*>(p.y + p.term_stride_out + e) = ql;
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// layout conversion kernels
+// --------------------------------------------------------------------------------------------------------
+__global__ void f32_to_blocked_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, int N, int C, int CG,
+                                      long long DHW, int terms) {
+  const long long total = (long long)N * CG * DHW;
+  const long long term_stride = total * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i % DHW;
+    const int cg = (int)((i / DHW) % CG);
+    const int n = (int)(i / (DHW * CG));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      v[j] = c < C ? x[((long long)n * C + c) * DHW + vox] : 0.f;
+    }
+    int4 qh, ql;
+    uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
+    uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+      __nv_bfloat162 t2 = __halves2bfloat162(h0, h1);
+      qh32[j] = *reinterpret_cast<uint32_t*>(&t2);
+      ql32[j] = pack_bf16x2(v[2 * j] - __bfloat162float(h0), v[2 * j + 1] - __bfloat162float(h1));
+    }
+    *reinterpret_cast<int4*>(xb + i * 8) = qh;
+    if (terms == 2) *reinterpret_cast<int4*>(xb + term_stride + i * 8) = ql;
+  }
+}
+
+__global__ void blocked_to_f32_kernel(const __nv_bfloat16* __restrict__ xb, float* __restrict__ x, int N, int C, int CG,
+                                      long long DHW, int terms) {
+  const long long total = (long long)N * CG * DHW;
+  const long long term_stride = total * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i % DHW;
+    const int cg = (int)((i / DHW) % CG);
+    const int n = (int)(i / (DHW * CG));
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < terms; ++t) {
+      const int4 q = *reinterpret_cast<const int4*>(xb + t * term_stride + i * 8);
+      unpack_bf16x8_add(q, v);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      if (c < C) x[((long long)n * C + c) * DHW + vox] = v[j];
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+static inline int round_up_i(int a, int m) { return (a + m - 1) / m * m; }
+
+static uint16_t f32_to_bf16_rn_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1);
+  return (uint16_t)(u >> 16);
+}
+static float bf16_to_f32_host(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+template <int COUT>
+static int launch_umma(const CUtensorMap& tmap, const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  static size_t attr_smem = 0;
+  if (!attr_set || smem > attr_smem) {
+    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+    attr_smem = 227 * 1024;
+  }
+  conv3d_umma_kernel<COUT><<<grid, NUM_THREADS, smem, st>>>(tmap, p);
+  return check_launch("conv3d_umma_kernel");
+}
+
+}  // namespace pccgeo
+
+using namespace pccgeo;
+
+extern "C" int pccgeo_set_option(const char* name, long long value) {
+  if (!name) return PCCGEO_EINVAL;
+  if (!strcmp(name, "umma_swap_lbo_sbo")) { g_opt_swap_lbo_sbo = (int)value; return PCCGEO_OK; }
+  if (!strcmp(name, "umma_max_ctas")) { g_opt_max_ctas = (int)value; return PCCGEO_OK; }
+  set_error("set_option: unknown option %s", name);
+  return PCCGEO_EINVAL;
+}
+
+extern "C" int pccgeo_f32_to_blocked(const float* x, void* xb, int n, int c, int d, int h, int wd, int terms, void* stream) {
+  PCCGEO_REQUIRE(x && xb && n > 0 && c > 0 && d > 0 && h > 0 && wd > 0 && (terms == 1 || terms == 2), "f32_to_blocked: bad argument");
+  const int CG = round_up_i(c, 16) / 8;
+  const long long DHW = (long long)d * h * wd, total = (long long)n * CG * DHW;
+  long long b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  f32_to_blocked_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xb, n, c, CG, DHW, terms);
+  return check_launch("f32_to_blocked_kernel");
+}
+
+extern "C" int pccgeo_blocked_to_f32(const void* xb, float* x, int n, int c, int d, int h, int wd, int terms, void* stream) {
+  PCCGEO_REQUIRE(x && xb && n > 0 && c > 0 && d > 0 && h > 0 && wd > 0 && (terms == 1 || terms == 2), "blocked_to_f32: bad argument");
+  const int CG = round_up_i(c, 16) / 8;
+  const long long DHW = (long long)d * h * wd, total = (long long)n * CG * DHW;
+  long long b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  blocked_to_f32_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xb, x, n, c, CG, DHW, terms);
+  return check_launch("blocked_to_f32_kernel");
+}
+
+// B image, per precision term: [kyx (9)][kc (Cin_p/16)][kcore (2)][ngroup (3*Cout_p/8)][8 n][8 k] bf16, where
+// n = j*Cout_p + co stacks the three z-taps (j=0: kz=2, j=1: kz=1, j=2: kz=0) and k = channel kc*16 + kcore*8 + ki.
+extern "C" long long pccgeo_umma_pack_weights_host(const float* w, void* out, int cin, int cout, int stride, int transposed,
+                                                   int terms) {
+  if (cin <= 0 || cout <= 0 || (terms != 1 && terms != 2)) { set_error("umma_pack_weights: bad argument"); return PCCGEO_EINVAL; }
+  if (stride != 1) { set_error("umma_pack_weights: stride %d not supported by the tensor-core path yet", stride); return PCCGEO_EINVAL; }
+  const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16), KC = cip / 16;
+  const long long per_term = 9LL * KC * 2 * (3 * cop / 8) * 64 * 2;
+  if (!out) return per_term * terms;
+  if (!w) { set_error("umma_pack_weights: null weights"); return PCCGEO_EINVAL; }
+  uint16_t* o = (uint16_t*)out;
+  memset(o, 0, (size_t)per_term * terms);
+  for (int kyx = 0; kyx < 9; ++kyx)
+    for (int kc = 0; kc < KC; ++kc)
+      for (int j = 0; j < 3; ++j)
+        for (int co = 0; co < cout; ++co)
+          for (int kk = 0; kk < 16; ++kk) {
+            const int ci = kc * 16 + kk;
+            if (ci >= cin) continue;
+            int kz = 2 - j, ky = kyx / 3, kx = kyx % 3;
+            if (transposed) { kz = 2 - kz; ky = 2 - ky; kx = 2 - kx; }  // stride-1 transposed conv == conv with flipped taps
+            const float val = w[((long long)((kz * 3 + ky) * 3 + kx) * cin + ci) * cout + co];
+            const int nrow = j * cop + co, kcore = kk >> 3, ki = kk & 7;
+            const long long idx = ((((long long)(kyx * KC + kc) * 2 + kcore) * (3 * cop / 8) + (nrow >> 3)) * 8 + (nrow & 7)) * 8 + ki;
+            const uint16_t hi = f32_to_bf16_rn_host(val);
+            o[idx] = hi;
+            if (terms == 2) o[per_term / 2 + idx] = f32_to_bf16_rn_host(val - bf16_to_f32_host(hi));
+          }
+  return per_term * terms;
+}
+
+extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
+                                  int n, int cin, int d, int h, int wd, int cout, int stride, int transposed, int relu,
+                                  int terms, void* stream) {
+  (void)transposed;  // taps are already flipped in the packed image
+  PCCGEO_REQUIRE(xb && wpacked && yb, "conv3d_umma: null pointer");
+  PCCGEO_REQUIRE(terms == 1 || terms == 2, "conv3d_umma: terms must be 1 or 2");
+  PCCGEO_REQUIRE(stride == 1, "conv3d_umma: stride %d not supported by the tensor-core path yet", stride);
+  PCCGEO_REQUIRE(n > 0 && d > 0 && h % TY == 0 && wd % TX == 0 && h > 0 && wd > 0, "conv3d_umma: H must be a multiple of 16 and W of 8 (got %dx%dx%d)", d, h, wd);
+  const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16);
+  PCCGEO_REQUIRE(cop == 16 || cop == 32 || cop == 64, "conv3d_umma: Cout %d unsupported", cout);
+  PCCGEO_REQUIRE(cip <= 64, "conv3d_umma: Cin %d unsupported", cin);
+  EncodeTiledFn enc = get_encode_fn();
+  PCCGEO_REQUIRE(enc, "conv3d_umma: cuTensorMapEncodeTiled unavailable");
+
+  UmmaConvParams p{};
+  p.bias = bias; p.res = (const __nv_bfloat16*)residual_b; p.y = (__nv_bfloat16*)yb; p.wimg = (const uint8_t*)wpacked;
+  p.N = n; p.D = d; p.H = h; p.W = wd; p.CGi = cip / 8; p.CGo = cop / 8; p.terms = terms; p.relu = relu; p.cout_real = cout;
+  p.ytiles = h / TY; p.xtiles = wd / TX; p.items = n * p.ytiles * p.xtiles;
+  p.wbytes_term = 9 * (cip / 16) * 2 * (3 * cop / 8) * 128;
+  p.swap = g_opt_swap_lbo_sbo;
+  p.term_stride_out = (long long)n * cop * d * h * wd;
+  // TMEM ring: up to 256 columns (leaves room for a second CTA per SM), power of two, >= 4 planes
+  p.nslots = 256 / cop;
+  if (p.nslots > MAX_SLOTS) p.nslots = MAX_SLOTS;
+  const int stage_bytes = terms * p.CGi * PLANE_CG_BYTES;
+  const int wall = (p.wbytes_term * terms + 127) & ~127;
+  const int avail = 227 * 1024 - HEADER_BYTES - wall;
+  PCCGEO_REQUIRE(avail >= 3 * stage_bytes, "conv3d_umma: weights (%d B) leave no room for the input pipeline", wall);
+  p.nstage = avail / stage_bytes;
+  if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
+  const size_t smem = HEADER_BYTES + wall + (size_t)p.nstage * stage_bytes;
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)terms * n * p.CGi};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)wd * 16, (cuuint64_t)wd * h * 16, (cuuint64_t)wd * h * d * 16};
+  const cuuint32_t box[5] = {8, PX, PY, 1, (cuuint32_t)p.CGi};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xb), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PCCGEO_REQUIRE(cr == CUDA_SUCCESS, "conv3d_umma: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+  int grid = p.items < 148 ? p.items : 148;
+  if (g_opt_max_ctas > 0 && grid > g_opt_max_ctas) grid = g_opt_max_ctas;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cop == 16) return launch_umma<16>(tmap, p, smem, grid, st);
+  if (cop == 32) return launch_umma<32>(tmap, p, smem, grid, st);
+  return launch_umma<64>(tmap, p, smem, grid, st);
+}

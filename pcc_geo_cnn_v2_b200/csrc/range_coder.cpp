@@ -1,0 +1,325 @@
+// Host range coder: the symbol-level contract of tensorflow-compression 1.3's
+// unbounded_index_range_encode/_decode (precision 16, overflow_width 4; reference call sites
+// src/utils/patch_gaussian_conditional.py:27-31 and the .compress/.decompress methods used at
+// src/model_types.py:291-292,382-387,404-407) over this project's own 32-bit carry-propagating range coder.
+// Byte format: DESIGN.md "Bitstream".  Independent streams (one per block and per latent) are spread over
+// worker threads; there is no shared state between streams.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <queue>
+#include <thread>
+#include <vector>
+
+#include "../../include/pccgeo.h"
+
+namespace pccgeo {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+constexpr uint32_t kTop = 1u << 24;
+
+struct Encoder {
+  uint64_t low = 0;
+  uint32_t range = 0xFFFFFFFFu;
+  uint8_t cache = 0;
+  uint64_t cache_size = 1;
+  std::vector<uint8_t> out;
+
+  void shift_low() {
+    if ((uint32_t)low < 0xFF000000u || (low >> 32) != 0) {
+      const uint8_t carry = (uint8_t)(low >> 32);
+      uint8_t temp = cache;
+      do {
+        out.push_back((uint8_t)(temp + carry));
+        temp = 0xFF;
+      } while (--cache_size != 0);
+      cache = (uint8_t)(low >> 24);
+    }
+    ++cache_size;
+    low = (low & 0x00FFFFFFull) << 8;
+  }
+  inline void encode(uint32_t lower, uint32_t upper, int precision) {
+    const uint32_t r = range >> precision;
+    low += (uint64_t)r * lower;
+    range = r * (upper - lower);
+    while (range < kTop) {
+      shift_low();
+      range <<= 8;
+    }
+  }
+  void finish() {
+    const uint64_t hi = low + range - 1;
+    for (int nbits = 32; nbits >= 0; --nbits) {
+      const uint64_t mask = (1ull << nbits) - 1;
+      const uint64_t v = (low + mask) & ~mask;
+      if (v <= hi) {
+        low = v;
+        break;
+      }
+    }
+    for (int i = 0; i < 5; ++i) shift_low();
+    out.erase(out.begin());  // the first byte is always 0
+    while (!out.empty() && out.back() == 0) out.pop_back();
+  }
+};
+
+struct Decoder {
+  const uint8_t* p;
+  const uint8_t* end;
+  uint32_t range = 0xFFFFFFFFu;
+  uint32_t code = 0;
+  Decoder(const uint8_t* b, const uint8_t* e) : p(b), end(e) {
+    for (int i = 0; i < 4; ++i) code = (code << 8) | next();
+  }
+  inline uint32_t next() { return p < end ? *p++ : (++p, 0u); }
+  inline void normalize() {
+    while (range < kTop) {
+      code = (code << 8) | next();
+      range <<= 8;
+    }
+  }
+  inline int decode(const int32_t* cdf, int n, int precision) {
+    const uint32_t r = range >> precision;
+    uint32_t value = code / r;
+    const uint32_t maxv = (1u << precision) - 1;
+    if (value > maxv) value = maxv;
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((uint32_t)cdf[mid] <= value) lo = mid; else hi = mid;
+    }
+    code -= r * (uint32_t)cdf[lo];
+    range = r * (uint32_t)(cdf[lo + 1] - cdf[lo]);
+    normalize();
+    return lo;
+  }
+  inline uint32_t decode_uniform(int bits) {
+    const uint32_t r = range >> bits;
+    uint32_t s = code / r;
+    const uint32_t maxv = (1u << bits) - 1;
+    if (s > maxv) s = maxv;
+    code -= r * s;
+    range = r;
+    normalize();
+    return s;
+  }
+};
+
+constexpr int kPrecision = 16;
+constexpr int kOverflowWidth = 4;
+
+struct Tables {
+  const int32_t* cdf;
+  int cdf_stride;
+  const int32_t* cdf_length;
+  const int32_t* offset;
+  int rows;
+  int index_mode;
+  long long channel_stride;
+  inline int index(const int32_t* idx, long long pos) const {
+    return index_mode == 0 ? idx[pos] : (int)((pos / channel_stride) % rows);
+  }
+};
+
+bool encode_stream(const Tables& t, const int32_t* sym, const int32_t* idx, long long n, Encoder& enc) {
+  const uint32_t max_overflow = (1u << kOverflowWidth) - 1;
+  for (long long i = 0; i < n; ++i) {
+    const int row_i = t.index(idx, i);
+    if (row_i < 0 || row_i >= t.rows) return false;
+    const int32_t* row = t.cdf + (long long)row_i * t.cdf_stride;
+    const int32_t max_value = t.cdf_length[row_i] - 2;
+    long long value = (long long)sym[i] - t.offset[row_i];
+    uint64_t overflow = 0;
+    if (value < 0) {
+      overflow = (uint64_t)(-2 * value - 1);
+      value = max_value;
+    } else if (value >= max_value) {
+      overflow = (uint64_t)(2 * (value - max_value));
+      value = max_value;
+    }
+    enc.encode((uint32_t)row[value], (uint32_t)row[value + 1], kPrecision);
+    if (value == max_value) {
+      int widths = 0;
+      while ((overflow >> (widths * kOverflowWidth)) != 0) ++widths;
+      uint32_t val = (uint32_t)widths;
+      while (val >= max_overflow) {
+        enc.encode(max_overflow, max_overflow + 1, kOverflowWidth);
+        val -= max_overflow;
+      }
+      enc.encode(val, val + 1, kOverflowWidth);
+      for (int j = 0; j < widths; ++j) {
+        val = (uint32_t)((overflow >> (j * kOverflowWidth)) & max_overflow);
+        enc.encode(val, val + 1, kOverflowWidth);
+      }
+    }
+  }
+  enc.finish();
+  return true;
+}
+
+bool decode_stream(const Tables& t, const uint8_t* b, const uint8_t* e, const int32_t* idx, long long n, int32_t* out) {
+  Decoder dec(b, e);
+  const uint32_t max_overflow = (1u << kOverflowWidth) - 1;
+  for (long long i = 0; i < n; ++i) {
+    const int row_i = t.index(idx, i);
+    if (row_i < 0 || row_i >= t.rows) return false;
+    const int32_t* row = t.cdf + (long long)row_i * t.cdf_stride;
+    const int32_t max_value = t.cdf_length[row_i] - 2;
+    long long value = dec.decode(row, max_value + 1, kPrecision);
+    if (value == max_value) {
+      int widths = 0;
+      for (;;) {
+        const uint32_t v = dec.decode_uniform(kOverflowWidth);
+        widths += (int)v;
+        if (v != max_overflow) break;
+        if (widths > 64) return false;
+      }
+      if (widths > 16) return false;
+      uint64_t overflow = 0;
+      for (int j = 0; j < widths; ++j) overflow |= (uint64_t)dec.decode_uniform(kOverflowWidth) << (j * kOverflowWidth);
+      value = (long long)(overflow >> 1);
+      if (overflow & 1) value = -value - 1; else value += max_value;
+    }
+    out[i] = (int32_t)(value + t.offset[row_i]);
+  }
+  // a decoder that ran far past the end of its string was fed a truncated / corrupt stream
+  return dec.p <= dec.end + 8;
+}
+
+template <class F>
+void parallel_for(int n, int threads, F&& f) {
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  if (threads <= 1) {
+    for (int i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<int> next{0};
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&] {
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= n) break;
+        f(i);
+      }
+    });
+  for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" int pccgeo_range_encode_host(const int32_t* symbols, const int32_t* indexes, const long long* sym_offsets,
+                                        int nstreams, const int32_t* cdf, int cdf_stride, const int32_t* cdf_length,
+                                        const int32_t* offset, int rows, int index_mode, long long channel_stride,
+                                        uint8_t* out_bytes, long long out_capacity, long long* out_offsets, int threads) {
+  if (!symbols || !sym_offsets || !cdf || !cdf_length || !offset || !out_offsets || nstreams < 0 || rows <= 0 ||
+      (index_mode == 0 && !indexes) || (index_mode == 1 && channel_stride <= 0) || (index_mode != 0 && index_mode != 1)) {
+    pccgeo::set_error("range_encode: bad argument");
+    return PCCGEO_EINVAL;
+  }
+  Tables t{cdf, cdf_stride, cdf_length, offset, rows, index_mode, channel_stride};
+  std::vector<Encoder> encs(nstreams);
+  std::atomic<int> bad{0};
+  parallel_for(nstreams, threads, [&](int i) {
+    const long long a = sym_offsets[i], b = sym_offsets[i + 1];
+    encs[i].out.reserve((size_t)((b - a) / 4 + 16));
+    if (!encode_stream(t, symbols + a, index_mode == 0 ? indexes + a : nullptr, b - a, encs[i])) bad.store(1);
+  });
+  if (bad.load()) {
+    pccgeo::set_error("range_encode: table index out of range");
+    return PCCGEO_EINVAL;
+  }
+  long long pos = 0;
+  out_offsets[0] = 0;
+  for (int i = 0; i < nstreams; ++i) {
+    pos += (long long)encs[i].out.size();
+    out_offsets[i + 1] = pos;
+  }
+  if (!out_bytes || pos > out_capacity) {
+    pccgeo::set_error("range_encode: output needs %lld bytes, capacity %lld", pos, out_capacity);
+    return PCCGEO_ENOSPC;
+  }
+  for (int i = 0; i < nstreams; ++i)
+    if (!encs[i].out.empty()) std::memcpy(out_bytes + out_offsets[i], encs[i].out.data(), encs[i].out.size());
+  return PCCGEO_OK;
+}
+
+extern "C" int pccgeo_range_decode_host(const uint8_t* bytes, const long long* byte_offsets, const int32_t* indexes,
+                                        const long long* sym_offsets, int nstreams, const int32_t* cdf, int cdf_stride,
+                                        const int32_t* cdf_length, const int32_t* offset, int rows, int index_mode,
+                                        long long channel_stride, int32_t* symbols_out, int threads) {
+  if (!byte_offsets || !sym_offsets || !cdf || !cdf_length || !offset || !symbols_out || nstreams < 0 || rows <= 0 ||
+      (index_mode == 0 && !indexes) || (index_mode == 1 && channel_stride <= 0) || (index_mode != 0 && index_mode != 1)) {
+    pccgeo::set_error("range_decode: bad argument");
+    return PCCGEO_EINVAL;
+  }
+  static const uint8_t kEmpty = 0;
+  const uint8_t* base = bytes ? bytes : &kEmpty;
+  Tables t{cdf, cdf_stride, cdf_length, offset, rows, index_mode, channel_stride};
+  std::atomic<int> bad{0};
+  parallel_for(nstreams, threads, [&](int i) {
+    const long long a = sym_offsets[i], b = sym_offsets[i + 1];
+    if (!decode_stream(t, base + byte_offsets[i], base + byte_offsets[i + 1], index_mode == 0 ? indexes + a : nullptr,
+                       b - a, symbols_out + a))
+      bad.store(1);
+  });
+  if (bad.load()) {
+    pccgeo::set_error("range_decode: corrupt stream");
+    return PCCGEO_EDATA;
+  }
+  return PCCGEO_OK;
+}
+
+extern "C" int pccgeo_pmf_to_quantized_cdf_host(const double* pmf, int len, int precision, int32_t* cdf) {
+  if (!pmf || !cdf || len <= 0 || precision < 1 || precision > 24 || len > (1 << precision)) {
+    pccgeo::set_error("pmf_to_quantized_cdf: bad argument");
+    return PCCGEO_EINVAL;
+  }
+  const long long target = 1ll << precision;
+  std::vector<long long> v(len);
+  long long total = 0;
+  for (int i = 0; i < len; ++i) {
+    long long q = (long long)std::nearbyint(pmf[i] * (double)target);
+    v[i] = q < 1 ? 1 : q;
+    total += v[i];
+  }
+  typedef std::pair<double, int> Item;
+  std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+  if (total > target) {
+    for (int i = 0; i < len; ++i)
+      if (v[i] > 1) heap.push(Item(pmf[i] * (std::log2((double)v[i]) - std::log2((double)(v[i] - 1))), i));
+    while (total > target) {
+      if (heap.empty()) {
+        pccgeo::set_error("pmf_to_quantized_cdf: cannot repair the sum");
+        return PCCGEO_EINVAL;
+      }
+      const int i = heap.top().second;
+      heap.pop();
+      --v[i];
+      --total;
+      if (v[i] > 1) heap.push(Item(pmf[i] * (std::log2((double)v[i]) - std::log2((double)(v[i] - 1))), i));
+    }
+  } else if (total < target) {
+    for (int i = 0; i < len; ++i) heap.push(Item(-pmf[i] * (std::log2((double)(v[i] + 1)) - std::log2((double)v[i])), i));
+    while (total < target) {
+      const int i = heap.top().second;
+      heap.pop();
+      ++v[i];
+      ++total;
+      heap.push(Item(-pmf[i] * (std::log2((double)(v[i] + 1)) - std::log2((double)v[i])), i));
+    }
+  }
+  cdf[0] = 0;
+  long long acc = 0;
+  for (int i = 0; i < len; ++i) {
+    acc += v[i];
+    cdf[i + 1] = (int32_t)acc;
+  }
+  return PCCGEO_OK;
+}

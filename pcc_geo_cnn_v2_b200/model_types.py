@@ -1,0 +1,321 @@
+"""Host mirror of the reference's model graphs (src/model_types.py:179-416): CompressionModelV1 (factorized
+prior) and CompressionModelV2 (scale hyperprior) with the same builder methods and block loops
+
+    m.compress(x_shape); m.compress_blocks(sess, blocks, binstr, points, resolution, level, ...)
+    m.decompress();      m.decompress_blocks(sess, blocks, x_shape, debug=False)
+    m.train(x, gamma, alpha, lmbda)  -> m.train_loss / m.train_fl / m.train_mbpov (forward values)
+
+There is no TF session: `sess` is accepted and ignored.  Unlike the reference (one sess.run per block,
+model_types.py:192-198), blocks are processed in batches of `self.batch_size` on the GPU: densify ->
+analysis -> [hyper] -> quantise -> synthesis -> clip/threshold/bit-pack all run as libpccgeo CUDA kernels; only
+int32 symbols / indexes and packed occupancy bits cross PCIe; the range coder runs on host threads, one
+independent stream per block and latent.
+"""
+import logging
+from enum import Enum
+
+import numpy as np
+import torch
+
+from . import ops
+from .entropy_models import EntropyBottleneck, GaussianConditional, make_scale_table
+from .focal_loss import focal_loss
+from .model_transforms import TransformType
+
+logger = logging.getLogger(__name__)
+
+
+def sparse_to_dense(block, x_shape, data_format='channels_first'):
+    """src/model_types.py:108-114 on the GPU: (n,3) integer coords -> fp32 occupancy of shape x_shape."""
+    assert data_format == 'channels_first'
+    b = np.asarray(block)[:, :3].astype(np.int16)
+    coords = np.concatenate([np.zeros((len(b), 1), np.int16), b], axis=1)
+    return ops.densify(torch.from_numpy(np.ascontiguousarray(coords)).cuda(), 1, *[int(s) for s in x_shape[2:]])
+
+
+def blocks_to_coords(blocks):
+    """list of (n_i, >=3) arrays -> one int16 (sum n_i, 4) array of (block, z, y, x) rows."""
+    rows = []
+    for j, b in enumerate(blocks):
+        b = np.asarray(b)
+        c = np.empty((len(b), 4), np.int16)
+        c[:, 0] = j
+        c[:, 1:] = b[:, :3].astype(np.int16)
+        rows.append(c)
+    return np.ascontiguousarray(np.concatenate(rows, axis=0)) if rows else np.zeros((0, 4), np.int16)
+
+
+def bits_to_points(bits_host, shape):
+    """packed occupancy words (uint32 little-endian bit order) -> float32 (m,3) argwhere rows, C order."""
+    occ = np.unpackbits(bits_host.view(np.uint8), bitorder='little').reshape(shape)
+    return np.argwhere(occ).astype(np.float32)
+
+
+def threshold_f32(thresholds, idx):
+    """largest float32 <= the float64 threshold, so that (fp32 x > t32) == (x > t64) (model_types.py:209,233)."""
+    t64 = np.asarray(thresholds, np.float64)[idx]
+    t32 = t64.astype(np.float32)
+    t32 = np.where(t32.astype(np.float64) > t64, np.nextafter(t32, np.float32(-np.inf)), t32)
+    return t32.astype(np.float32)
+
+
+class CompressionModel:
+    def __init__(self, n_thresholds=2 ** 8, data_format='channels_first', batch_size=32):
+        self.thresholds = np.linspace(0, 1.0, n_thresholds)  # model_types.py:181
+        self.data_format = data_format
+        self.batch_size = batch_size
+        self.coder_threads = 0  # 0 = all host cores
+        self.x = self.x_hat = self.strings = self.debug_tensors = None
+        self.x_shape = None
+
+    # -- weights -------------------------------------------------------------------------------------
+    def transforms(self):
+        raise NotImplementedError
+
+    def get_weights(self):
+        """{'analysis': [...], 'synthesis': [...], ['hyper_*': ...], 'entropy_bottleneck': {...}} (Keras layouts)."""
+        w = {k: t.get_weights() for k, t in self.transforms().items()}
+        w['entropy_bottleneck'] = self.entropy_bottleneck.get_weights()
+        return w
+
+    def set_weights(self, w):
+        for k, t in self.transforms().items():
+            t.set_weights(w[k])
+        self.entropy_bottleneck.set_weights(w['entropy_bottleneck'])
+
+    # -- batched device passes (implemented by V1 / V2) ----------------------------------------------
+    def _encode_device(self, x):
+        raise NotImplementedError
+
+    def _encode_host(self, dev):
+        raise NotImplementedError
+
+    def _decode_batch(self, strings_list, x_shape):
+        raise NotImplementedError
+
+    # -- public block loops --------------------------------------------------------------------------
+    def encode_blocks(self, blocks, x_shape=None):
+        """Batched analysis + entropy coding + synthesis.  Returns (strings per block, x_hat fp32 CUDA (n,1,D,H,W))."""
+        dims = [int(s) for s in (x_shape if x_shape is not None else self.x_shape)][-3:]
+        strings, xhats = [], []
+        for i in range(0, len(blocks), self.batch_size):
+            chunk = blocks[i:i + self.batch_size]
+            coords = torch.from_numpy(blocks_to_coords(chunk)).cuda()
+            x = ops.densify(coords, len(chunk), *dims)
+            dev = self._encode_device(x)
+            strings += self._encode_host(dev)
+            xhats.append(dev['x_hat'])
+        return strings, (torch.cat(xhats) if len(xhats) > 1 else xhats[0])
+
+    def compress_blocks(self, sess, blocks, binstr, points, resolution, level, with_normals=False,
+                        opt_metrics=('d1_mse',), max_deltas=(np.inf,), fixed_threshold=False, debug=False):
+        """src/model_types.py:184-218.  Returns (data_list, metadata, debug_t_list)."""
+        assert self.x_shape is not None, 'call compress(x_shape) first'
+        strings_list, x_hat = self.encode_blocks(blocks)
+        n = len(blocks)
+        if fixed_threshold:
+            opt_metrics_ret = list(opt_metrics)
+            thr_idx = np.full((n, len(opt_metrics_ret)), len(self.thresholds) // 2, np.int64)  # model_opt.py:27-31
+        else:
+            thr_idx, opt_metrics_ret = self._optimal_thresholds(blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas)
+        x_hat_list = []
+        for m in range(thr_idx.shape[1]):
+            t = torch.from_numpy(threshold_f32(self.thresholds, thr_idx[:, m])).cuda()
+            bits, _ = ops.threshold_pack(x_hat, t)
+            bh = bits.cpu().numpy()
+            x_hat_list.append([bits_to_points(bh[j], tuple(x_hat.shape[2:])) for j in range(n)])
+        threshold_list = [tuple(int(v) for v in thr_idx[:, m]) for m in range(thr_idx.shape[1])]
+        metadata = self._select_best(binstr, x_hat_list, level, opt_metrics_ret, points, resolution, with_normals)
+        data_list = [list(zip(strings_list, threshold_list[x['idx']])) for x in metadata]
+        debug_t_list = [None] * n
+        return data_list, metadata, debug_t_list
+
+    def _optimal_thresholds(self, blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas):
+        """Per-block threshold search (reference src/model_opt.py:21-77) is host-side kd-tree work outside the hot
+        path ("next" #1): reuse the reference's own module when it is importable."""
+        try:
+            from model_opt import compute_optimal_thresholds  # the reference's src/ on sys.path
+        except ImportError as e:
+            raise NotImplementedError('adaptive thresholds need the reference host module model_opt.py on sys.path '
+                                      '(out of the hot path); pass fixed_threshold=True otherwise') from e
+        xh = torch.clamp(x_hat[:, 0], 0.0, 1.0).cpu().numpy()
+        idx, ret = [], None
+        for j, block in enumerate(blocks):
+            normals = block[:, block.shape[1] - 3:] if with_normals else None
+            ret, best = compute_optimal_thresholds(block, xh[j], self.thresholds, resolution, normals=normals,
+                                                   opt_metrics=opt_metrics, max_deltas=max_deltas, fixed_threshold=False)
+            idx.append(best)
+        return np.asarray(idx, np.int64), list(ret)
+
+    def _select_best(self, binstr, x_hat_list, level, opt_metrics, points, resolution, with_normals):
+        """select_best_per_opt_metric (model_types.py:128-176) needs the reference's octree + metric host modules;
+        without them the first opt_metric is selected and no metrics are reported."""
+        try:
+            from model_types import select_best_per_opt_metric  # noqa: the reference's own host code
+            return select_best_per_opt_metric(binstr, x_hat_list, level, opt_metrics, points, resolution, with_normals)
+        except Exception:
+            return [{'idx': 0, 'metrics': {}, 'x_hat_list': x_hat_list[0], 'blocks_depart': None, 'blocks_full': None}]
+
+    def decompress_blocks(self, sess, blocks, x_shape, debug=False):
+        """src/model_types.py:220-238: blocks = [(strings, threshold_idx)] -> ([float32 (m,3)], debug list)."""
+        dims = tuple(int(s) for s in x_shape)[-3:]
+        dec_blocks, debug_t_list = [], []
+        for i in range(0, len(blocks), self.batch_size):
+            chunk = blocks[i:i + self.batch_size]
+            strings = [c[0] for c in chunk]
+            idx = np.asarray([int(c[1]) for c in chunk], np.int64)
+            x_hat, dbg = self._decode_batch(strings, dims)
+            t = torch.from_numpy(threshold_f32(self.thresholds, idx)).cuda()
+            bits, _ = ops.threshold_pack(x_hat, t)
+            bh = bits.cpu().numpy()
+            dec_blocks += [bits_to_points(bh[j], dims) for j in range(len(chunk))]
+            debug_t_list += [dbg if debug else None] * len(chunk)
+        return dec_blocks, debug_t_list
+
+    # -- training graph (forward values; see DESIGN.md for the backward status) ----------------------
+    def _finish_train(self, x, x_tilde, log_sums, gamma, alpha, lmbda):
+        n_occ = x.sum(dtype=torch.float64)
+        denom = -np.log(2) * n_occ
+        mb = [s[0] / denom for s in log_sums]
+        self.train_mbpov = sum(mb[1:], mb[0])
+        self.train_fl = focal_loss(x, x_tilde, gamma=gamma, alpha=alpha)
+        self.train_loss = lmbda * self.train_fl + self.train_mbpov
+        self.num_occupied_voxels = n_occ
+        self.x_tilde = x_tilde
+        self.merged_summary = {'loss': self.train_loss, 'fl': self.train_fl, 'mbpov/total': self.train_mbpov,
+                               'num_occupied_voxels': n_occ}
+        self.step = getattr(self, 'step', 0)
+        self.train_op = None  # backward/optimizer: not part of this round (DESIGN.md "Out of scope / next")
+        return mb
+
+
+class CompressionModelV1(CompressionModel):
+    def __init__(self, num_filters=32, analysis_transform_type=TransformType.AnalysisTransformV1,
+                 synthesis_transform_type=TransformType.SynthesisTransformV1, *args, **kwargs):
+        self.num_filters = num_filters
+        self.analysis_transform_class = analysis_transform_type.value
+        self.synthesis_transform_class = synthesis_transform_type.value
+        super().__init__(*args, **kwargs)
+        self.analysis_transform = self.analysis_transform_class(num_filters, data_format=self.data_format)
+        self.synthesis_transform = self.synthesis_transform_class(num_filters, data_format=self.data_format)
+        self.entropy_bottleneck = EntropyBottleneck(data_format=self.data_format)
+        self.entropy_bottleneck.build(num_filters)
+
+    def transforms(self):
+        return {'analysis': self.analysis_transform, 'synthesis': self.synthesis_transform}
+
+    def train(self, x, gamma, alpha, lmbda, noise_y=None):  # model_types.py:250-281
+        y = self.analysis_transform(x)
+        y_tilde, _ = self.entropy_bottleneck(y, training=True, noise=noise_y)
+        x_tilde = self.synthesis_transform(y_tilde)
+        self._finish_train(x, x_tilde, [self.entropy_bottleneck.log_likelihood_sum(y_tilde)], gamma, alpha, lmbda)
+        self.y, self.y_tilde = y, y_tilde
+
+    def compress(self, x_shape):  # model_types.py:283-295
+        self.x_shape = tuple(int(s) for s in x_shape)
+
+    def decompress(self):  # model_types.py:297-309
+        pass
+
+    def _encode_device(self, x):
+        y = self.analysis_transform(x)
+        y_sym, y_hat = self.entropy_bottleneck.quantize(y)
+        x_hat = self.synthesis_transform(y_hat)
+        self.x, self.x_hat = x, x_hat
+        self.debug_tensors = {'y_hat': y_hat, 'x_hat': x_hat}
+        return {'y_sym': y_sym, 'y_hat': y_hat, 'x_hat': x_hat}
+
+    def _encode_host(self, dev):
+        ys = self.entropy_bottleneck.encode_symbols(dev['y_sym'].cpu().numpy(), self.coder_threads)
+        return [(s,) for s in ys]
+
+    def _decode_batch(self, strings_list, dims):
+        f = self.num_filters
+        shp = (f,) + tuple(d // 8 for d in dims)  # model_types.py:305
+        sym = self.entropy_bottleneck.decode_symbols([s[0] for s in strings_list], shp, self.coder_threads)
+        y_hat = ops.eb_dequantize(torch.from_numpy(sym).cuda(), self.entropy_bottleneck.device_params())
+        x_hat = self.synthesis_transform(y_hat)
+        self.x_hat = x_hat
+        return x_hat, {'y_hat': y_hat, 'x_hat': x_hat}
+
+
+class CompressionModelV2(CompressionModel):
+    def __init__(self, num_filters=32, analysis_transform_type=TransformType.AnalysisTransformV1,
+                 synthesis_transform_type=TransformType.SynthesisTransformV1,
+                 hyper_analysis_transform_type=TransformType.HyperAnalysisTransform,
+                 hyper_synthesis_transform_type=TransformType.HyperSynthesisTransform,
+                 scales_min=0.11, scales_max=256, scales_levels=64, *args, **kwargs):
+        self.num_filters = num_filters
+        self.analysis_transform_class = analysis_transform_type.value
+        self.synthesis_transform_class = synthesis_transform_type.value
+        self.hyper_analysis_transform_class = hyper_analysis_transform_type.value
+        self.hyper_synthesis_transform_class = hyper_synthesis_transform_type.value
+        self.scale_table = make_scale_table(scales_min, scales_max, scales_levels)  # model_types.py:324
+        super().__init__(*args, **kwargs)
+        df = self.data_format
+        self.analysis_transform = self.analysis_transform_class(num_filters, data_format=df)
+        self.synthesis_transform = self.synthesis_transform_class(num_filters, data_format=df)
+        self.hyper_analysis_transform = self.hyper_analysis_transform_class(num_filters, data_format=df)
+        self.hyper_synthesis_transform = self.hyper_synthesis_transform_class(num_filters, data_format=df)
+        self.entropy_bottleneck = EntropyBottleneck(data_format=df)
+        self.entropy_bottleneck.build(num_filters)
+
+    def transforms(self):
+        return {'analysis': self.analysis_transform, 'synthesis': self.synthesis_transform,
+                'hyper_analysis': self.hyper_analysis_transform, 'hyper_synthesis': self.hyper_synthesis_transform}
+
+    def train(self, x, gamma, alpha, lmbda, noise_y=None, noise_z=None):  # model_types.py:327-369
+        y = self.analysis_transform(x)
+        z = self.hyper_analysis_transform(y)
+        z_tilde, _ = self.entropy_bottleneck(z, training=True, noise=noise_z)
+        sigma_tilde = self.hyper_synthesis_transform(z_tilde)
+        cb = GaussianConditional(sigma_tilde, self.scale_table, data_format=self.data_format)
+        y_tilde, _ = cb(y, training=True, noise=noise_y)
+        x_tilde = self.synthesis_transform(y_tilde)
+        mb = self._finish_train(x, x_tilde, [cb.log_likelihood_sum(y_tilde), self.entropy_bottleneck.log_likelihood_sum(z_tilde)],
+                                gamma, alpha, lmbda)
+        self.train_mbpov_y, self.train_mbpov_z = mb
+        self.y, self.z, self.y_tilde, self.z_tilde, self.sigma_tilde = y, z, y_tilde, z_tilde, sigma_tilde
+
+    def compress(self, x_shape):  # model_types.py:371-391
+        self.x_shape = tuple(int(s) for s in x_shape)
+
+    def decompress(self):  # model_types.py:393-411
+        pass
+
+    def _encode_device(self, x):
+        y = self.analysis_transform(x)
+        z = self.hyper_analysis_transform(y)
+        z_sym, z_hat = self.entropy_bottleneck.quantize(z)
+        sigma_hat = self.hyper_synthesis_transform(z_hat)
+        cb = GaussianConditional(sigma_hat, self.scale_table, data_format=self.data_format)
+        y_sym, y_hat, idx = cb.quantize(y)
+        x_hat = self.synthesis_transform(y_hat)
+        self.x, self.x_hat = x, x_hat
+        self.debug_tensors = {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat}
+        return {'y': y, 'z': z, 'z_sym': z_sym, 'z_hat': z_hat, 'sigma_hat': sigma_hat, 'y_sym': y_sym, 'y_hat': y_hat,
+                'indexes': idx, 'x_hat': x_hat, 'cb': cb}
+
+    def _encode_host(self, dev):
+        zs = self.entropy_bottleneck.encode_symbols(dev['z_sym'].cpu().numpy(), self.coder_threads)
+        ys = dev['cb'].encode_symbols(dev['y_sym'].cpu().numpy(), dev['indexes'].cpu().numpy(), self.coder_threads)
+        return list(zip(ys, zs))  # (y_string, z_string): model_types.py:389
+
+    def _decode_batch(self, strings_list, dims):
+        f = self.num_filters
+        zshp = (f,) + tuple(d // 16 for d in dims)  # model_types.py:403
+        zsym = self.entropy_bottleneck.decode_symbols([s[1] for s in strings_list], zshp, self.coder_threads)
+        z_hat = ops.eb_dequantize(torch.from_numpy(zsym).cuda(), self.entropy_bottleneck.device_params())
+        sigma_hat = self.hyper_synthesis_transform(z_hat)
+        cb = GaussianConditional(sigma_hat, self.scale_table, data_format=self.data_format)
+        idx = cb.indexes()
+        ysym = cb.decode_symbols([s[0] for s in strings_list], idx.cpu().numpy(), self.coder_threads)
+        y_hat = ops.i32_to_f32(torch.from_numpy(ysym).cuda())
+        x_hat = self.synthesis_transform(y_hat)
+        self.x_hat = x_hat
+        return x_hat, {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat}
+
+
+class ModelType(Enum):
+    v1 = CompressionModelV1
+    v2 = CompressionModelV2

@@ -1,0 +1,254 @@
+"""Thin, allocation-explicit wrappers over the C ABI (include/pccgeo.h).  torch is used only for device
+memory and the current stream; every compute step is a libpccgeo kernel."""
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), 'expects a contiguous fp32 CUDA tensor'
+    return t
+
+
+def same_out(n, stride, transposed):
+    return n * stride if transposed else -(-n // stride)
+
+
+def conv3d_f32(x, w_tap, bias, cout, k, stride, transposed, relu, residual=None, out=None):
+    """Keras Conv3D / Conv3DTranspose ('same') + bias + ReLU + residual on fp32 (N,C,D,H,W).
+    w_tap: device fp32 (k^3, Cin, Cout)."""
+    L.require_cuda()
+    _f32c(x)
+    n, cin, d, h, w = x.shape
+    shp = (n, cout, same_out(d, stride, transposed), same_out(h, stride, transposed), same_out(w, stride, transposed))
+    if out is None:
+        out = torch.empty(shp, device=x.device, dtype=torch.float32)
+    assert tuple(out.shape) == shp and out.is_contiguous()
+    if residual is not None:
+        assert tuple(residual.shape) == shp
+        _f32c(residual)
+    L.check(L.lib().pccgeo_conv3d_f32(L.ptr(x), L.ptr(w_tap), L.ptr(bias), L.ptr(residual), L.ptr(out),
+                                      n, cin, d, h, w, cout, k, stride, int(transposed), int(relu), L.stream_ptr()),
+            'conv3d_f32')
+    return out
+
+
+# ---- blocked bf16 layout for the tcgen05 path ---------------------------------------------------------
+def round_up(a, m):
+    return -(-a // m) * m
+
+
+def blocked_numel(n, c, d, h, w, terms):
+    return terms * n * round_up(c, 16) * d * h * w
+
+
+def f32_to_blocked(x, terms, out=None):
+    L.require_cuda()
+    _f32c(x)
+    n, c, d, h, w = x.shape
+    if out is None:
+        out = torch.empty(blocked_numel(n, c, d, h, w, terms), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().pccgeo_f32_to_blocked(L.ptr(x), L.ptr(out), n, c, d, h, w, terms, L.stream_ptr()), 'f32_to_blocked')
+    return out
+
+
+def blocked_to_f32(xb, shape, terms, out=None):
+    L.require_cuda()
+    n, c, d, h, w = shape
+    if out is None:
+        out = torch.empty(shape, device=xb.device, dtype=torch.float32)
+    L.check(L.lib().pccgeo_blocked_to_f32(L.ptr(xb), L.ptr(out), n, c, d, h, w, terms, L.stream_ptr()), 'blocked_to_f32')
+    return out
+
+
+def umma_pack_weights(w_tap_host, cin, cout, stride, transposed, terms):
+    """numpy fp32 (27, Cin, Cout) -> device uint8 image for pccgeo_conv3d_umma."""
+    w = np.ascontiguousarray(w_tap_host, np.float32)
+    size = L.lib().pccgeo_umma_pack_weights_host(L.ptr(w), None, cin, cout, stride, int(transposed), terms)
+    if size <= 0:
+        L.check(int(size) if size < 0 else -1, 'umma_pack_weights')
+    img = np.zeros(size, np.uint8)
+    rc = L.lib().pccgeo_umma_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, stride, int(transposed), terms)
+    if rc < 0:
+        L.check(int(rc), 'umma_pack_weights')
+    return torch.from_numpy(img).cuda()
+
+
+def conv3d_umma(xb, in_shape, wpacked, bias, cout, stride, transposed, relu, terms, residual_b=None, out=None):
+    """Blocked-layout tensor-core conv.  in_shape = logical (N, Cin, D, H, W).  Returns (yb, out_shape)."""
+    L.require_cuda()
+    n, cin, d, h, w = in_shape
+    shp = (n, cout, same_out(d, stride, transposed), same_out(h, stride, transposed), same_out(w, stride, transposed))
+    if out is None:
+        out = torch.empty(blocked_numel(*shp, terms), device=xb.device, dtype=torch.bfloat16)
+    L.check(L.lib().pccgeo_conv3d_umma(L.ptr(xb), L.ptr(wpacked), L.ptr(bias), L.ptr(residual_b), L.ptr(out),
+                                       n, cin, d, h, w, cout, stride, int(transposed), int(relu), terms,
+                                       L.stream_ptr()), 'conv3d_umma')
+    return out, shp
+
+
+# ---- entropy models ------------------------------------------------------------------------------------
+_ws = {}
+
+
+def reduce_ws(device):
+    key = str(device)
+    if key not in _ws:
+        _ws[key] = torch.empty(int(L.lib().pccgeo_reduce_ws_doubles()), device=device, dtype=torch.float64)
+    return _ws[key]
+
+
+def eb_quantize(x, eb_params, want_symbols=True, want_xhat=True):
+    L.require_cuda()
+    _f32c(x)
+    n, c = x.shape[:2]
+    sp = x[0, 0].numel()
+    sym = torch.empty(x.shape, device=x.device, dtype=torch.int32) if want_symbols else None
+    xh = torch.empty_like(x) if want_xhat else None
+    L.check(L.lib().pccgeo_eb_quantize(L.ptr(x), L.ptr(eb_params), L.ptr(sym), L.ptr(xh), n, c, sp, L.stream_ptr()), 'eb_quantize')
+    return sym, xh
+
+
+def eb_dequantize(sym, eb_params):
+    L.require_cuda()
+    assert sym.is_cuda and sym.dtype == torch.int32 and sym.is_contiguous()
+    n, c = sym.shape[:2]
+    sp = sym[0, 0].numel()
+    out = torch.empty(sym.shape, device=sym.device, dtype=torch.float32)
+    L.check(L.lib().pccgeo_eb_dequantize(L.ptr(sym), L.ptr(eb_params), L.ptr(out), n, c, sp, L.stream_ptr()), 'eb_dequantize')
+    return out
+
+
+def eb_likelihood(values, eb_params, want_likelihood=True, want_sum=True):
+    L.require_cuda()
+    _f32c(values)
+    n, c = values.shape[:2]
+    sp = values[0, 0].numel()
+    lik = torch.empty_like(values) if want_likelihood else None
+    s = torch.empty(1, device=values.device, dtype=torch.float64) if want_sum else None
+    L.check(L.lib().pccgeo_eb_likelihood(L.ptr(values), L.ptr(eb_params), L.ptr(lik), L.ptr(s), L.ptr(reduce_ws(values.device)),
+                                         n, c, sp, L.stream_ptr()), 'eb_likelihood')
+    return lik, s
+
+
+def gc_quantize(y, sigma, scale_table, want_symbols=True, want_yhat=True, want_indexes=True):
+    L.require_cuda()
+    ref = y if y is not None else sigma
+    _f32c(ref)
+    sym = torch.empty(ref.shape, device=ref.device, dtype=torch.int32) if (want_symbols and y is not None) else None
+    yh = torch.empty(ref.shape, device=ref.device, dtype=torch.float32) if (want_yhat and y is not None) else None
+    idx = torch.empty(ref.shape, device=ref.device, dtype=torch.int32) if want_indexes else None
+    L.check(L.lib().pccgeo_gc_quantize(L.ptr(y), L.ptr(sigma), L.ptr(scale_table), int(scale_table.numel()),
+                                       L.ptr(sym), L.ptr(yh), L.ptr(idx), ref.numel(), L.stream_ptr()), 'gc_quantize')
+    return sym, yh, idx
+
+
+def gc_likelihood(values, sigma, scale_min, want_likelihood=True, want_sum=True):
+    L.require_cuda()
+    _f32c(values)
+    _f32c(sigma)
+    lik = torch.empty_like(values) if want_likelihood else None
+    s = torch.empty(1, device=values.device, dtype=torch.float64) if want_sum else None
+    L.check(L.lib().pccgeo_gc_likelihood(L.ptr(values), L.ptr(sigma), float(scale_min), L.ptr(lik), L.ptr(s),
+                                         L.ptr(reduce_ws(values.device)), values.numel(), L.stream_ptr()), 'gc_likelihood')
+    return lik, s
+
+
+def i32_to_f32(sym):
+    L.require_cuda()
+    out = torch.empty(sym.shape, device=sym.device, dtype=torch.float32)
+    L.check(L.lib().pccgeo_i32_to_f32(L.ptr(sym), L.ptr(out), sym.numel(), L.stream_ptr()), 'i32_to_f32')
+    return out
+
+
+# ---- voxel helpers -------------------------------------------------------------------------------------
+def densify(coords_i16, n, d, h, w, out=None):
+    """coords_i16: CUDA int16 (npts, 4) rows (block, z, y, x) -> fp32 (n,1,d,h,w) occupancy."""
+    L.require_cuda()
+    if out is None:
+        out = torch.zeros((n, 1, d, h, w), device='cuda', dtype=torch.float32)
+    else:
+        out.zero_()
+    npts = 0 if coords_i16 is None else coords_i16.shape[0]
+    if npts:
+        assert coords_i16.is_cuda and coords_i16.dtype == torch.int16 and coords_i16.is_contiguous()
+    L.check(L.lib().pccgeo_densify(L.ptr(coords_i16) if npts else None, npts, L.ptr(out), n, d, h, w, L.stream_ptr()), 'densify')
+    return out
+
+
+def threshold_pack(x_hat, thresholds):
+    """x_hat fp32 (n,1,d,h,w), thresholds fp32 (n,) -> (bits uint32 as int32 tensor (n, vox/32), counts int32 (n,))."""
+    L.require_cuda()
+    _f32c(x_hat)
+    n = x_hat.shape[0]
+    vpb = x_hat[0].numel()
+    bits = torch.empty((n, vpb // 32), device=x_hat.device, dtype=torch.int32)
+    counts = torch.empty(n, device=x_hat.device, dtype=torch.int32)
+    L.check(L.lib().pccgeo_threshold_pack(L.ptr(x_hat), L.ptr(thresholds), L.ptr(bits), L.ptr(counts), n, vpb, L.stream_ptr()),
+            'threshold_pack')
+    return bits, counts
+
+
+def focal_loss_sum(x_true, x_pred, gamma, alpha):
+    L.require_cuda()
+    _f32c(x_true)
+    _f32c(x_pred)
+    out = torch.empty(1, device=x_true.device, dtype=torch.float64)
+    L.check(L.lib().pccgeo_focal_loss(L.ptr(x_true), L.ptr(x_pred), float(gamma), float(alpha), L.ptr(out),
+                                      L.ptr(reduce_ws(x_true.device)), x_true.numel(), L.stream_ptr()), 'focal_loss')
+    return out
+
+
+# ---- host range coder ------------------------------------------------------------------------------------
+def range_encode(symbols, sym_offsets, tables, indexes=None, channel_stride=0, threads=0):
+    """symbols int32 (host numpy, concatenated streams); returns list of bytes, one per stream."""
+    import os
+    symbols = np.ascontiguousarray(symbols, np.int32)
+    offs = np.ascontiguousarray(sym_offsets, np.int64)
+    ns = len(offs) - 1
+    cdf = np.ascontiguousarray(tables['cdf'], np.int32)
+    cl = np.ascontiguousarray(tables['cdf_length'], np.int32)
+    of = np.ascontiguousarray(tables['offset'], np.int32)
+    mode = 0 if indexes is not None else 1
+    if indexes is not None:
+        indexes = np.ascontiguousarray(indexes, np.int32)
+    cap = int(symbols.size) * 4 + 64 * ns + 64
+    out = np.empty(cap, np.uint8)
+    out_offs = np.zeros(ns + 1, np.int64)
+    threads = threads or min(ns, os.cpu_count() or 1) or 1
+    L.check(L.lib().pccgeo_range_encode_host(L.ptr(symbols), L.ptr(indexes), L.ptr(offs), ns, L.ptr(cdf), cdf.shape[1],
+                                             L.ptr(cl), L.ptr(of), cdf.shape[0], mode, int(channel_stride),
+                                             L.ptr(out), cap, L.ptr(out_offs), threads), 'range_encode')
+    buf = out.tobytes()
+    return [buf[out_offs[i]:out_offs[i + 1]] for i in range(ns)]
+
+
+def range_decode(strings, sym_offsets, tables, indexes=None, channel_stride=0, threads=0):
+    """strings: list of bytes; returns int32 numpy of the concatenated symbols."""
+    import os
+    offs = np.ascontiguousarray(sym_offsets, np.int64)
+    ns = len(offs) - 1
+    assert len(strings) == ns
+    boffs = np.zeros(ns + 1, np.int64)
+    boffs[1:] = np.cumsum([len(s) for s in strings])
+    blob = np.frombuffer(b''.join(strings) + b'\x00', np.uint8)
+    cdf = np.ascontiguousarray(tables['cdf'], np.int32)
+    cl = np.ascontiguousarray(tables['cdf_length'], np.int32)
+    of = np.ascontiguousarray(tables['offset'], np.int32)
+    mode = 0 if indexes is not None else 1
+    if indexes is not None:
+        indexes = np.ascontiguousarray(indexes, np.int32)
+    out = np.empty(int(offs[-1]), np.int32)
+    threads = threads or min(ns, os.cpu_count() or 1) or 1
+    L.check(L.lib().pccgeo_range_decode_host(L.ptr(blob), L.ptr(boffs), L.ptr(indexes), L.ptr(offs), ns, L.ptr(cdf),
+                                             cdf.shape[1], L.ptr(cl), L.ptr(of), cdf.shape[0], mode, int(channel_stride),
+                                             L.ptr(out), threads), 'range_decode')
+    return out
+
+
+def pmf_to_quantized_cdf(pmf, precision=16):
+    pmf = np.ascontiguousarray(pmf, np.float64)
+    cdf = np.zeros(len(pmf) + 1, np.int32)
+    L.check(L.lib().pccgeo_pmf_to_quantized_cdf_host(L.ptr(pmf), len(pmf), precision, L.ptr(cdf)), 'pmf_to_quantized_cdf')
+    return cdf

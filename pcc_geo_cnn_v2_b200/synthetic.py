@@ -1,0 +1,67 @@
+"""Seeded synthetic inputs and "trained-like" synthetic parameters (no datasets / checkpoints are available
+offline).  Used by bench.py, the tests and __graft_entry__.smoke().
+
+Keras-default initialisation (Glorot-uniform, zero bias) drives sparse occupancy inputs to all-zero latents,
+which exercises nothing; `trained_like_weights` rescales the same Glorot draws (gain 2.0, synthesis 1.7) and adds
+small biases so latents spread over roughly +-20 (z overflows the factorized prior's table -> escape codes),
+scale indexes cover most of the table and x_hat straddles the thresholds."""
+import math
+
+import numpy as np
+
+
+def surface_blocks(n_blocks, size=64, seed=42):
+    """Voxelised random surfaces (sphere shells and planes), ~2-3 % occupancy like the ModelNet40 blocks the
+    reference trains on.  Returns a list of float32 (n_i, 3) arrays of unique coords."""
+    rng = np.random.default_rng(seed)
+    g = np.indices((size, size, size)).astype(np.float32)
+    out = []
+    for _ in range(n_blocks):
+        occ = np.zeros((size, size, size), bool)
+        for _ in range(int(rng.integers(1, 3))):
+            if rng.random() < 0.5:
+                c = rng.uniform(0.2 * size, 0.8 * size, 3).astype(np.float32)
+                r = rng.uniform(0.2 * size, 0.45 * size)
+                d = np.sqrt(((g - c[:, None, None, None]) ** 2).sum(0))
+                occ |= np.abs(d - r) < 0.6
+            else:
+                nrm = rng.normal(size=3).astype(np.float32)
+                nrm /= np.linalg.norm(nrm)
+                off = rng.uniform(0.3 * size, 0.7 * size)
+                occ |= np.abs(np.tensordot(nrm, g - size / 2, axes=(0, 0)) + size / 2 - off) < 0.5
+        pts = np.argwhere(occ).astype(np.float32)
+        if len(pts) == 0:
+            pts = np.array([[size // 2] * 3], np.float32)
+        out.append(pts)
+    return out
+
+
+def trained_like_weights(model, seed=42, gain=2.0, synthesis_gain=1.7, bias_scale=0.05):
+    """Deterministic parameter set for a pcc_geo_cnn_v2_b200 model (dict accepted by model.set_weights)."""
+    rng = np.random.default_rng(seed)
+    f = model.num_filters
+    in_ch = {'analysis': 1, 'synthesis': f, 'hyper_analysis': f, 'hyper_synthesis': f}
+    w = {}
+    for name, tf in model.transforms().items():
+        c = in_ch[name]
+        g = synthesis_gain if name == 'synthesis' else gain
+        layers = []
+        for layer in tf.leaf_layers():
+            k, fo = layer.k, layer.filters
+            limit = g * math.sqrt(6.0 / (k ** 3 * (c + fo)))
+            shape = (k, k, k, fo, c) if layer.transposed else (k, k, k, c, fo)
+            kern = rng.uniform(-limit, limit, size=shape).astype(np.float32)
+            bias = rng.uniform(-bias_scale, bias_scale, size=(fo,)).astype(np.float32) if layer.use_bias else None
+            layers.append({'kernel': kern, 'bias': bias})
+            c = fo
+        w[name] = layers
+    eb = model.entropy_bottleneck
+    eb.build(f)
+    ew = eb.get_weights()
+    ew = {'matrices': [m.copy() for m in ew['matrices']],
+          'biases': [rng.uniform(-0.5, 0.5, size=b.shape).astype(np.float32) for b in ew['biases']],
+          'factors': [rng.uniform(-0.2, 0.2, size=t.shape).astype(np.float32) for t in ew['factors']],
+          'quantiles': ew['quantiles'].copy()}
+    ew['quantiles'][:, 0, 1] = rng.uniform(-0.4, 0.4, size=f).astype(np.float32)  # non-trivial medians
+    w['entropy_bottleneck'] = ew
+    return w
