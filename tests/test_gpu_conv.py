@@ -1,0 +1,111 @@
+"""Parity of the convolution kernels with the oracle (torch-CPU restatement of Keras Conv3D/Conv3DTranspose
+'same'), through the C ABI.  fp32 CUDA-core kernel: abs/rel 1e-5 of the output scale.  tcgen05 kernel: bf16x3
+mode within 3e-5 of the output scale (fp32-class), bf16 mode within 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import transforms as T
+from pcc_geo_cnn_v2_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(rng, transposed, k, s, cin, cout, shape, n=2):
+    x = torch.from_numpy(rng.normal(size=(n, cin) + shape).astype(np.float32))
+    x = x * (torch.rand_like(x) < 0.5)  # sparse-ish, like post-ReLU activations
+    kshape = (k, k, k, cout, cin) if transposed else (k, k, k, cin, cout)
+    kern = torch.from_numpy((rng.normal(size=kshape) / np.sqrt(k ** 3 * cin)).astype(np.float32))
+    bias = torch.from_numpy(rng.normal(size=(cout,)).astype(np.float32) * 0.1)
+    return x, kern, bias
+
+
+def _tap_major(kern, transposed):
+    k = kern.shape[0]
+    w = kern.permute(0, 1, 2, 4, 3) if transposed else kern
+    return w.reshape(k ** 3, w.shape[3], w.shape[4]).contiguous()
+
+
+def _oracle(x, kern, bias, s, relu, transposed, res=None):
+    fn = T.conv3d_transpose_same if transposed else T.conv3d_same
+    y = fn(x.double(), kern.double(), None if bias is None else bias.double(), s, relu)
+    return y if res is None else y + res.double()
+
+
+CASES = [
+    # transposed, k, stride, cin, cout, spatial
+    (False, 3, 1, 16, 16, (8, 8, 8)), (False, 3, 2, 1, 16, (16, 16, 16)), (False, 3, 2, 16, 32, (8, 8, 8)),
+    (False, 3, 1, 64, 64, (4, 4, 4)), (False, 9, 2, 1, 32, (16, 16, 16)), (False, 5, 2, 32, 32, (8, 8, 8)),
+    (False, 3, 2, 4, 6, (7, 7, 7)), (False, 3, 1, 3, 5, (1, 1, 1)),
+    (True, 3, 1, 16, 16, (8, 8, 8)), (True, 3, 2, 64, 32, (4, 4, 4)), (True, 3, 1, 16, 1, (16, 16, 16)),
+    (True, 5, 2, 32, 32, (4, 4, 4)), (True, 9, 2, 32, 1, (8, 8, 8)), (True, 3, 2, 5, 3, (3, 3, 3)), (True, 9, 2, 2, 2, (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize('transposed,k,s,cin,cout,shape', CASES)
+def test_direct_conv_matches_oracle(transposed, k, s, cin, cout, shape):
+    rng = np.random.default_rng(hash((transposed, k, s, cin, cout)) % 2 ** 31)
+    x, kern, bias = _case(rng, transposed, k, s, cin, cout, shape)
+    want = _oracle(x, kern, bias, s, True, transposed)
+    got = ops.conv3d_f32(x.cuda(), _tap_major(kern, transposed).cuda(), bias.cuda(), cout, k, s, transposed, True)
+    assert tuple(got.shape) == tuple(want.shape)
+    scale = float(want.abs().max()) + 1e-6
+    assert float((got.cpu().double() - want).abs().max()) < 1e-5 * scale
+    # no bias, no relu, residual
+    res = torch.from_numpy(rng.normal(size=tuple(want.shape)).astype(np.float32))
+    want2 = _oracle(x, kern, None, s, False, transposed, res)
+    got2 = ops.conv3d_f32(x.cuda(), _tap_major(kern, transposed).cuda(), None, cout, k, s, transposed, False, res.cuda())
+    assert float((got2.cpu().double() - want2).abs().max()) < 1e-5 * (float(want2.abs().max()) + 1e-6)
+
+
+def test_blocked_layout_round_trip():
+    x = torch.randn(3, 20, 4, 16, 8, device='cuda')
+    for terms, tol in ((2, 2e-5), (1, 1e-2)):
+        xb = ops.f32_to_blocked(x, terms)
+        assert xb.numel() == terms * 3 * 32 * 4 * 16 * 8
+        back = ops.blocked_to_f32(xb, tuple(x.shape), terms)
+        assert float((back - x).abs().max()) <= tol * float(x.abs().max())
+
+
+UMMA_CASES = [
+    # transposed, cin, cout, (D,H,W), n
+    (False, 16, 16, (4, 16, 8), 1), (False, 16, 16, (16, 16, 16), 2), (True, 16, 16, (8, 32, 16), 1),
+    (False, 32, 32, (16, 16, 16), 2), (True, 32, 32, (5, 16, 8), 3), (False, 16, 32, (3, 16, 8), 1),
+    (True, 32, 16, (20, 16, 24), 1), (False, 16, 16, (1, 16, 8), 1), (False, 16, 16, (40, 32, 32), 5),
+]
+
+
+@pytest.mark.parametrize('terms,tol', [(2, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize('transposed,cin,cout,shape,n', UMMA_CASES)
+def test_umma_conv_matches_oracle(transposed, cin, cout, shape, n, terms, tol):
+    rng = np.random.default_rng(hash((transposed, cin, cout, shape, n)) % 2 ** 31)
+    x, kern, bias = _case(rng, transposed, 3, 1, cin, cout, shape, n)
+    res = torch.from_numpy(rng.normal(size=(n, cout) + shape).astype(np.float32))
+    want = _oracle(x, kern, bias, 1, True, transposed, res)
+    wp = ops.umma_pack_weights(_tap_major(kern, transposed).numpy(), cin, cout, 1, transposed, terms)
+    xb = ops.f32_to_blocked(x.cuda(), terms)
+    rb = ops.f32_to_blocked(res.cuda(), terms)
+    yb, shp = ops.conv3d_umma(xb, tuple(x.shape), wp, bias.cuda(), cout, 1, transposed, True, terms, rb)
+    got = ops.blocked_to_f32(yb, shp, terms)
+    torch.cuda.synchronize()
+    assert shp == tuple(want.shape)
+    err = float((got.cpu().double() - want).abs().max())
+    scale = float(want.abs().max())
+    assert err < tol * scale, f'max err {err:.3e} vs scale {scale:.3e}'
+
+
+@pytest.mark.parametrize('terms', [2, 1])
+def test_umma_full_size_layer_matches_fp32_kernel(terms):
+    """BASELINE-size check (64^3, 16->16, batch 4): tensor-core kernel against the fp32 CUDA-core kernel."""
+    rng = np.random.default_rng(11)
+    x, kern, bias = _case(rng, True, 3, 1, 16, 16, (64, 64, 64), 4)
+    xd = x.cuda()
+    ref = ops.conv3d_f32(xd, _tap_major(kern, True).cuda(), bias.cuda(), 16, 3, 1, True, True)
+    wp = ops.umma_pack_weights(_tap_major(kern, True).numpy(), 16, 16, 1, True, terms)
+    yb, shp = ops.conv3d_umma(ops.f32_to_blocked(xd, terms), tuple(x.shape), wp, bias.cuda(), 16, 1, True, True, terms)
+    got = ops.blocked_to_f32(yb, shp, terms)
+    err = float((got - ref).abs().max())
+    assert err < (3e-5 if terms == 2 else 2e-2) * float(ref.abs().max())
+    # deterministic: same launch twice -> identical bits
+    yb2, _ = ops.conv3d_umma(ops.f32_to_blocked(xd, terms), tuple(x.shape), wp, bias.cuda(), 16, 1, True, True, terms)
+    assert torch.equal(yb, yb2)

@@ -1,0 +1,154 @@
+"""End-to-end parity of the CUDA path with the oracle and the committed golden fixtures, through the reference's
+own call signatures (ModelConfigType[...].build(), compress_blocks / decompress_blocks, TransformType).
+
+Bars: int32 symbols / indexes / byte strings / decoded points are compared exactly; because analysis latents are
+*rounded*, a different fp32 summation order can legitimately flip a symbol that sits within ~1e-5 of a rounding
+boundary, so symbol comparisons allow a stated, tiny flip budget (and strings are compared only where the symbols
+agree).  Decoding the oracle's strings must reproduce the oracle's points except voxels the fixture marks fragile
+(|x_hat - t| < 1e-4)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.model import OracleModel
+from pcc_geo_cnn_v2_b200 import model_transforms as MT
+from pcc_geo_cnn_v2_b200 import synthetic
+from pcc_geo_cnn_v2_b200.model_configs import ModelConfigType
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _model(config, seed):
+    m = ModelConfigType[config].build()
+    m.set_weights(synthetic.trained_like_weights(m, seed=seed))
+    return m
+
+
+def _as_set(p):
+    return {tuple(int(v) for v in r) for r in np.asarray(p)}
+
+
+@pytest.fixture(autouse=True)
+def _default_precision():
+    MT.set_precision('bf16x3')
+    yield
+    MT.set_precision('bf16x3')
+
+
+# reference src/test_model_transforms.py:14-73, run against the CUDA implementation (channels_last like the original)
+@pytest.mark.parametrize('name,filters,inp,kw,expect', [
+    ('AnalysisTransformV1', 1, (1, 8, 8, 8, 1), {}, (1, 1, 1, 1, 1)),
+    ('SynthesisTransformV1', 2, (1, 1, 1, 1, 1), {}, (1, 8, 8, 8, 1)),
+    ('AnalysisTransformV2', 2, (1, 8, 8, 8, 1), {}, (1, 1, 1, 1, 2)),
+    ('AnalysisTransformV2', 2, (1, 8, 8, 8, 1), {'residual_mode': 'concat'}, (1, 1, 1, 1, 2)),
+    ('SynthesisTransformV2', 2, (1, 1, 1, 1, 1), {}, (1, 8, 8, 8, 1)),
+    ('SynthesisTransformV2', 2, (1, 1, 1, 1, 1), {'residual_mode': 'concat'}, (1, 8, 8, 8, 1)),
+    ('AnalysisTransformProgressiveV2', 4, (1, 8, 8, 8, 1), {}, (1, 1, 1, 1, 4)),
+    ('SynthesisTransformProgressiveV2', 4, (1, 1, 1, 1, 1), {}, (1, 8, 8, 8, 1)),
+    ('HyperAnalysisTransform', 1, (1, 8, 8, 8, 1), {}, (1, 4, 4, 4, 1)),
+    ('HyperSynthesisTransform', 1, (1, 1, 1, 1, 1), {}, (1, 2, 2, 2, 1)),
+])
+def test_reference_shape_contracts_on_gpu(name, filters, inp, kw, expect):
+    layer = MT.TransformType[name].value(filters, data_format='channels_last', **kw)
+    y = layer(torch.zeros(inp, device='cuda'))
+    assert tuple(y.shape) == expect
+
+
+def test_blocks_shape_contracts_on_gpu():
+    x = torch.zeros((1, 8, 8, 8, 1), device='cuda')
+    assert tuple(MT.AnalysisBlock(1, data_format='channels_last')(x).shape) == (1, 4, 4, 4, 1)
+    assert tuple(MT.AnalysisBlock(1, data_format='channels_last', residual_mode='concat')(x).shape) == (1, 4, 4, 4, 2)
+    y = torch.zeros((1, 1, 1, 1, 1), device='cuda')
+    assert tuple(MT.SynthesisBlock(1, data_format='channels_last')(y).shape) == (1, 2, 2, 2, 1)
+    assert tuple(MT.SynthesisBlock(1, data_format='channels_last', residual_mode='concat')(y).shape) == (1, 2, 2, 2, 2)
+    with pytest.raises(TypeError):
+        MT.AnalysisBlock(1, data_format='channels_last')(torch.zeros((1, 8, 8, 8, 1)))   # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize('fixture', sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, '*.npz'))))
+@pytest.mark.parametrize('precision', ['bf16x3', 'fp32'])
+def test_golden_fixture(fixture, precision):
+    g = np.load(os.path.join(GOLDEN, fixture))
+    config, size, seed, nb = str(g['config']), int(g['size']), int(g['seed']), int(g['n_blocks'])
+    MT.set_precision(precision)
+    m = _model(config, seed)
+    m.compress((1, 1, size, size, size))
+    blocks = [g[f'block{j}'].astype(np.float32) for j in range(nb)]
+    v2 = f'z_sym0' in g
+    # ---- encoder side: symbols / indexes / strings
+    x = torch.zeros(0)
+    from pcc_geo_cnn_v2_b200 import ops
+    from pcc_geo_cnn_v2_b200.model_types import blocks_to_coords
+    x = ops.densify(torch.from_numpy(blocks_to_coords(blocks)).cuda(), nb, size, size, size)
+    dev = m._encode_device(x)
+    strings = m._encode_host(dev)
+    ysym = dev['y_sym'].cpu().numpy()
+    total = flips = 0
+    for j in range(nb):
+        d = ysym[j] != g[f'y_sym{j}']
+        assert np.abs(ysym[j].astype(np.int64) - g[f'y_sym{j}']).max() <= 1
+        flips += int(d.sum())
+        total += d.size
+        same = not d.any()
+        if v2:
+            assert np.array_equal(dev['z_sym'][j].cpu().numpy(), g[f'z_sym{j}'])
+            same &= np.array_equal(dev['indexes'][j].cpu().numpy(), g[f'idx{j}'])
+            assert (dev['indexes'][j].cpu().numpy() != g[f'idx{j}']).mean() <= 1e-3
+        if same:
+            for i, s in enumerate(strings[j]):
+                assert s == g[f'string{j}_{i}'].tobytes(), f'string {i} of block {j} differs'
+    assert flips <= max(1, int(2e-4 * total)), f'{flips}/{total} symbols differ from the oracle'
+    # ---- decoder side: oracle-made strings -> points
+    data = [(tuple(g[f'string{j}_{i}'].tobytes() for i in range(2 if v2 else 1)), 128) for j in range(nb)]
+    m.decompress()
+    try:
+        dec, _ = m.decompress_blocks(None, data, (size, size, size))
+    except Exception as e:  # an index flip against the oracle desynchronises the y stream: reported, not hidden
+        pytest.fail(f'decoding the oracle strings failed: {e}')
+    for j in range(nb):
+        want, got = _as_set(g[f'points{j}']), _as_set(dec[j])
+        assert dec[j].dtype == np.float32
+        assert (want ^ got) <= _as_set(g[f'fragile{j}']), f'{len(want ^ got)} voxels differ beyond the fragile set'
+        assert dec[j].tolist() == sorted(dec[j].tolist())      # argwhere (C) order
+
+
+@pytest.mark.parametrize('config,size', [('c3p', 64), ('c1', 64), ('c2', 32), ('c3', 64)])
+def test_encode_decode_self_consistency(config, size):
+    """decompress_octree.py --debug contract (decompress_octree.py:94-119): the decoder's point set equals the
+    encoder's exactly, block by block, here over a ragged batch (incl. a 1-point block)."""
+    m = _model(config, 7)
+    m.batch_size = 4
+    blocks = synthetic.surface_blocks(6, size=size, seed=9) + [np.array([[0, 0, 0]], np.float32)]
+    m.compress((1, 1, size, size, size))
+    data_list, metadata, _ = m.compress_blocks(None, blocks, None, None, size, 0, fixed_threshold=True)
+    assert len(data_list) == 1 and len(data_list[0]) == len(blocks)
+    assert all(t == 128 and isinstance(s, tuple) and all(isinstance(b, bytes) for b in s) for s, t in data_list[0])
+    m.decompress()
+    dec, _ = m.decompress_blocks(None, data_list[0], (size, size, size))
+    enc_pts = metadata[0]['x_hat_list']
+    for a, b in zip(enc_pts, dec):
+        assert np.array_equal(a, b)
+
+
+def test_train_forward_matches_oracle():
+    """tr_train.py path forward values (model_types.py:327-355): loss = lambda*FL + mbpov with the SAME noise."""
+    m = _model('c3p', 21)
+    o = OracleModel('c3p')
+    w = m.get_weights()
+    o.set_params({k: v for k, v in w.items() if k != 'entropy_bottleneck'}, w['entropy_bottleneck'])
+    from oracle.model import sparse_to_dense
+    blocks = synthetic.surface_blocks(2, size=32, seed=3)
+    x = np.concatenate([sparse_to_dense(b, (1, 1, 32, 32, 32)) for b in blocks])
+    g = torch.Generator().manual_seed(0)
+    ny = torch.rand((2, 64, 4, 4, 4), generator=g) - 0.5
+    nz = torch.rand((2, 64, 2, 2, 2), generator=g) - 0.5
+    ref = o.train_forward(x, 2, 0.75, 1e-4, ny, nz)
+    m.train(torch.from_numpy(x).cuda(), 2, 0.75, 1e-4, noise_y=ny.cuda(), noise_z=nz.cuda())
+    for got, want in ((m.train_fl, ref['fl']), (m.train_mbpov, ref['mbpov']), (m.train_loss, ref['loss'])):
+        assert abs(float(got) - float(want)) < 1e-4 * abs(float(want)), (float(got), float(want))
+    rel = (m.y.cpu() - ref['y']).abs().max() / ref['y'].abs().max()
+    assert float(rel) < 3e-5
