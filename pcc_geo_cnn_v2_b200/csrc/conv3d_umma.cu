@@ -12,7 +12,7 @@
 // No im2col copy, no swizzle phase to keep consistent.
 //
 // Pipeline (one CTA, persistent over work items = (n, y-tile, x-tile) columns, streamed along z):
-//   warp 0      TMA producer: one 5-D box load {8ch, 10 x, 18 y, 1 z, C/8 groups} per input plane and precision
+//   warp 0      TMA producer: one 4-D box load {10 x * 8 ch = 160 B rows, 18 y, 1 z, C/8 groups} per input plane and precision
 //               term into a ring of stages; out-of-bounds coordinates are zero-filled = TF 'SAME' padding.
 //   warp 1      MMA issuer (one elected thread): for input plane z and each (ky,kx,k-chunk) ONE tcgen05.mma with
 //               N = 3*Cout whose B operand stacks the three z-taps, accumulating into three neighbouring output
@@ -67,11 +67,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -85,6 +85,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, with the descriptors given as (lo, hi) halves: only the low word (start address) changes between MMAs
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -95,6 +110,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -133,7 +159,7 @@ struct UmmaConvParams {
   int CGi, CGo;          // channel groups (of 8) in / out
   int terms, relu, cout_real;
   int ytiles, xtiles, items;
-  int nstage, nslots;
+  int nstage, nslots, slot_shift;
   int wbytes_term;       // bytes of one precision term of the weight image
   int swap;              // debug: swap LBO/SBO roles
   long long term_stride_out;  // elements between precision terms of y / res
@@ -162,13 +188,12 @@ __device__ __forceinline__ void unpack_bf16x8_add(const int4& q, float* v) {
   }
 }
 
-template <int COUT>  // padded output channels: 16, 32 or 64
+template <int COUT, int TERMS, int KC>  // padded output channels (16,32,64); precision terms (1,2); Cin/16 (1,2,4)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KC = p.CGi >> 1;                                  // 16-channel K chunks
   const int wbytes_all = p.wbytes_term * p.terms;
   uint8_t* wsm = smem + HEADER_BYTES;
   const int stage_bytes = p.terms * p.CGi * PLANE_CG_BYTES;
@@ -193,88 +218,117 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = hdr->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, hdr->tmem_base, 0);  // shuffle => provably warp-uniform
 
   const int D = p.D;
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      uint32_t q = 0;  // running input-plane counter
+      uint32_t s = 0, phase = 0;  // stage ring position / phase
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int xt = item % p.xtiles, yt = (item / p.xtiles) % p.ytiles, n = item / (p.xtiles * p.ytiles);
-        for (int z = 0; z < D; ++z, ++q) {
-          const int s = q % p.nstage;
-          const uint32_t use = q / p.nstage;
-          mbar_wait(smem_u32(&hdr->in_empty[s]), (use & 1) ^ 1);
+        for (int z = 0; z < D; ++z) {
+          mbar_wait(smem_u32(&hdr->in_empty[s]), phase ^ 1);
           const uint32_t full = smem_u32(&hdr->in_full[s]);
           mbar_expect_tx(full, (uint32_t)stage_bytes);
           for (int t = 0; t < p.terms; ++t)
-            tma_load_5d(smem_u32(stages + (size_t)s * stage_bytes + (size_t)t * p.CGi * PLANE_CG_BYTES), &tmap_x, full, 0,
-                        xt * TX - 1, yt * TY - 1, z, (t * p.N + n) * p.CGi);
+            tma_load_4d(smem_u32(stages + (size_t)s * stage_bytes + (size_t)t * p.CGi * PLANE_CG_BYTES), &tmap_x, full,
+                        (xt * TX - 1) * 8, yt * TY - 1, z, (t * p.N + n) * p.CGi);
+          if (++s == (uint32_t)p.nstage) { s = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t lbo_a = p.swap ? ROW_PITCH : PLANE_CG_BYTES, sbo_a = p.swap ? PLANE_CG_BYTES : ROW_PITCH;
-      const uint32_t b_kcore = 3 * (COUT / 8) * 128;  // bytes between the two K core matrices of a B tile
-      const uint32_t lbo_b = p.swap ? 128 : b_kcore, sbo_b = p.swap ? b_kcore : 128;
-      const uint32_t b_tile = 2 * b_kcore;            // one (ky,kx,kc) tile: [2 kcore][3*COUT/8 groups][8][8] bf16
-      const int npairs = p.terms == 2 ? 3 : 1;
-      uint32_t q = 0;   // running input-plane counter
-      uint32_t g0 = 0;  // running output-plane counter at the start of this item
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += D) {
-        for (int z = 0; z < D; ++z, ++q) {
-          const int s = q % p.nstage;
-          mbar_wait(smem_u32(&hdr->in_full[s]), (q / p.nstage) & 1);
-          tc_fence_after();
-          const uint32_t a_stage = smem_u32(stages + (size_t)s * stage_bytes);
-          const int pa = z > 0 ? z - 1 : 0, pb = z + 1 < D ? z + 1 : D - 1;  // output planes touched
-          // planes touched for the first time by this input plane: z+1 (if any), and plane 0 when z == 0
+    // The whole warp walks the (uniform) loop so that address arithmetic stays on the uniform datapath; only the
+    // tcgen05 instructions themselves are issued by one elected lane.  Nothing in the per-MMA path divides or
+    // branches on data: per input plane we precompute <= 2 accumulator segments (split only where the TMEM ring
+    // wraps) and every descriptor is a 64-bit add on a per-plane base.
+    const uint32_t lbo_a = p.swap ? ROW_PITCH : PLANE_CG_BYTES, sbo_a = p.swap ? PLANE_CG_BYTES : ROW_PITCH;
+    constexpr uint32_t b_kcore = 3 * (COUT / 8) * 128;  // bytes between the two K core matrices of a B tile
+    const uint32_t lbo_b = p.swap ? 128 : b_kcore, sbo_b = p.swap ? b_kcore : 128;
+    constexpr uint32_t b_tile16 = 2 * b_kcore / 16;     // one (ky,kx,kc) tile, in 16-byte units
+    constexpr uint32_t b_plane16 = (COUT / 8) * 128 / 16;  // one stacked z-tap (COUT rows), in 16-byte units
+    constexpr int npairs = TERMS == 2 ? 3 : 1;
+    const uint32_t slot_mask = p.nslots - 1;             // nslots is a power of two
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(wsm), lbo_b, sbo_b);
+    const uint32_t b_lo0 = (uint32_t)bdesc0, b_hi = (uint32_t)(bdesc0 >> 32);
+    const uint64_t adesc_proto = make_smem_desc(0, lbo_a, sbo_a);
+    const uint32_t a_hi = (uint32_t)(adesc_proto >> 32), a_lo_proto = (uint32_t)adesc_proto;
+    const uint32_t a_term16 = p.CGi * PLANE_CG_BYTES / 16, w_term16 = p.wbytes_term / 16;
+    const uint32_t stage16 = stage_bytes / 16, stages16 = smem_u32(stages) / 16;
+    uint32_t s = 0, in_phase = 0;  // input stage ring position / phase
+    uint32_t g0 = 0;               // running output-plane counter at the start of this item
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += D) {
+      for (int z = 0; z < D; ++z) {
+        mbar_wait(smem_u32(&hdr->in_full[s]), in_phase);
+        const int pa = z > 0 ? z - 1 : 0, pb = z + 1 < D ? z + 1 : D - 1;  // output planes touched by input plane z
+        // planes touched for the first time by this input plane: z+1 (if it exists), and plane 0 when z == 0
+        if (z == 0) {
+          const uint32_t g = g0;
+          mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), ((g >> p.slot_shift) & 1) ^ 1);
+        }
+        if (z + 1 < D) {
+          const uint32_t g = g0 + z + 1;
+          mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), ((g >> p.slot_shift) & 1) ^ 1);
+        }
+        tc_fence_after();
+        const uint32_t a_lo0 = a_lo_proto + stages16 + s * stage16;
+        // steady-state segments (accumulate): planes pa..pb, split where the ring wraps
+        const uint32_t slot_a = (g0 + pa) & slot_mask;
+        const int nplanes = pb - pa + 1;
+        const int n0 = min(nplanes, (int)(p.nslots - slot_a));   // planes before the wrap
+        const uint32_t j0 = pa - (z - 1);                         // stacked-tap index of plane pa (0 or 1)
+        const uint32_t seg_d0 = tmem_base + slot_a * COUT, seg_b0 = b_lo0 + j0 * b_plane16, seg_i0 = make_idesc(n0 * COUT);
+        const uint32_t seg_d1 = tmem_base, seg_b1 = b_lo0 + (j0 + n0) * b_plane16, seg_i1 = make_idesc((nplanes - n0) * COUT);
+        const bool two = n0 < nplanes;
+        if (elect_one()) {
+          // ---- first (ky,kx,kc,pair): one MMA per plane so that first-touched planes can overwrite (accumulate = 0)
           for (int pl = pa; pl <= pb; ++pl) {
             const bool first = (pl == z + 1) || (z == 0 && pl == 0);
-            if (first) {
-              const uint32_t g = g0 + pl;
-              mbar_wait(smem_u32(&hdr->acc_empty[g % p.nslots]), ((g / p.nslots) & 1) ^ 1);
-            }
+            umma_bf16_lh(tmem_base + ((g0 + pl) & slot_mask) * COUT, a_lo0, a_hi, b_lo0 + (uint32_t)(pl - (z - 1)) * b_plane16, b_hi,
+                         make_idesc(COUT), first ? 0u : 1u);
           }
-          tc_fence_after();
-          int combo = 0;
-          for (int kyx = 0; kyx < 9; ++kyx) {
-            const int ky = kyx / 3, kx = kyx % 3;
-            for (int kc = 0; kc < KC; ++kc, ++combo) {
-              for (int pr = 0; pr < npairs; ++pr) {
-                const int ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-                const uint32_t a_addr = a_stage + ta * p.CGi * PLANE_CG_BYTES + (2 * kc) * PLANE_CG_BYTES + ky * ROW_PITCH + kx * 16;
-                const uint64_t adesc = make_smem_desc(a_addr, lbo_a, sbo_a);
-                const uint32_t b_base = smem_u32(wsm) + tb * p.wbytes_term + (uint32_t)(kyx * KC + kc) * b_tile;
-                const bool very_first = (combo == 0 && pr == 0);
-                // emit maximal runs of planes that are contiguous in the TMEM ring and share the accumulate flag
-                int pl = pa;
-                while (pl <= pb) {
-                  const uint32_t g = g0 + pl;
-                  const int slot = g % p.nslots;
-                  const bool first = very_first && ((pl == z + 1) || (z == 0 && pl == 0));
-                  int run = 1;
-                  while (pl + run <= pb && slot + run < p.nslots) {
-                    const bool f2 = very_first && ((pl + run == z + 1) || (z == 0 && pl + run == 0));
-                    if (f2 != first) break;
-                    ++run;
-                  }
-                  // B rows: plane pl <-> stacked tap index j = pl - (z-1)  (j=0: kz=2, j=1: kz=1, j=2: kz=0)
-                  const int j = pl - (z - 1);
-                  const uint64_t bdesc = make_smem_desc(b_base + (uint32_t)j * (COUT / 8) * 128, lbo_b, sbo_b);
-                  umma_bf16(tmem_base + (uint32_t)slot * COUT, adesc, bdesc, make_idesc(run * COUT), first ? 0u : 1u);
-                  pl += run;
+          // ---- everything else accumulates into the whole window
+          if (!two) {
+#pragma unroll
+            for (int kyx = 0; kyx < 9; ++kyx) {
+              const uint32_t a_kyx16 = ((kyx / 3) * ROW_PITCH + (kyx % 3) * 16) / 16;
+#pragma unroll
+              for (int kc = 0; kc < KC; ++kc) {
+#pragma unroll
+                for (int pr = 0; pr < npairs; ++pr) {
+                  if (kyx == 0 && pr == 0 && kc == 0) continue;
+                  const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+                  umma_bf16_lh(seg_d0, a_lo0 + a_kyx16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16), a_hi,
+                               seg_b0 + tb * w_term16 + (uint32_t)(kyx * KC + kc) * b_tile16, b_hi, seg_i0, 1u);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int kyx = 0; kyx < 9; ++kyx) {
+              const uint32_t a_kyx16 = ((kyx / 3) * ROW_PITCH + (kyx % 3) * 16) / 16;
+#pragma unroll
+              for (int kc = 0; kc < KC; ++kc) {
+#pragma unroll
+                for (int pr = 0; pr < npairs; ++pr) {
+                  if (kyx == 0 && pr == 0 && kc == 0) continue;
+                  const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+                  const uint32_t a_lo = a_lo0 + a_kyx16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16);
+                  const uint32_t b_off = tb * w_term16 + (uint32_t)(kyx * KC + kc) * b_tile16;
+                  umma_bf16_lh(seg_d0, a_lo, a_hi, seg_b0 + b_off, b_hi, seg_i0, 1u);
+                  umma_bf16_lh(seg_d1, a_lo, a_hi, seg_b1 + b_off, b_hi, seg_i1, 1u);
                 }
               }
             }
           }
           umma_commit(smem_u32(&hdr->in_empty[s]));  // input stage may be refilled once these MMAs retire
-          if (z >= 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z - 1) % p.nslots]));
-          if (z == D - 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z) % p.nslots]));
+          if (z >= 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z - 1) & slot_mask]));
+          if (z == D - 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z) & slot_mask]));
         }
+        __syncwarp();
+        if (++s == (uint32_t)p.nstage) { s = 0; in_phase ^= 1; }
       }
     }
   } else {
@@ -295,8 +349,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
       for (int pl = 0; pl < D; ++pl) {
         const uint32_t g = g0 + pl;
         if ((int)(g & 1) != grp) continue;
-        const int slot = g % p.nslots;
-        mbar_wait(smem_u32(&hdr->acc_full[slot]), (g / p.nslots) & 1);
+        const int slot = g & (p.nslots - 1);
+        mbar_wait(smem_u32(&hdr->acc_full[slot]), (g >> p.slot_shift) & 1);
         tc_fence_after();
         uint32_t r[COUT];
 #pragma unroll
@@ -336,7 +390,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
             qh32[i] = *reinterpret_cast<uint32_t*>(&t2);
           }
           *reinterpret_cast<int4*>(p.y + e) = qh;
-          if (p.terms == 2) {
+          if (TERMS == 2) {
             int4 ql;
             uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
 #pragma unroll
@@ -444,16 +498,16 @@ static float bf16_to_f32_host(uint16_t h) {
   return f;
 }
 
-template <int COUT>
+template <int COUT, int TERMS, int KC>
 static int launch_umma(const CUtensorMap& tmap, const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
   static bool attr_set = false;
   static size_t attr_smem = 0;
   if (!attr_set || smem > attr_smem) {
-    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<COUT, TERMS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
     attr_smem = 227 * 1024;
   }
-  conv3d_umma_kernel<COUT><<<grid, NUM_THREADS, smem, st>>>(tmap, p);
+  conv3d_umma_kernel<COUT, TERMS, KC><<<grid, NUM_THREADS, smem, st>>>(tmap, p);
   return check_launch("conv3d_umma_kernel");
 }
 
@@ -530,7 +584,7 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   PCCGEO_REQUIRE(n > 0 && d > 0 && h % TY == 0 && wd % TX == 0 && h > 0 && wd > 0, "conv3d_umma: H must be a multiple of 16 and W of 8 (got %dx%dx%d)", d, h, wd);
   const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16);
   PCCGEO_REQUIRE(cop == 16 || cop == 32 || cop == 64, "conv3d_umma: Cout %d unsupported", cout);
-  PCCGEO_REQUIRE(cip <= 64, "conv3d_umma: Cin %d unsupported", cin);
+  PCCGEO_REQUIRE(cip == 16 || cip == 32 || cip == 64, "conv3d_umma: Cin %d unsupported", cin);
   EncodeTiledFn enc = get_encode_fn();
   PCCGEO_REQUIRE(enc, "conv3d_umma: cuTensorMapEncodeTiled unavailable");
 
@@ -544,6 +598,8 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   // TMEM ring: up to 256 columns (leaves room for a second CTA per SM), power of two, >= 4 planes
   p.nslots = 256 / cop;
   if (p.nslots > MAX_SLOTS) p.nslots = MAX_SLOTS;
+  p.slot_shift = 0;
+  while ((1 << p.slot_shift) < p.nslots) ++p.slot_shift;
   const int stage_bytes = terms * p.CGi * PLANE_CG_BYTES;
   const int wall = (p.wbytes_term * terms + 127) & ~127;
   const int avail = 227 * 1024 - HEADER_BYTES - wall;
@@ -553,11 +609,13 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   const size_t smem = HEADER_BYTES + wall + (size_t)p.nstage * stage_bytes;
 
   CUtensorMap tmap;
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)terms * n * p.CGi};
-  const cuuint64_t gstr[4] = {16, (cuuint64_t)wd * 16, (cuuint64_t)wd * h * 16, (cuuint64_t)wd * h * d * 16};
-  const cuuint32_t box[5] = {8, PX, PY, 1, (cuuint32_t)p.CGi};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xb), gdim, gstr, box, estr,
+  // the (x, 8-channel) pair is one contiguous run in the blocked layout: make it the (wide) innermost TMA dimension so a
+  // halo'd row is ONE 160-byte request instead of ten 16-byte ones; a negative / past-the-end start is zero-filled.
+  const cuuint64_t gdim[4] = {(cuuint64_t)wd * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)terms * n * p.CGi};
+  const cuuint64_t gstr[3] = {(cuuint64_t)wd * 16, (cuuint64_t)wd * h * 16, (cuuint64_t)wd * h * d * 16};
+  const cuuint32_t box[4] = {PX * 8, PY, 1, (cuuint32_t)p.CGi};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(xb), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PCCGEO_REQUIRE(cr == CUDA_SUCCESS, "conv3d_umma: cuTensorMapEncodeTiled failed (%d)", (int)cr);
@@ -565,7 +623,15 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   int grid = p.items < 148 ? p.items : 148;
   if (g_opt_max_ctas > 0 && grid > g_opt_max_ctas) grid = g_opt_max_ctas;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cop == 16) return launch_umma<16>(tmap, p, smem, grid, st);
-  if (cop == 32) return launch_umma<32>(tmap, p, smem, grid, st);
-  return launch_umma<64>(tmap, p, smem, grid, st);
+  const int kc = cip / 16;
+#define PCCGEO_DISPATCH(CO, T, K) if (cop == CO && terms == T && kc == K) return launch_umma<CO, T, K>(tmap, p, smem, grid, st);
+  PCCGEO_DISPATCH(16, 1, 1) PCCGEO_DISPATCH(16, 1, 2) PCCGEO_DISPATCH(16, 1, 4)
+  PCCGEO_DISPATCH(32, 1, 1) PCCGEO_DISPATCH(32, 1, 2) PCCGEO_DISPATCH(32, 1, 4)
+  PCCGEO_DISPATCH(64, 1, 1) PCCGEO_DISPATCH(64, 1, 2) PCCGEO_DISPATCH(64, 1, 4)
+  PCCGEO_DISPATCH(16, 2, 1) PCCGEO_DISPATCH(16, 2, 2) PCCGEO_DISPATCH(16, 2, 4)
+  PCCGEO_DISPATCH(32, 2, 1) PCCGEO_DISPATCH(32, 2, 2) PCCGEO_DISPATCH(32, 2, 4)
+  PCCGEO_DISPATCH(64, 2, 1) PCCGEO_DISPATCH(64, 2, 2) PCCGEO_DISPATCH(64, 2, 4)
+#undef PCCGEO_DISPATCH
+  set_error("conv3d_umma: unsupported channel configuration %d -> %d", cin, cout);
+  return PCCGEO_EINVAL;
 }
