@@ -82,6 +82,18 @@ int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, c
                        void* yb, int n, int cin, int d, int h, int wd, int cout, int stride, int transposed,
                        int relu, int terms, void* stream);
 
+/* General tensor-core path (gather-im2col -> tcgen05): any cubic kernel <= 9, stride 1 or 2, conv or transposed conv,
+ * 16..64 channels, any volume size (the batch is folded into the GEMM rows).  Same reference call sites as above, plus
+ * the 5^3 / 9^3 layers of AnalysisTransformV1 / SynthesisTransformV1 (src/model_transforms.py:41-59).
+ * pccgeo_gemm_pack_weights_host: tap-major fp32 (k^3, Cin, Cout) HOST weights -> self-describing image (tap table +
+ * per-tap bf16 B-operand chunks); returns the size when out == NULL.  The caller uploads the image and also passes its
+ * first 128 bytes from HOST memory (`wimg_header_host`) so that the launch needs no device read-back. */
+long long pccgeo_gemm_pack_weights_host(const float* w_host, void* out_host, int cin, int cout, int k, int stride,
+                                        int transposed, int terms);
+int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const void* wimg_header_host, const float* bias,
+                       const void* residual_b, void* yb, int n, int cin, int d, int h, int wd, int cout, int relu,
+                       void* stream);
+
 /* ---- entropy models ------------------------------------------------------------------------------
  * tfc.EntropyBottleneck (factorized prior; used at src/model_types.py:254,258,287,291-292,300,306,333,338,
  * 377,382-383,397,404).  `eb_params` is the packed per-channel parameter block, C x 58 floats:

@@ -1,0 +1,426 @@
+// General tcgen05 implicit-GEMM 3D convolution: gather-im2col -> UMMA.  Covers what the TMA halo-plane kernel
+// (conv3d_umma.cu) does not: stride-2 convs, stride-2 transposed convs (8 sub-pixel parity classes), 64-channel
+// layers (weights streamed per tap), 5^3 kernels, and volumes of any size -- the batch is folded into the GEMM M
+// dimension, so a 4^3 latent volume still fills 128-row tiles.
+//
+// Replaces Keras Conv3D / Conv3DTranspose 'same' + BiasAdd + Relu + ResidualLayer add
+// (reference src/model_transforms.py:45-47,56-58,67-69,78-80,93,107,121,135,144-146,155-157).
+//
+// Formulation (same as conv3d_direct.cu): outputs are split into `ncls` sub-pixel classes; within a class, output
+// voxel o (written at o*s_out + P) gathers input voxel o*s_in + off_t for each tap t of the class.  A GEMM tile is 128
+// consecutive (n, o) rows of one class; K runs over taps x Cin.
+//
+// Pipeline per CTA (persistent over tiles):
+//   warps 0-3  gather producers: thread r owns tile row r; per tap it loads the row's Cin channels from the blocked
+//              bf16 layout (16-byte LDG per channel group and precision term, zeros when out of bounds) and stores
+//              them into the UMMA no-swizzle K-major layout of a ring stage (conflict-free 16-byte STS);
+//              fence.proxy.async + mbarrier arrive.  Thread 0 also streams the tap's weight chunk with cp.async.bulk.
+//   warp 4     MMA issuer: per tap, KC x {1|3} tcgen05.mma (M=128, N=Cout) into one of two TMEM accumulators.
+//   warps 5-8  epilogue: tcgen05.ld -> +bias -> ReLU -> +residual -> bf16 hi[/lo] -> 16-byte global stores, overlapped
+//              with the next tile's main loop through the second accumulator.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "umma_ptx.cuh"
+
+namespace pccgeo {
+
+constexpr int GM = 128;
+constexpr int G_THREADS = 9 * 32;
+constexpr int G_MAX_STAGES = 8;
+constexpr int G_HEADER_BYTES = 1024;
+
+struct GemmConvParams {
+  const __nv_bfloat16* x;
+  const uint8_t* wchunks;  // weight chunks, one per tap (all precision terms)
+  const int4* taps;        // (dz, dy, dx, chunk index) per tap, classes concatenated
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+  int N, Din, Hin, Win, Dout, Hout, Wout, Dc, Hc, Wc;
+  int CGi, CGo, cout_real;
+  int s_in, s_out, ncls, relu;
+  int cls_tap_begin[9];
+  long long rows_per_cls;
+  int tiles_per_cls, total_tiles;
+  long long term_stride_in, term_stride_out;
+  int nstage, wchunk_bytes, a_stage_bytes, stage_bytes;
+};
+
+struct __align__(8) GemmSmemHeader {
+  uint64_t full[G_MAX_STAGES], empty[G_MAX_STAGES];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int COUT, int TERMS, int KC>
+__global__ void __launch_bounds__(G_THREADS, 1) conv3d_gemm_kernel(const GemmConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  GemmSmemHeader* hdr = reinterpret_cast<GemmSmemHeader*>(smem);
+  uint8_t* stages = smem + G_HEADER_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int CGI = 2 * KC;
+  constexpr uint32_t tmem_cols = 2 * COUT < 32 ? 32 : 2 * COUT;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&hdr->full[i]), GM); mbar_init(smem_u32(&hdr->empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&hdr->tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, hdr->tmem_base, 0);
+
+  if (warp < 4) {
+    // ================= gather producers =================
+    const int r = threadIdx.x;
+    const long long HWin = (long long)p.Hin * p.Win, DHWin = HWin * p.Din;
+    const uint32_t row_off = (uint32_t)(r >> 3) * 128 + (uint32_t)(r & 7) * 16;
+    uint32_t s = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int cls = tile / p.tiles_per_cls, t = tile - cls * p.tiles_per_cls;
+      long long L = (long long)t * GM + r;
+      const bool valid = L < p.rows_per_cls;
+      if (!valid) L = 0;
+      const int ox = (int)(L % p.Wc); L /= p.Wc;
+      const int oy = (int)(L % p.Hc); L /= p.Hc;
+      const int oz = (int)(L % p.Dc);
+      const int n = (int)(L / p.Dc);
+      const int iz0 = oz * p.s_in, iy0 = oy * p.s_in, ix0 = ox * p.s_in;
+      const __nv_bfloat16* xn = p.x + (long long)n * CGI * DHWin * 8;
+      const int t_end = p.cls_tap_begin[cls + 1];
+      for (int ti = p.cls_tap_begin[cls]; ti < t_end; ++ti) {
+        const int4 tp = __ldg(p.taps + ti);
+        const int iz = iz0 + tp.x, iy = iy0 + tp.y, ix = ix0 + tp.z;
+        const bool inb = valid && iz >= 0 && iz < p.Din && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+        const __nv_bfloat16* src = xn + (iz * HWin + (long long)iy * p.Win + ix) * 8;
+        int4 v[TERMS * CGI];
+#pragma unroll
+        for (int tt = 0; tt < TERMS; ++tt)
+#pragma unroll
+          for (int cg = 0; cg < CGI; ++cg)
+            v[tt * CGI + cg] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8))
+                                   : make_int4(0, 0, 0, 0);
+        mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1);
+        uint8_t* st = stages + (size_t)s * p.stage_bytes;
+        if (r == 0) {
+          const uint32_t full = smem_u32(&hdr->full[s]);
+          mbar_expect_tx_only(full, (uint32_t)p.wchunk_bytes);
+          bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)tp.w * p.wchunk_bytes, (uint32_t)p.wchunk_bytes, full);
+        }
+#pragma unroll
+        for (int i = 0; i < TERMS * CGI; ++i) *reinterpret_cast<int4*>(st + i * 2048 + row_off) = v[i];
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&hdr->full[s]));
+        if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    // ================= MMA issuer =================
+    constexpr uint32_t b_kc16 = 2 * (COUT / 8) * 128 / 16;     // one k-chunk of B (two K core matrices), 16-byte units
+    constexpr uint32_t b_term16 = KC * b_kc16;
+    constexpr int npairs = TERMS == 2 ? 3 : 1;
+    const uint64_t a_proto = make_smem_desc(0, 2048, 128);
+    const uint64_t b_proto = make_smem_desc(0, (COUT / 8) * 128, 128);
+    const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
+    const uint32_t stages16 = smem_u32(stages) / 16, stage16 = p.stage_bytes / 16, aw16 = p.a_stage_bytes / 16;
+    constexpr uint32_t idesc = make_idesc(COUT);
+    uint32_t s = 0, ph = 0, u = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++u) {
+      const int cls = tile / p.tiles_per_cls;
+      const int t0 = p.cls_tap_begin[cls], t1 = p.cls_tap_begin[cls + 1];
+      const uint32_t buf = u & 1;
+      mbar_wait(smem_u32(&hdr->acc_empty[buf]), ((u >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + buf * COUT;
+      for (int ti = t0; ti < t1; ++ti) {
+        mbar_wait(smem_u32(&hdr->full[s]), ph);
+        tc_fence_after();
+        const uint32_t a_lo0 = (uint32_t)a_proto + stages16 + s * stage16;
+        const uint32_t b_lo0 = (uint32_t)b_proto + stages16 + s * stage16 + aw16;
+        if (elect_one()) {
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+            for (int pr = 0; pr < npairs; ++pr) {
+              const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+              umma_bf16_lh(d, a_lo0 + (ta * CGI + 2 * kc) * (2048 / 16), a_hi, b_lo0 + tb * b_term16 + kc * b_kc16, b_hi, idesc,
+                           (ti == t0 && kc == 0 && pr == 0) ? 0u : 1u);
+            }
+          umma_commit(smem_u32(&hdr->empty[s]));
+          if (ti == t1 - 1) umma_commit(smem_u32(&hdr->acc_full[buf]));
+        }
+        __syncwarp();
+        if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    float bias_r[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) bias_r[c] = (p.bias && c < p.cout_real) ? __ldg(p.bias + c) : 0.f;
+    const long long HWo = (long long)p.Hout * p.Wout, DHWo = HWo * p.Dout;
+    uint32_t u = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++u) {
+      const int cls = tile / p.tiles_per_cls, t = tile - cls * p.tiles_per_cls;
+      const uint32_t buf = u & 1;
+      mbar_wait(smem_u32(&hdr->acc_full[buf]), (u >> 1) & 1);
+      tc_fence_after();
+      uint32_t rg[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; c += 16) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * COUT + c, rg + c);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[buf]));
+      long long L = (long long)t * GM + row;
+      if (L >= p.rows_per_cls) continue;
+      const int ox = (int)(L % p.Wc); L /= p.Wc;
+      const int oy = (int)(L % p.Hc); L /= p.Hc;
+      const int oz = (int)(L % p.Dc);
+      const int n = (int)(L / p.Dc);
+      const int Pz = (cls >> 2) & 1, Py = (cls >> 1) & 1, Px = cls & 1;
+      const long long vox = (long long)(oz * p.s_out + Pz) * HWo + (long long)(oy * p.s_out + Py) * p.Wout + (ox * p.s_out + Px);
+      float v[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        v[c] = __uint_as_float(rg[c]) + bias_r[c];
+        if (p.relu) v[c] = fmaxf(v[c], 0.f);
+      }
+      if (p.res) {
+#pragma unroll
+        for (int tt = 0; tt < TERMS; ++tt)
+#pragma unroll
+          for (int cg = 0; cg < COUT / 8; ++cg) {
+            const long long e = tt * p.term_stride_out + (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
+            const int4 qv = __ldg(reinterpret_cast<const int4*>(p.res + e));
+            unpack_bf16x8_add(qv, v + cg * 8);
+          }
+      }
+#pragma unroll
+      for (int cg = 0; cg < COUT / 8; ++cg) {
+        const long long e = (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
+        float* vv = v + cg * 8;
+        __nv_bfloat16 hi[8];
+        int4 qh;
+        uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hi[i] = __float2bfloat16_rn(vv[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 t2 = __halves2bfloat162(hi[2 * i], hi[2 * i + 1]);
+          qh32[i] = *reinterpret_cast<uint32_t*>(&t2);
+        }
+        *reinterpret_cast<int4*>(p.y + e) = qh;
+        if (TERMS == 2) {
+          int4 ql;
+          uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            ql32[i] = pack_bf16x2(vv[2 * i] - __bfloat162float(hi[2 * i]), vv[2 * i + 1] - __bfloat162float(hi[2 * i + 1]));
+          *reinterpret_cast<int4*>(p.y + p.term_stride_out + e) = ql;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// host side: tap tables + weight image
+// --------------------------------------------------------------------------------------------------------
+struct TapTable {
+  int ncls = 1, s_in = 1, s_out = 1;
+  int begin[9] = {0};
+  std::vector<int4> taps;  // (dz,dy,dx, kernel tap index (kz*k+ky)*k+kx)
+};
+
+static inline int round_up_i(int a, int m) { return (a + m - 1) / m * m; }
+
+// Even spatial dims are assumed for stride 2 (TF SAME pad_before then does not depend on the size).
+static bool build_taps(int k, int stride, int transposed, TapTable& T) {
+  if (k < 1 || k > 9 || !(k & 1) || (stride != 1 && stride != 2)) return false;
+  int nt[2] = {0, 0}, tk[2][9], toff[2][9];
+  if (!transposed) {
+    const int pb = stride == 1 ? (k - 1) / 2 : (k - 2) / 2;  // SAME, even sizes: total = k - stride, before = total / 2
+    T.ncls = 1; T.s_in = stride; T.s_out = 1;
+    nt[0] = k;
+    for (int j = 0; j < k; ++j) { tk[0][j] = j; toff[0][j] = j - pb; }
+  } else {
+    const int pb = stride == 1 ? (k - 1) / 2 : (k - 2) / 2;
+    T.ncls = stride == 1 ? 1 : 8; T.s_in = 1; T.s_out = stride;
+    for (int P = 0; P < stride; ++P) {
+      int cnt = 0;
+      for (int j = 0; j < k; ++j) {
+        const int num = P + pb - j;
+        if (((num % stride) + stride) % stride != 0) continue;
+        tk[P][cnt] = j; toff[P][cnt] = num / stride; ++cnt;
+      }
+      nt[P] = cnt;
+    }
+  }
+  T.taps.clear();
+  for (int cls = 0; cls < T.ncls; ++cls) {
+    const int Pz = (cls >> 2) & 1, Py = (cls >> 1) & 1, Px = cls & 1;
+    T.begin[cls] = (int)T.taps.size();
+    for (int jz = 0; jz < nt[Pz]; ++jz)
+      for (int jy = 0; jy < nt[Py]; ++jy)
+        for (int jx = 0; jx < nt[Px]; ++jx)
+          T.taps.push_back(make_int4(toff[Pz][jz], toff[Py][jy], toff[Px][jx], (tk[Pz][jz] * k + tk[Py][jy]) * k + tk[Px][jx]));
+  }
+  T.begin[T.ncls] = (int)T.taps.size();
+  return true;
+}
+
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1);
+  return (uint16_t)(u >> 16);
+}
+static float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// image = [int32 header: magic, ntaps, ncls, begin[9], wchunk_bytes, taps_offset, chunks_offset, ...pad to 128 B]
+//         [int4 taps (chunk index = position)] [pad to 128] [chunks: ntaps x (terms x [kc][kcore][Cout_p/8][8 n][8 k] bf16)]
+constexpr int kImgMagic = 0x47454d31;  // "GEM1"
+constexpr int kImgHeaderBytes = 128;
+
+template <int COUT, int TERMS, int KC>
+static int launch_gemm(const GemmConvParams& p, size_t smem, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_gemm_kernel<COUT, TERMS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv3d_gemm_kernel<COUT, TERMS, KC><<<grid, G_THREADS, smem, st>>>(p);
+  return check_launch("conv3d_gemm_kernel");
+}
+
+}  // namespace pccgeo
+
+using namespace pccgeo;
+
+extern "C" long long pccgeo_gemm_pack_weights_host(const float* w, void* out, int cin, int cout, int k, int stride,
+                                                   int transposed, int terms) {
+  TapTable T;
+  if (cin <= 0 || cout <= 0 || (terms != 1 && terms != 2) || !build_taps(k, stride, transposed, T)) {
+    set_error("gemm_pack_weights: bad argument");
+    return PCCGEO_EINVAL;
+  }
+  const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16), KC = cip / 16;
+  const int ntaps = (int)T.taps.size();
+  const long long per_term = (long long)KC * 2 * (cop / 8) * 128;
+  const long long wchunk = per_term * terms;
+  const long long taps_off = kImgHeaderBytes;
+  const long long chunks_off = (taps_off + (long long)ntaps * 16 + 127) / 128 * 128;
+  const long long total = chunks_off + wchunk * ntaps;
+  if (!out) return total;
+  if (!w) { set_error("gemm_pack_weights: null weights"); return PCCGEO_EINVAL; }
+  uint8_t* img = (uint8_t*)out;
+  memset(img, 0, (size_t)total);
+  int32_t* h = (int32_t*)img;
+  h[0] = kImgMagic; h[1] = ntaps; h[2] = T.ncls;
+  for (int i = 0; i < 9; ++i) h[3 + i] = i <= T.ncls ? T.begin[i] : ntaps;
+  h[12] = (int32_t)wchunk; h[13] = (int32_t)taps_off; h[14] = (int32_t)chunks_off;
+  h[15] = cin; h[16] = cout; h[17] = k; h[18] = stride; h[19] = transposed; h[20] = terms; h[21] = T.s_in; h[22] = T.s_out;
+  int4* taps = (int4*)(img + taps_off);
+  for (int i = 0; i < ntaps; ++i) {
+    taps[i] = T.taps[i];
+    const int kidx = T.taps[i].w;
+    taps[i].w = i;  // chunk index
+    uint16_t* o = (uint16_t*)(img + chunks_off + wchunk * i);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci) {
+        const float val = w[((long long)kidx * cin + ci) * cout + co];
+        const int kc = ci / 16, kk = ci % 16, kcore = kk >> 3, ki = kk & 7;
+        const long long idx = ((((long long)kc * 2 + kcore) * (cop / 8) + (co >> 3)) * 8 + (co & 7)) * 8 + ki;
+        const uint16_t hi = f2bf(val);
+        o[idx] = hi;
+        if (terms == 2) o[per_term / 2 + idx] = f2bf(val - bf2f(hi));
+      }
+  }
+  return total;
+}
+
+extern "C" int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const void* wimg_header_host, const float* bias,
+                                  const void* residual_b, void* yb, int n, int cin, int d, int h, int wd, int cout, int relu,
+                                  void* stream) {
+  PCCGEO_REQUIRE(xb && wimg_dev && wimg_header_host && yb, "conv3d_gemm: null pointer");
+  const int32_t* hh = (const int32_t*)wimg_header_host;
+  PCCGEO_REQUIRE(hh[0] == kImgMagic, "conv3d_gemm: bad weight image");
+  PCCGEO_REQUIRE(hh[15] == cin && hh[16] == cout, "conv3d_gemm: weight image is %dx%d, layer is %dx%d", hh[15], hh[16], cin, cout);
+  const int k = hh[17], stride = hh[18], transposed = hh[19], terms = hh[20];
+  PCCGEO_REQUIRE(n > 0 && d > 0 && h > 0 && wd > 0, "conv3d_gemm: bad shape");
+  PCCGEO_REQUIRE(stride == 1 || transposed || (d % 2 == 0 && h % 2 == 0 && wd % 2 == 0), "conv3d_gemm: stride-2 conv needs even dims");
+  (void)k;
+  const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16), KC = cip / 16;
+  PCCGEO_REQUIRE((cop == 16 || cop == 32 || cop == 64) && (KC == 1 || KC == 2 || KC == 4), "conv3d_gemm: channels %d -> %d unsupported", cin, cout);
+  GemmConvParams p{};
+  p.x = (const __nv_bfloat16*)xb;
+  p.taps = (const int4*)((const uint8_t*)wimg_dev + hh[13]);
+  p.wchunks = (const uint8_t*)wimg_dev + hh[14];
+  p.bias = bias; p.res = (const __nv_bfloat16*)residual_b; p.y = (__nv_bfloat16*)yb;
+  p.N = n; p.Din = d; p.Hin = h; p.Win = wd;
+  p.s_in = hh[21]; p.s_out = hh[22]; p.ncls = hh[2];
+  if (transposed) { p.Dout = d * stride; p.Hout = h * stride; p.Wout = wd * stride; }
+  else { p.Dout = (d + stride - 1) / stride; p.Hout = (h + stride - 1) / stride; p.Wout = (wd + stride - 1) / stride; }
+  p.Dc = p.Dout / p.s_out; p.Hc = p.Hout / p.s_out; p.Wc = p.Wout / p.s_out;
+  p.CGi = cip / 8; p.CGo = cop / 8; p.cout_real = cout; p.relu = relu;
+  for (int i = 0; i < 9; ++i) p.cls_tap_begin[i] = hh[3 + i];
+  p.rows_per_cls = (long long)n * p.Dc * p.Hc * p.Wc;
+  p.tiles_per_cls = (int)((p.rows_per_cls + GM - 1) / GM);
+  p.total_tiles = p.tiles_per_cls * p.ncls;
+  p.term_stride_in = (long long)n * cip * d * h * wd;
+  p.term_stride_out = (long long)n * cop * p.Dout * p.Hout * p.Wout;
+  p.wchunk_bytes = hh[12];
+  p.a_stage_bytes = terms * p.CGi * 2048;
+  p.stage_bytes = (p.a_stage_bytes + p.wchunk_bytes + 127) & ~127;
+  const int avail = 227 * 1024 - G_HEADER_BYTES;
+  p.nstage = avail / p.stage_bytes;
+  if (p.nstage > G_MAX_STAGES) p.nstage = G_MAX_STAGES;
+  PCCGEO_REQUIRE(p.nstage >= 2, "conv3d_gemm: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
+  const size_t smem = G_HEADER_BYTES + (size_t)p.nstage * p.stage_bytes;
+  int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+  cudaStream_t st = (cudaStream_t)stream;
+#define PCCGEO_DISPATCH(CO, T, K) if (cop == CO && terms == T && KC == K) return launch_gemm<CO, T, K>(p, smem, grid, st);
+  PCCGEO_DISPATCH(16, 1, 1) PCCGEO_DISPATCH(16, 1, 2) PCCGEO_DISPATCH(16, 1, 4)
+  PCCGEO_DISPATCH(32, 1, 1) PCCGEO_DISPATCH(32, 1, 2) PCCGEO_DISPATCH(32, 1, 4)
+  PCCGEO_DISPATCH(64, 1, 1) PCCGEO_DISPATCH(64, 1, 2) PCCGEO_DISPATCH(64, 1, 4)
+  PCCGEO_DISPATCH(16, 2, 1) PCCGEO_DISPATCH(16, 2, 2) PCCGEO_DISPATCH(16, 2, 4)
+  PCCGEO_DISPATCH(32, 2, 1) PCCGEO_DISPATCH(32, 2, 2) PCCGEO_DISPATCH(32, 2, 4)
+  PCCGEO_DISPATCH(64, 2, 1) PCCGEO_DISPATCH(64, 2, 2) PCCGEO_DISPATCH(64, 2, 4)
+#undef PCCGEO_DISPATCH
+  set_error("conv3d_gemm: unsupported configuration");
+  return PCCGEO_EINVAL;
+}

@@ -145,6 +145,10 @@ class _ConvBase(Layer):
                 self._dev[key] = torch.from_numpy(self.tap_major()).cuda()
             elif key == 'bias':
                 self._dev[key] = None if self.bias is None else torch.from_numpy(self.bias).cuda()
+            elif key.startswith('w_gemm'):
+                terms = int(key[-1])
+                self._dev[key] = ops.gemm_pack_weights(self.tap_major(), self.in_channels, self.filters, self.k, self.stride,
+                                                       self.transposed, terms)
             elif key.startswith('w_umma'):
                 terms = int(key[-1])
                 self._dev[key] = ops.umma_pack_weights(self.tap_major(), self.in_channels, self.filters, self.stride,
@@ -154,11 +158,18 @@ class _ConvBase(Layer):
         return self._dev[key]
 
     def umma_eligible(self, in_shape):
-        """3x3x3 stride-1 layers with 16/32-wide channels on volumes the 16x8 row tile divides."""
+        """TMA halo-plane kernel: 3x3x3 stride-1 layers with <=32-wide channels on volumes the 16x8 row tile divides."""
         n, c, d, h, w = in_shape
         cp, fp = ops.round_up(c, 16), ops.round_up(self.filters, 16)
-        return (self.k == 3 and self.stride == 1 and c >= 8 and self.filters >= 8 and cp <= 32 and fp <= 32
-                and h % 16 == 0 and w % 8 == 0)
+        return (self.k == 3 and self.stride == 1 and c >= 8 and cp <= 32 and fp <= 32 and h % 16 == 0 and w % 8 == 0
+                and h * w >= 256)
+
+    def gemm_eligible(self, in_shape):
+        """gather -> tcgen05 kernel: everything else with >= 8 input channels and <= 64-wide channels."""
+        n, c, d, h, w = in_shape
+        cp, fp = ops.round_up(c, 16), ops.round_up(self.filters, 16)
+        even = self.stride == 1 or self.transposed or (d % 2 == 0 and h % 2 == 0 and w % 2 == 0)
+        return c >= 8 and cp <= 64 and fp <= 64 and even
 
     def __call__(self, tensor):
         return _run_transform(self, tensor, self.data_format)
@@ -413,6 +424,11 @@ def run_steps(steps, out_id, x):
             if terms and layer.umma_eligible(v.shape):
                 rb = vals[res].as_blk(terms) if res is not None else None
                 yb, shp = ops.conv3d_umma(v.as_blk(terms), v.shape, layer.dev(f'w_umma{terms}'), layer.dev('bias'),
+                                          layer.filters, layer.stride, layer.transposed, layer.relu, terms, rb)
+                vals[dst] = _Val(blk=yb, shape=shp, terms=terms)
+            elif terms and layer.gemm_eligible(v.shape):
+                rb = vals[res].as_blk(terms) if res is not None else None
+                yb, shp = ops.conv3d_gemm(v.as_blk(terms), v.shape, layer.dev(f'w_gemm{terms}'), layer.dev('bias'),
                                           layer.filters, layer.stride, layer.transposed, layer.relu, terms, rb)
                 vals[dst] = _Val(blk=yb, shape=shp, terms=terms)
             else:

@@ -88,6 +88,31 @@ def conv3d_umma(xb, in_shape, wpacked, bias, cout, stride, transposed, relu, ter
     return out, shp
 
 
+def gemm_pack_weights(w_tap_host, cin, cout, k, stride, transposed, terms):
+    """numpy fp32 (k^3, Cin, Cout) -> (device uint8 image, host header bytes) for pccgeo_conv3d_gemm."""
+    w = np.ascontiguousarray(w_tap_host, np.float32)
+    size = L.lib().pccgeo_gemm_pack_weights_host(L.ptr(w), None, cin, cout, k, stride, int(transposed), terms)
+    if size <= 0:
+        L.check(int(size) if size < 0 else -1, 'gemm_pack_weights')
+    img = np.zeros(size, np.uint8)
+    rc = L.lib().pccgeo_gemm_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, k, stride, int(transposed), terms)
+    if rc < 0:
+        L.check(int(rc), 'gemm_pack_weights')
+    return torch.from_numpy(img).cuda(), np.ascontiguousarray(img[:128].copy())
+
+
+def conv3d_gemm(xb, in_shape, wimg, bias, cout, stride, transposed, relu, terms, residual_b=None, out=None):
+    """General blocked-layout tensor-core conv.  wimg = (device image, host header) from gemm_pack_weights."""
+    L.require_cuda()
+    n, cin, d, h, w = in_shape
+    shp = (n, cout, same_out(d, stride, transposed), same_out(h, stride, transposed), same_out(w, stride, transposed))
+    if out is None:
+        out = torch.empty(blocked_numel(*shp, terms), device=xb.device, dtype=torch.bfloat16)
+    L.check(L.lib().pccgeo_conv3d_gemm(L.ptr(xb), L.ptr(wimg[0]), L.ptr(wimg[1]), L.ptr(bias), L.ptr(residual_b), L.ptr(out),
+                                       n, cin, d, h, w, cout, int(relu), L.stream_ptr()), 'conv3d_gemm')
+    return out, shp
+
+
 # ---- entropy models ------------------------------------------------------------------------------------
 _ws = {}
 

@@ -109,3 +109,38 @@ def test_umma_full_size_layer_matches_fp32_kernel(terms):
     # deterministic: same launch twice -> identical bits
     yb2, _ = ops.conv3d_umma(ops.f32_to_blocked(xd, terms), tuple(x.shape), wp, bias.cuda(), 16, 1, True, True, terms)
     assert torch.equal(yb, yb2)
+
+
+GEMM_CASES = [
+    # transposed, k, stride, cin, cout, (D,H,W), n
+    (False, 3, 1, 64, 64, (8, 8, 8), 3), (False, 3, 1, 64, 64, (4, 4, 4), 5), (True, 3, 1, 64, 64, (16, 16, 16), 1),
+    (False, 3, 2, 16, 32, (16, 16, 16), 2), (False, 3, 2, 32, 64, (8, 8, 8), 3), (False, 3, 2, 64, 64, (8, 8, 8), 2),
+    (True, 3, 2, 64, 64, (4, 4, 4), 3), (True, 3, 2, 64, 32, (8, 8, 8), 2), (True, 3, 2, 32, 16, (16, 16, 16), 1),
+    (True, 3, 1, 16, 1, (8, 16, 8), 2), (False, 5, 2, 32, 32, (8, 8, 8), 2), (True, 5, 2, 32, 32, (4, 4, 4), 2),
+    (True, 9, 2, 32, 1, (4, 4, 4), 1), (False, 3, 1, 16, 16, (3, 5, 7), 2), (True, 3, 2, 16, 16, (3, 5, 7), 1),
+]
+
+
+@pytest.mark.parametrize('terms,tol', [(2, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize('transposed,k,s,cin,cout,shape,n', GEMM_CASES)
+def test_gemm_conv_matches_oracle(transposed, k, s, cin, cout, shape, n, terms, tol):
+    rng = np.random.default_rng(hash((transposed, k, s, cin, cout, shape, n)) % 2 ** 31)
+    x, kern, bias = _case(rng, transposed, k, s, cin, cout, shape, n)
+    want0 = _oracle(x, kern, bias, s, True, transposed)
+    res = torch.from_numpy(rng.normal(size=tuple(want0.shape)).astype(np.float32))
+    want = want0 + res.double()
+    wimg = ops.gemm_pack_weights(_tap_major(kern, transposed).numpy(), cin, cout, k, s, transposed, terms)
+    xb = ops.f32_to_blocked(x.cuda(), terms)
+    rb = ops.f32_to_blocked(res.cuda(), terms)
+    yb, shp = ops.conv3d_gemm(xb, tuple(x.shape), wimg, bias.cuda(), cout, s, transposed, True, terms, rb)
+    got = ops.blocked_to_f32(yb, shp, terms)
+    torch.cuda.synchronize()
+    assert shp == tuple(want.shape)
+    err = float((got.cpu().double() - want).abs().max())
+    scale = float(want.abs().max())
+    assert err < tol * scale, f'max err {err:.3e} vs scale {scale:.3e}'
+    # no bias / relu / residual
+    yb2, _ = ops.conv3d_gemm(xb, tuple(x.shape), wimg, None, cout, s, transposed, False, terms)
+    got2 = ops.blocked_to_f32(yb2, shp, terms)
+    want2 = _oracle(x, kern, None, s, False, transposed)
+    assert float((got2.cpu().double() - want2).abs().max()) < tol * float(want2.abs().max())
