@@ -157,6 +157,11 @@ int pccgeo_range_decode_host(const uint8_t* bytes, const long long* byte_offsets
                              const long long* sym_offsets, int nstreams, const int32_t* cdf, int cdf_stride,
                              const int32_t* cdf_length, const int32_t* offset, int rows, int index_mode,
                              long long channel_stride, int32_t* symbols_out, int threads);
+/* HOST: packed occupancy words from pccgeo_threshold_pack (copied to the host) -> float32 (z,y,x) rows in np.argwhere
+ * order, the host half of the reference's `np.argwhere(x_hat > t).astype(float32)` (src/model_types.py:209,234).
+ * offsets (n_blocks+1) receives the prefix sum of per-block point counts; pass points == NULL to query sizes only. */
+int pccgeo_bits_to_points_host(const uint32_t* bits, int n_blocks, int d, int h, int w, long long* offsets,
+                               float* points, long long capacity_points, int threads);
 /* tfc pmf_to_quantized_cdf (precision 16): pmf (len) doubles -> cdf (len+1) int32, HOST */
 int pccgeo_pmf_to_quantized_cdf_host(const double* pmf, int len, int precision, int32_t* cdf);
 

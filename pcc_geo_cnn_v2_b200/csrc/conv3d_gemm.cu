@@ -96,28 +96,37 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv3d_gemm_kernel(const GemmCon
     uint32_t s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int cls = tile / p.tiles_per_cls, t = tile - cls * p.tiles_per_cls;
-      long long L = (long long)t * GM + r;
-      const bool valid = L < p.rows_per_cls;
+      uint32_t L = (uint32_t)t * GM + r;                      // rows_per_cls < 2^31 (host-checked): 32-bit decode
+      const bool valid = L < (uint32_t)p.rows_per_cls;
       if (!valid) L = 0;
-      const int ox = (int)(L % p.Wc); L /= p.Wc;
-      const int oy = (int)(L % p.Hc); L /= p.Hc;
-      const int oz = (int)(L % p.Dc);
-      const int n = (int)(L / p.Dc);
+      const int ox = (int)(L % (uint32_t)p.Wc); L /= (uint32_t)p.Wc;
+      const int oy = (int)(L % (uint32_t)p.Hc); L /= (uint32_t)p.Hc;
+      const int oz = (int)(L % (uint32_t)p.Dc);
+      const int n = (int)(L / (uint32_t)p.Dc);
       const int iz0 = oz * p.s_in, iy0 = oy * p.s_in, ix0 = ox * p.s_in;
       const __nv_bfloat16* xn = p.x + (long long)n * CGI * DHWin * 8;
-      const int t_end = p.cls_tap_begin[cls + 1];
-      for (int ti = p.cls_tap_begin[cls]; ti < t_end; ++ti) {
-        const int4 tp = __ldg(p.taps + ti);
-        const int iz = iz0 + tp.x, iy = iy0 + tp.y, ix = ix0 + tp.z;
+      const int t_begin = p.cls_tap_begin[cls], t_end = p.cls_tap_begin[cls + 1];
+      // software pipeline: the loads of tap ti+1 are in flight while tap ti waits for its stage and is stored
+      int4 v[TERMS * CGI], vn[TERMS * CGI];
+      int4 tp = __ldg(p.taps + t_begin);
+      auto issue_loads = [&](const int4& tap, int4* dst) {
+        const int iz = iz0 + tap.x, iy = iy0 + tap.y, ix = ix0 + tap.z;
         const bool inb = valid && iz >= 0 && iz < p.Din && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
         const __nv_bfloat16* src = xn + (iz * HWin + (long long)iy * p.Win + ix) * 8;
-        int4 v[TERMS * CGI];
 #pragma unroll
         for (int tt = 0; tt < TERMS; ++tt)
 #pragma unroll
           for (int cg = 0; cg < CGI; ++cg)
-            v[tt * CGI + cg] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8))
-                                   : make_int4(0, 0, 0, 0);
+            dst[tt * CGI + cg] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8))
+                                     : make_int4(0, 0, 0, 0);
+      };
+      issue_loads(tp, v);
+      for (int ti = t_begin; ti < t_end; ++ti) {
+        int4 tpn = tp;
+        if (ti + 1 < t_end) {
+          tpn = __ldg(p.taps + ti + 1);
+          issue_loads(tpn, vn);
+        }
         mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1);
         uint8_t* st = stages + (size_t)s * p.stage_bytes;
         if (r == 0) {
@@ -130,6 +139,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv3d_gemm_kernel(const GemmCon
         fence_proxy_async();
         mbar_arrive(smem_u32(&hdr->full[s]));
         if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
+#pragma unroll
+        for (int i = 0; i < TERMS * CGI; ++i) v[i] = vn[i];
+        tp = tpn;
       }
     }
   } else if (warp == 4) {
@@ -192,12 +204,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv3d_gemm_kernel(const GemmCon
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[buf]));
-      long long L = (long long)t * GM + row;
-      if (L >= p.rows_per_cls) continue;
-      const int ox = (int)(L % p.Wc); L /= p.Wc;
-      const int oy = (int)(L % p.Hc); L /= p.Hc;
-      const int oz = (int)(L % p.Dc);
-      const int n = (int)(L / p.Dc);
+      uint32_t L = (uint32_t)t * GM + row;
+      if (L >= (uint32_t)p.rows_per_cls) continue;
+      const int ox = (int)(L % (uint32_t)p.Wc); L /= (uint32_t)p.Wc;
+      const int oy = (int)(L % (uint32_t)p.Hc); L /= (uint32_t)p.Hc;
+      const int oz = (int)(L % (uint32_t)p.Dc);
+      const int n = (int)(L / (uint32_t)p.Dc);
       const int Pz = (cls >> 2) & 1, Py = (cls >> 1) & 1, Px = cls & 1;
       const long long vox = (long long)(oz * p.s_out + Pz) * HWo + (long long)(oy * p.s_out + Py) * p.Wout + (ox * p.s_out + Px);
       float v[COUT];
@@ -399,6 +411,7 @@ extern "C" int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const vo
   p.CGi = cip / 8; p.CGo = cop / 8; p.cout_real = cout; p.relu = relu;
   for (int i = 0; i < 9; ++i) p.cls_tap_begin[i] = hh[3 + i];
   p.rows_per_cls = (long long)n * p.Dc * p.Hc * p.Wc;
+  PCCGEO_REQUIRE(p.rows_per_cls < (1LL << 31) - GM, "conv3d_gemm: too many output voxels per launch (%lld)", p.rows_per_cls);
   p.tiles_per_cls = (int)((p.rows_per_cls + GM - 1) / GM);
   p.total_tiles = p.tiles_per_cls * p.ncls;
   p.term_stride_in = (long long)n * cip * d * h * wd;

@@ -135,9 +135,12 @@ __global__ void gc_likelihood_kernel(const float* __restrict__ v, const float* _
   __shared__ double sm[32];
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    const float s = fmaxf(sigma[i], smin);
-    const float a = fabsf(v[i]);
-    float l = phi_((0.5f - a) / s) - phi_((-0.5f - a) / s);
+    // The difference of two Phi values near 0.5 cancels catastrophically in fp32 for large scales; this kernel touches
+    // only the latents (32 K values per block), so the difference is evaluated in double and rounded once.
+    const double s = (double)fmaxf(sigma[i], smin);
+    const double a = (double)fabsf(v[i]);
+    const double kInvSqrt2 = 0.70710678118654752440;
+    float l = (float)(0.5 * (erfc(-kInvSqrt2 * ((0.5 - a) / s)) - erfc(-kInvSqrt2 * ((-0.5 - a) / s))));
     l = fmaxf(l, 1e-9f);
     if (lik) lik[i] = l;
     acc += (double)logf(l);

@@ -323,3 +323,46 @@ extern "C" int pccgeo_pmf_to_quantized_cdf_host(const double* pmf, int len, int 
   }
   return PCCGEO_OK;
 }
+
+// Packed occupancy words (one block = d*h*w/32 uint32, bit i of word w <-> voxel w*32+i in C order) -> float32 (z,y,x)
+// rows in np.argwhere order, the host half of decompress_blocks / compress_blocks (reference src/model_types.py:209,234).
+// offsets[b] (prefix sum of the per-block popcounts, computed here when counts == NULL) gives each block's first row.
+extern "C" int pccgeo_bits_to_points_host(const uint32_t* bits, int n_blocks, int d, int h, int w, long long* offsets,
+                                          float* points, long long capacity_points, int threads) {
+  if (!bits || !offsets || n_blocks < 0 || d <= 0 || h <= 0 || w <= 0 || ((long long)d * h * w) % 32 != 0) {
+    pccgeo::set_error("bits_to_points: bad argument");
+    return PCCGEO_EINVAL;
+  }
+  const long long words = (long long)d * h * w / 32;
+  std::vector<long long> cnt(n_blocks, 0);
+  parallel_for(n_blocks, threads, [&](int b) {
+    long long c = 0;
+    const uint32_t* p = bits + (long long)b * words;
+    for (long long i = 0; i < words; ++i) c += __builtin_popcount(p[i]);
+    cnt[b] = c;
+  });
+  offsets[0] = 0;
+  for (int b = 0; b < n_blocks; ++b) offsets[b + 1] = offsets[b] + cnt[b];
+  if (!points) return PCCGEO_OK;  // size query
+  if (offsets[n_blocks] > capacity_points) {
+    pccgeo::set_error("bits_to_points: need %lld rows, capacity %lld", offsets[n_blocks], capacity_points);
+    return PCCGEO_ENOSPC;
+  }
+  const int hw = h * w;
+  parallel_for(n_blocks, threads, [&](int b) {
+    const uint32_t* p = bits + (long long)b * words;
+    float* o = points + offsets[b] * 3;
+    for (long long i = 0; i < words; ++i) {
+      uint32_t m = p[i];
+      while (m) {
+        const int bit = __builtin_ctz(m);
+        m &= m - 1;
+        const long long v = i * 32 + bit;
+        const int z = (int)(v / hw), rem = (int)(v % hw);
+        o[0] = (float)z; o[1] = (float)(rem / w); o[2] = (float)(rem % w);
+        o += 3;
+      }
+    }
+  });
+  return PCCGEO_OK;
+}

@@ -122,8 +122,7 @@ class CompressionModel:
         for m in range(thr_idx.shape[1]):
             t = torch.from_numpy(threshold_f32(self.thresholds, thr_idx[:, m])).cuda()
             bits, _ = ops.threshold_pack(x_hat, t)
-            bh = bits.cpu().numpy()
-            x_hat_list.append([bits_to_points(bh[j], tuple(x_hat.shape[2:])) for j in range(n)])
+            x_hat_list.append(ops.bits_to_points(bits.cpu().numpy(), tuple(x_hat.shape[2:]), self.coder_threads))
         threshold_list = [tuple(int(v) for v in thr_idx[:, m]) for m in range(thr_idx.shape[1])]
         metadata = self._select_best(binstr, x_hat_list, level, opt_metrics_ret, points, resolution, with_normals)
         data_list = [list(zip(strings_list, threshold_list[x['idx']])) for x in metadata]
@@ -167,8 +166,7 @@ class CompressionModel:
             x_hat, dbg = self._decode_batch(strings, dims)
             t = torch.from_numpy(threshold_f32(self.thresholds, idx)).cuda()
             bits, _ = ops.threshold_pack(x_hat, t)
-            bh = bits.cpu().numpy()
-            dec_blocks += [bits_to_points(bh[j], dims) for j in range(len(chunk))]
+            dec_blocks += ops.bits_to_points(bits.cpu().numpy(), dims, self.coder_threads)
             debug_t_list += [dbg if debug else None] * len(chunk)
         return dec_blocks, debug_t_list
 

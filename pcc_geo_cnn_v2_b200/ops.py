@@ -272,6 +272,21 @@ def range_decode(strings, sym_offsets, tables, indexes=None, channel_stride=0, t
     return out
 
 
+def bits_to_points(bits_host, dims, threads=0):
+    """bits_host: numpy int32/uint32 (n, d*h*w/32) packed occupancy -> list of float32 (m_i, 3) arrays, argwhere order."""
+    import os
+    bits = np.ascontiguousarray(bits_host).view(np.uint32)
+    n = bits.shape[0]
+    d, h, w = (int(v) for v in dims)
+    offs = np.zeros(n + 1, np.int64)
+    threads = threads or min(n, os.cpu_count() or 1) or 1
+    L.check(L.lib().pccgeo_bits_to_points_host(L.ptr(bits), n, d, h, w, L.ptr(offs), None, 0, threads), 'bits_to_points')
+    pts = np.empty((int(offs[-1]), 3), np.float32)
+    L.check(L.lib().pccgeo_bits_to_points_host(L.ptr(bits), n, d, h, w, L.ptr(offs), L.ptr(pts), int(offs[-1]), threads),
+            'bits_to_points')
+    return [pts[offs[i]:offs[i + 1]] for i in range(n)]
+
+
 def pmf_to_quantized_cdf(pmf, precision=16):
     pmf = np.ascontiguousarray(pmf, np.float64)
     cdf = np.zeros(len(pmf) + 1, np.int32)

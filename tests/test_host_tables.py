@@ -83,3 +83,17 @@ def test_synthetic_blocks_are_valid():
         assert b.dtype == np.float32 and b.min() >= 0 and b.max() <= 31
         assert len(np.unique(b, axis=0)) == len(b)
         assert 0.005 < len(b) / 32 ** 3 < 0.12
+
+
+def test_bits_to_points_cpp_matches_numpy():
+    from pcc_geo_cnn_v2_b200 import ops
+    rng = np.random.default_rng(2)
+    occ = rng.random((5, 8, 16, 32)) < 0.07
+    occ[3] = False                                            # empty block
+    occ[4] = True                                             # full block
+    words = np.packbits(occ.reshape(5, -1), axis=1, bitorder='little').view(np.uint32)
+    got = ops.bits_to_points(words, (8, 16, 32), threads=3)
+    for j in range(5):
+        want = np.argwhere(occ[j]).astype(np.float32)
+        assert got[j].dtype == np.float32 and np.array_equal(got[j], want)
+        assert np.array_equal(MTY.bits_to_points(words[j], (8, 16, 32)), want)
