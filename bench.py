@@ -265,8 +265,15 @@ def main():
     del xin
 
     # ---- e2e through the public API: host blocks in, strings out, strings in, host points out ----
+    EB = 4  # batches per e2e step: the block loops pipeline batches (host coding of batch i overlaps GPU work of batch i+1)
+    e2e_blocks = blocks * EB
+
     def e2e_step():
-        data_list, meta, _ = m.compress_blocks(None, blocks, None, None, SIZE, 0, fixed_threshold=True)
+        data_list, meta, _ = m.compress_blocks(None, e2e_blocks, None, None, SIZE, 0, fixed_threshold=True)
+        if world > 1:  # the path's only exchange step: per-block byte strings gathered over NCCL (rank 0 writes the container)
+            from pcc_geo_cnn_v2_b200.sharding import gather_block_data
+            gathered = gather_block_data(data_list[0])
+            assert len(gathered) == world * B * EB
         dec, _ = m.decompress_blocks(None, data_list[0], (SIZE, SIZE, SIZE))
         return data_list, dec
 
@@ -281,11 +288,11 @@ def main():
     et = torch.tensor([time.perf_counter() - t0], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * esteps / float(et[0])
-    nsym = B * 64 * (8 ** 3 + 4 ** 3)
-    h2d = coords_host.nbytes + nsym * 4 + B * 4 * 2                 # coords (enc) + symbols (dec) + thresholds
-    d2h = nsym * 4 + B * 64 * 8 ** 3 * 4 * 2 + 2 * B * SIZE ** 3 // 8   # symbols + indexes (enc+dec) + packed occupancy (enc+dec)
-    str_bytes = sum(len(s) for blk, _ in data_list[0] for s in blk)
+    e2e_value = world * B * EB * esteps / float(et[0])
+    nsym = B * EB * 64 * (8 ** 3 + 4 ** 3)
+    h2d = coords_host.nbytes * EB + nsym * 4 + B * EB * 4 * 2         # coords (enc) + symbols (dec) + thresholds
+    d2h = nsym * 4 + B * EB * 64 * 8 ** 3 * 4 * 2 + 2 * B * EB * SIZE ** 3 // 8   # symbols + indexes (enc+dec) + packed occupancy (enc+dec)
+    str_bytes = sum(len(s) for blk, _ in data_list[0] for s in blk) / EB
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -299,7 +306,7 @@ def main():
             'tensor_frac_whole_step': value / world * (GFLOP_ENCODE + GFLOP_DECODE) / 1e3 / peak_tf,
             'roofline': roofline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': esteps, 'bitstream_bytes_per_block': str_bytes / B},
+                    'steps': esteps, 'blocks_per_step_per_gpu': B * EB, 'bitstream_bytes_per_block': str_bytes / B},
             'gpu_launches': int(launches), 'clocks': cs.summary()}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, cores = cpu_encode_decode(args.cpu_blocks)

@@ -64,7 +64,11 @@ class CompressionModel:
         self.thresholds = np.linspace(0, 1.0, n_thresholds)  # model_types.py:181
         self.data_format = data_format
         self.batch_size = batch_size
-        self.coder_threads = 0  # 0 = all host cores
+        import os
+        # host threads per range-coder / point-extraction call; half the cores, because `pipeline_depth` batches are
+        # coded concurrently (measured on the 16-core B200 host: depth 3 x 8 threads is the sweet spot)
+        self.coder_threads = max(1, (os.cpu_count() or 2) // 2)
+        self.pipeline_depth = 3  # batches in flight (worker threads / CUDA streams) in the block loops
         self.x = self.x_hat = self.strings = self.debug_tensors = None
         self.x_shape = None
 
@@ -93,36 +97,94 @@ class CompressionModel:
     def _decode_batch(self, strings_list, x_shape):
         raise NotImplementedError
 
+    # -- batch pipeline ------------------------------------------------------------------------------
+    def _map_batches(self, fn, batches):
+        """Run fn(batch) for every batch, results in order.  With more than one batch, each batch's whole chain
+        (H2D -> kernels -> D2H -> C++ range coding / point extraction) runs in a worker thread on its own CUDA stream,
+        so the host stages of batch i overlap the GPU stages of batch i+1.  ctypes / torch release the GIL in the heavy
+        calls; kernels are per-sample deterministic, so results do not depend on the schedule."""
+        if len(batches) <= 1 or self.pipeline_depth <= 1:
+            return [fn(b) for b in batches]
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        first = fn(batches[0])  # warms the per-layer device caches single-threaded
+        local = threading.local()
+        dev = torch.cuda.current_device()
+        main_stream = torch.cuda.current_stream()
+
+        def run(b):
+            torch.cuda.set_device(dev)
+            if not hasattr(local, 'stream'):
+                local.stream = torch.cuda.Stream()
+                local.stream.wait_stream(main_stream)
+            with torch.cuda.stream(local.stream):
+                out = fn(b)
+                local.stream.synchronize()
+            return out
+
+        with ThreadPoolExecutor(max_workers=self.pipeline_depth) as pool:
+            rest = list(pool.map(run, batches[1:]))
+        return [first] + rest
+
+    def _chunks(self, items):
+        return [items[i:i + self.batch_size] for i in range(0, len(items), self.batch_size)]
+
+    def _h2d(self, arr):
+        """numpy -> CUDA through pinned memory (async on the current stream)."""
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        return t.pin_memory().cuda(non_blocking=True) if t.numel() else t.cuda()
+
     # -- public block loops --------------------------------------------------------------------------
-    def encode_blocks(self, blocks, x_shape=None):
-        """Batched analysis + entropy coding + synthesis.  Returns (strings per block, x_hat fp32 CUDA (n,1,D,H,W))."""
+    def encode_blocks(self, blocks, x_shape=None, thr_idx=None, keep_x_hat=True):
+        """Batched analysis + entropy coding + synthesis.
+        Returns (strings per block, x_hat fp32 CUDA (n,1,D,H,W) or None, points per block or None).
+        thr_idx (n,) fixes the per-block threshold so that clip/threshold/bit-pack and the point extraction ride in
+        the same pipelined pass (compress_blocks with fixed_threshold)."""
         dims = [int(s) for s in (x_shape if x_shape is not None else self.x_shape)][-3:]
-        strings, xhats = [], []
-        for i in range(0, len(blocks), self.batch_size):
-            chunk = blocks[i:i + self.batch_size]
-            coords = torch.from_numpy(blocks_to_coords(chunk)).cuda()
-            x = ops.densify(coords, len(chunk), *dims)
+        spans = [(i, min(i + self.batch_size, len(blocks))) for i in range(0, len(blocks), self.batch_size)]
+
+        def run(span):
+            chunk = blocks[span[0]:span[1]]
+            x = ops.densify(self._h2d(blocks_to_coords(chunk)), len(chunk), *dims)
             dev = self._encode_device(x)
-            strings += self._encode_host(dev)
-            xhats.append(dev['x_hat'])
-        return strings, (torch.cat(xhats) if len(xhats) > 1 else xhats[0])
+            pts = None
+            bits = None
+            if thr_idx is not None:
+                t = self._h2d(threshold_f32(self.thresholds, thr_idx[span[0]:span[1]]))
+                bits, _ = ops.threshold_pack(dev['x_hat'], t)
+            strings = self._encode_host(dev)
+            if bits is not None:
+                pts = ops.bits_to_points(bits.cpu().numpy(), dims, self.coder_threads)
+            return strings, (dev['x_hat'] if keep_x_hat else None), pts
+
+        res = self._map_batches(run, spans)
+        strings = [s for r in res for s in r[0]]
+        x_hat = None
+        if keep_x_hat:
+            xs = [r[1] for r in res]
+            torch.cuda.current_stream().synchronize()
+            x_hat = torch.cat(xs) if len(xs) > 1 else xs[0]
+        pts = [q for r in res for q in r[2]] if thr_idx is not None else None
+        return strings, x_hat, pts
 
     def compress_blocks(self, sess, blocks, binstr, points, resolution, level, with_normals=False,
                         opt_metrics=('d1_mse',), max_deltas=(np.inf,), fixed_threshold=False, debug=False):
         """src/model_types.py:184-218.  Returns (data_list, metadata, debug_t_list)."""
         assert self.x_shape is not None, 'call compress(x_shape) first'
-        strings_list, x_hat = self.encode_blocks(blocks)
         n = len(blocks)
         if fixed_threshold:
             opt_metrics_ret = list(opt_metrics)
             thr_idx = np.full((n, len(opt_metrics_ret)), len(self.thresholds) // 2, np.int64)  # model_opt.py:27-31
+            strings_list, _, pts = self.encode_blocks(blocks, thr_idx=thr_idx[:, 0], keep_x_hat=False)
+            x_hat_list = [pts] * thr_idx.shape[1]  # every opt_metric gets the same fixed threshold
         else:
+            strings_list, x_hat, _ = self.encode_blocks(blocks)
             thr_idx, opt_metrics_ret = self._optimal_thresholds(blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas)
-        x_hat_list = []
-        for m in range(thr_idx.shape[1]):
-            t = torch.from_numpy(threshold_f32(self.thresholds, thr_idx[:, m])).cuda()
-            bits, _ = ops.threshold_pack(x_hat, t)
-            x_hat_list.append(ops.bits_to_points(bits.cpu().numpy(), tuple(x_hat.shape[2:]), self.coder_threads))
+            x_hat_list = []
+            for m in range(thr_idx.shape[1]):
+                t = self._h2d(threshold_f32(self.thresholds, thr_idx[:, m]))
+                bits, _ = ops.threshold_pack(x_hat, t)
+                x_hat_list.append(ops.bits_to_points(bits.cpu().numpy(), tuple(x_hat.shape[2:]), self.coder_threads))
         threshold_list = [tuple(int(v) for v in thr_idx[:, m]) for m in range(thr_idx.shape[1])]
         metadata = self._select_best(binstr, x_hat_list, level, opt_metrics_ret, points, resolution, with_normals)
         data_list = [list(zip(strings_list, threshold_list[x['idx']])) for x in metadata]
@@ -158,17 +220,17 @@ class CompressionModel:
     def decompress_blocks(self, sess, blocks, x_shape, debug=False):
         """src/model_types.py:220-238: blocks = [(strings, threshold_idx)] -> ([float32 (m,3)], debug list)."""
         dims = tuple(int(s) for s in x_shape)[-3:]
-        dec_blocks, debug_t_list = [], []
-        for i in range(0, len(blocks), self.batch_size):
-            chunk = blocks[i:i + self.batch_size]
+
+        def run(chunk):
             strings = [c[0] for c in chunk]
             idx = np.asarray([int(c[1]) for c in chunk], np.int64)
             x_hat, dbg = self._decode_batch(strings, dims)
-            t = torch.from_numpy(threshold_f32(self.thresholds, idx)).cuda()
-            bits, _ = ops.threshold_pack(x_hat, t)
-            dec_blocks += ops.bits_to_points(bits.cpu().numpy(), dims, self.coder_threads)
-            debug_t_list += [dbg if debug else None] * len(chunk)
-        return dec_blocks, debug_t_list
+            bits, _ = ops.threshold_pack(x_hat, self._h2d(threshold_f32(self.thresholds, idx)))
+            pts = ops.bits_to_points(bits.cpu().numpy(), dims, self.coder_threads)
+            return pts, [dbg if debug else None] * len(chunk)
+
+        res = self._map_batches(run, self._chunks(list(blocks)))
+        return [p for r in res for p in r[0]], [d for r in res for d in r[1]]
 
     # -- training graph (forward values; see DESIGN.md for the backward status) ----------------------
     def _finish_train(self, x, x_tilde, log_sums, gamma, alpha, lmbda):
@@ -231,7 +293,7 @@ class CompressionModelV1(CompressionModel):
         f = self.num_filters
         shp = (f,) + tuple(d // 8 for d in dims)  # model_types.py:305
         sym = self.entropy_bottleneck.decode_symbols([s[0] for s in strings_list], shp, self.coder_threads)
-        y_hat = ops.eb_dequantize(torch.from_numpy(sym).cuda(), self.entropy_bottleneck.device_params())
+        y_hat = ops.eb_dequantize(self._h2d(sym), self.entropy_bottleneck.device_params())
         x_hat = self.synthesis_transform(y_hat)
         self.x_hat = x_hat
         return x_hat, {'y_hat': y_hat, 'x_hat': x_hat}
@@ -303,12 +365,12 @@ class CompressionModelV2(CompressionModel):
         f = self.num_filters
         zshp = (f,) + tuple(d // 16 for d in dims)  # model_types.py:403
         zsym = self.entropy_bottleneck.decode_symbols([s[1] for s in strings_list], zshp, self.coder_threads)
-        z_hat = ops.eb_dequantize(torch.from_numpy(zsym).cuda(), self.entropy_bottleneck.device_params())
+        z_hat = ops.eb_dequantize(self._h2d(zsym), self.entropy_bottleneck.device_params())
         sigma_hat = self.hyper_synthesis_transform(z_hat)
         cb = GaussianConditional(sigma_hat, self.scale_table, data_format=self.data_format)
         idx = cb.indexes()
         ysym = cb.decode_symbols([s[0] for s in strings_list], idx.cpu().numpy(), self.coder_threads)
-        y_hat = ops.i32_to_f32(torch.from_numpy(ysym).cuda())
+        y_hat = ops.i32_to_f32(self._h2d(ysym))
         x_hat = self.synthesis_transform(y_hat)
         self.x_hat = x_hat
         return x_hat, {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat}

@@ -245,7 +245,7 @@ def range_encode(symbols, sym_offsets, tables, indexes=None, channel_stride=0, t
     L.check(L.lib().pccgeo_range_encode_host(L.ptr(symbols), L.ptr(indexes), L.ptr(offs), ns, L.ptr(cdf), cdf.shape[1],
                                              L.ptr(cl), L.ptr(of), cdf.shape[0], mode, int(channel_stride),
                                              L.ptr(out), cap, L.ptr(out_offs), threads), 'range_encode')
-    buf = out.tobytes()
+    buf = out[:int(out_offs[-1])].tobytes()
     return [buf[out_offs[i]:out_offs[i + 1]] for i in range(ns)]
 
 
