@@ -66,7 +66,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 template <int COUT, int TERMS, int KC>
-__global__ void __launch_bounds__(G_THREADS, 1) conv3d_gemm_kernel(const GemmConvParams p) {
+// small configurations (<= 8 gather registers-vectors per tap) fit twice on an SM: 2 CTAs hide each other's latencies
+__global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32) ? 2 : 1) conv3d_gemm_kernel(const GemmConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   GemmSmemHeader* hdr = reinterpret_cast<GemmSmemHeader*>(smem);
   uint8_t* stages = smem + G_HEADER_BYTES;
@@ -94,55 +95,78 @@ __global__ void __launch_bounds__(G_THREADS, 1) conv3d_gemm_kernel(const GemmCon
     const long long HWin = (long long)p.Hin * p.Win, DHWin = HWin * p.Din;
     const uint32_t row_off = (uint32_t)(r >> 3) * 128 + (uint32_t)(r & 7) * 16;
     uint32_t s = 0, ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int cls = tile / p.tiles_per_cls, t = tile - cls * p.tiles_per_cls;
-      uint32_t L = (uint32_t)t * GM + r;                      // rows_per_cls < 2^31 (host-checked): 32-bit decode
-      const bool valid = L < (uint32_t)p.rows_per_cls;
-      if (!valid) L = 0;
+    // flat iterator over this CTA's (tile, tap) pairs: the loads of the NEXT pair -- which may belong to the next
+    // tile -- are in flight while the current pair waits for its ring stage and is stored (software pipeline)
+    struct Cursor {
+      int tile, ti, t_end, iz0, iy0, ix0;
+      bool valid;
+      const __nv_bfloat16* xn;
+    };
+    auto open_tile = [&](Cursor& c) {
+      if (c.tile >= p.total_tiles) return;
+      const int cls = c.tile / p.tiles_per_cls, t = c.tile - cls * p.tiles_per_cls;
+      uint32_t L = (uint32_t)t * GM + r;  // rows_per_cls < 2^31 (host-checked): 32-bit decode
+      c.valid = L < (uint32_t)p.rows_per_cls;
+      if (!c.valid) L = 0;
       const int ox = (int)(L % (uint32_t)p.Wc); L /= (uint32_t)p.Wc;
       const int oy = (int)(L % (uint32_t)p.Hc); L /= (uint32_t)p.Hc;
       const int oz = (int)(L % (uint32_t)p.Dc);
       const int n = (int)(L / (uint32_t)p.Dc);
-      const int iz0 = oz * p.s_in, iy0 = oy * p.s_in, ix0 = ox * p.s_in;
-      const __nv_bfloat16* xn = p.x + (long long)n * CGI * DHWin * 8;
-      const int t_begin = p.cls_tap_begin[cls], t_end = p.cls_tap_begin[cls + 1];
-      // software pipeline: the loads of tap ti+1 are in flight while tap ti waits for its stage and is stored
-      int4 v[TERMS * CGI], vn[TERMS * CGI];
-      int4 tp = __ldg(p.taps + t_begin);
-      auto issue_loads = [&](const int4& tap, int4* dst) {
-        const int iz = iz0 + tap.x, iy = iy0 + tap.y, ix = ix0 + tap.z;
-        const bool inb = valid && iz >= 0 && iz < p.Din && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-        const __nv_bfloat16* src = xn + (iz * HWin + (long long)iy * p.Win + ix) * 8;
+      c.iz0 = oz * p.s_in; c.iy0 = oy * p.s_in; c.ix0 = ox * p.s_in;
+      c.xn = p.x + (long long)n * CGI * DHWin * 8;
+      c.ti = p.cls_tap_begin[cls];
+      c.t_end = p.cls_tap_begin[cls + 1];
+    };
+    auto advance = [&](Cursor& c) {
+      if (++c.ti == c.t_end) { c.tile += gridDim.x; open_tile(c); }
+    };
+    auto issue_loads = [&](const Cursor& c, const int4& tap, int4* dst) {
+      const int iz = c.iz0 + tap.x, iy = c.iy0 + tap.y, ix = c.ix0 + tap.z;
+      const bool inb = c.valid && iz >= 0 && iz < p.Din && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+      const __nv_bfloat16* src = c.xn + (iz * HWin + (long long)iy * p.Win + ix) * 8;
 #pragma unroll
-        for (int tt = 0; tt < TERMS; ++tt)
+      for (int tt = 0; tt < TERMS; ++tt)
 #pragma unroll
-          for (int cg = 0; cg < CGI; ++cg)
-            dst[tt * CGI + cg] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8))
-                                     : make_int4(0, 0, 0, 0);
-      };
-      issue_loads(tp, v);
-      for (int ti = t_begin; ti < t_end; ++ti) {
-        int4 tpn = tp;
-        if (ti + 1 < t_end) {
-          tpn = __ldg(p.taps + ti + 1);
-          issue_loads(tpn, vn);
-        }
-        mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1);
-        uint8_t* st = stages + (size_t)s * p.stage_bytes;
-        if (r == 0) {
-          const uint32_t full = smem_u32(&hdr->full[s]);
-          mbar_expect_tx_only(full, (uint32_t)p.wchunk_bytes);
-          bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)tp.w * p.wchunk_bytes, (uint32_t)p.wchunk_bytes, full);
-        }
-#pragma unroll
-        for (int i = 0; i < TERMS * CGI; ++i) *reinterpret_cast<int4*>(st + i * 2048 + row_off) = v[i];
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&hdr->full[s]));
-        if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
-#pragma unroll
-        for (int i = 0; i < TERMS * CGI; ++i) v[i] = vn[i];
-        tp = tpn;
+        for (int cg = 0; cg < CGI; ++cg)
+          dst[tt * CGI + cg] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8))
+                                   : make_int4(0, 0, 0, 0);
+    };
+    Cursor cur;
+    cur.tile = blockIdx.x;
+    cur.ti = cur.t_end = 0;
+    cur.valid = false;
+    cur.xn = p.x;
+    open_tile(cur);
+    int4 v[TERMS * CGI], vn[TERMS * CGI];
+    int4 tp = make_int4(0, 0, 0, 0);
+    if (cur.tile < p.total_tiles) {
+      tp = __ldg(p.taps + cur.ti);
+      issue_loads(cur, tp, v);
+    }
+    while (cur.tile < p.total_tiles) {
+      Cursor nxt = cur;
+      advance(nxt);
+      int4 tpn = tp;
+      if (nxt.tile < p.total_tiles) {
+        tpn = __ldg(p.taps + nxt.ti);
+        issue_loads(nxt, tpn, vn);
       }
+      mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1);
+      uint8_t* st = stages + (size_t)s * p.stage_bytes;
+      if (r == 0) {
+        const uint32_t full = smem_u32(&hdr->full[s]);
+        mbar_expect_tx_only(full, (uint32_t)p.wchunk_bytes);
+        bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)tp.w * p.wchunk_bytes, (uint32_t)p.wchunk_bytes, full);
+      }
+#pragma unroll
+      for (int i = 0; i < TERMS * CGI; ++i) *reinterpret_cast<int4*>(st + i * 2048 + row_off) = v[i];
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&hdr->full[s]));
+      if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
+#pragma unroll
+      for (int i = 0; i < TERMS * CGI; ++i) v[i] = vn[i];
+      tp = tpn;
+      cur = nxt;
     }
   } else if (warp == 4) {
     // ================= MMA issuer =================
@@ -419,12 +443,13 @@ extern "C" int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const vo
   p.wchunk_bytes = hh[12];
   p.a_stage_bytes = terms * p.CGi * 2048;
   p.stage_bytes = (p.a_stage_bytes + p.wchunk_bytes + 127) & ~127;
-  const int avail = 227 * 1024 - G_HEADER_BYTES;
+  const int ctas_per_sm = (terms * 2 * KC <= 8 && cop <= 32) ? 2 : 1;
+  const int avail = (ctas_per_sm == 2 ? 110 : 227) * 1024 - G_HEADER_BYTES;
   p.nstage = avail / p.stage_bytes;
   if (p.nstage > G_MAX_STAGES) p.nstage = G_MAX_STAGES;
   PCCGEO_REQUIRE(p.nstage >= 2, "conv3d_gemm: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
   const size_t smem = G_HEADER_BYTES + (size_t)p.nstage * p.stage_bytes;
-  int grid = p.total_tiles < 148 ? p.total_tiles : 148;
+  int grid = p.total_tiles < 148 * ctas_per_sm ? p.total_tiles : 148 * ctas_per_sm;
   cudaStream_t st = (cudaStream_t)stream;
 #define PCCGEO_DISPATCH(CO, T, K) if (cop == CO && terms == T && KC == K) return launch_gemm<CO, T, K>(p, smem, grid, st);
   PCCGEO_DISPATCH(16, 1, 1) PCCGEO_DISPATCH(16, 1, 2) PCCGEO_DISPATCH(16, 1, 4)

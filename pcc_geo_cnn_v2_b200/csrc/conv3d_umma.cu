@@ -146,14 +146,16 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
       for (int z = 0; z < D; ++z) {
         mbar_wait(smem_u32(&hdr->in_full[s]), in_phase);
         const int pa = z > 0 ? z - 1 : 0, pb = z + 1 < D ? z + 1 : D - 1;  // output planes touched by input plane z
-        // planes touched for the first time by this input plane: z+1 (if it exists), and plane 0 when z == 0
+        // planes touched for the first time by this input plane: z+1 (if it exists), and plane 0 when z == 0.  Their
+        // TMEM slots were zeroed by the epilogue when it drained the previous tenant (or at kernel start), so every MMA
+        // below accumulates and all MMAs of a plane have one shape: no accumulate=0 special cases that drain the pipe.
         if (z == 0) {
           const uint32_t g = g0;
-          mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), ((g >> p.slot_shift) & 1) ^ 1);
+          mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), (g >> p.slot_shift) & 1);
         }
         if (z + 1 < D) {
           const uint32_t g = g0 + z + 1;
-          mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), ((g >> p.slot_shift) & 1) ^ 1);
+          mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), (g >> p.slot_shift) & 1);
         }
         tc_fence_after();
         const uint32_t a_lo0 = a_lo_proto + stages16 + s * stage16;
@@ -166,13 +168,6 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
         const uint32_t seg_d1 = tmem_base, seg_b1 = b_lo0 + (j0 + n0) * b_plane16, seg_i1 = make_idesc((nplanes - n0) * COUT);
         const bool two = n0 < nplanes;
         if (elect_one()) {
-          // ---- first (ky,kx,kc,pair): one MMA per plane so that first-touched planes can overwrite (accumulate = 0)
-          for (int pl = pa; pl <= pb; ++pl) {
-            const bool first = (pl == z + 1) || (z == 0 && pl == 0);
-            umma_bf16_lh(tmem_base + ((g0 + pl) & slot_mask) * COUT, a_lo0, a_hi, b_lo0 + (uint32_t)(pl - (z - 1)) * b_plane16, b_hi,
-                         make_idesc(COUT), first ? 0u : 1u);
-          }
-          // ---- everything else accumulates into the whole window
           if (!two) {
 #pragma unroll
             for (int kyx = 0; kyx < 9; ++kyx) {
@@ -181,7 +176,6 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
               for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
                 for (int pr = 0; pr < npairs; ++pr) {
-                  if (kyx == 0 && pr == 0 && kc == 0) continue;
                   const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
                   umma_bf16_lh(seg_d0, a_lo0 + a_kyx16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16), a_hi,
                                seg_b0 + tb * w_term16 + (uint32_t)(kyx * KC + kc) * b_tile16, b_hi, seg_i0, 1u);
@@ -196,7 +190,6 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
               for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
                 for (int pr = 0; pr < npairs; ++pr) {
-                  if (kyx == 0 && pr == 0 && kc == 0) continue;
                   const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
                   const uint32_t a_lo = a_lo0 + a_kyx16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16);
                   const uint32_t b_off = tb * w_term16 + (uint32_t)(kyx * KC + kc) * b_tile16;
@@ -225,6 +218,16 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
 #pragma unroll
     for (int c = 0; c < COUT; ++c) bias_r[c] = (p.bias && c < p.cout_real) ? __ldg(p.bias + c) : 0.f;
     const long long HW = (long long)p.H * p.W, DHW = HW * D;
+    // zero every accumulator slot this group owns (slot parity == group) and publish it as empty: completes phase 0 of
+    // acc_empty, which is what the MMA issuer waits for before the first use of a slot
+    for (int slot = grp; slot < p.nslots; slot += 2) {
+#pragma unroll
+      for (int c = 0; c < COUT; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * COUT + c);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[slot]));
+    }
     uint32_t g0 = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += D) {
       const int xt = item % p.xtiles, yt = (item / p.xtiles) % p.ytiles, n = item / (p.xtiles * p.ytiles);
@@ -239,6 +242,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
 #pragma unroll
         for (int c = 0; c < COUT; c += 16) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * COUT + c, r + c);
         tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < COUT; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * COUT + c);
+        tmem_st_wait();  // the slot is handed back zeroed: its next tenant only ever accumulates
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[slot]));  // accumulator slot is free again
