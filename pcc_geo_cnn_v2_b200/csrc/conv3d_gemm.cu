@@ -1,23 +1,28 @@
 // General tcgen05 implicit-GEMM 3D convolution: gather-im2col -> UMMA.  Covers what the TMA halo-plane kernel
-// (conv3d_umma.cu) does not: stride-2 convs, stride-2 transposed convs (8 sub-pixel parity classes), 64-channel
-// layers (weights streamed per tap), 5^3 kernels, and volumes of any size -- the batch is folded into the GEMM M
-// dimension, so a 4^3 latent volume still fills 128-row tiles.
+// (conv3d_umma.cu) does not: stride-2 convs, stride-2 transposed convs, 64-channel layers (weights streamed per tap),
+// 5^3 / 9^3 kernels, and volumes of any size -- the batch is folded into the GEMM M dimension, so a 4^3 latent volume
+// still fills 128-row tiles.
 //
 // Replaces Keras Conv3D / Conv3DTranspose 'same' + BiasAdd + Relu + ResidualLayer add
 // (reference src/model_transforms.py:45-47,56-58,67-69,78-80,93,107,121,135,144-146,155-157).
 //
-// Formulation (same as conv3d_direct.cu): outputs are split into `ncls` sub-pixel classes; within a class, output
-// voxel o (written at o*s_out + P) gathers input voxel o*s_in + off_t for each tap t of the class.  A GEMM tile is 128
-// consecutive (n, o) rows of one class; K runs over taps x Cin.
+// Formulation (same as conv3d_direct.cu): outputs are split into sub-pixel classes (1, or 8 parity classes for a
+// stride-2 transposed conv); within a class, output voxel o (written at o*s_out + P) gathers input voxel o*s_in + off_t
+// for each tap t of the class.  Two tilings:
+//   NACC = 1  "class mode": a GEMM tile is 128 consecutive (n, o) rows of ONE class; K runs over that class's taps.
+//   NACC = 8  "shift mode" (stride-2 transposed convs): a tile is 128 (n, o) rows and carries all 8 class accumulators
+//             in TMEM.  The A tile of one input offset vector is gathered ONCE and multiplied with the weight chunk of
+//             every class that uses that offset (3^3 kernel: 8 gathers feed 27 MMAs instead of 27 gathers).
 //
 // Pipeline per CTA (persistent over tiles):
 //   warps 0-3  gather producers: thread r owns tile row r; per tap it loads the row's Cin channels from the blocked
 //              bf16 layout (16-byte LDG per channel group and precision term, zeros when out of bounds) and stores
 //              them into the UMMA no-swizzle K-major layout of a ring stage (conflict-free 16-byte STS);
-//              fence.proxy.async + mbarrier arrive.  Thread 0 also streams the tap's weight chunk with cp.async.bulk.
-//   warp 4     MMA issuer: per tap, KC x {1|3} tcgen05.mma (M=128, N=Cout) into one of two TMEM accumulators.
+//              fence.proxy.async + mbarrier arrive.  The loads of the next (tile, tap) pair are already in flight
+//              (software pipeline across tile boundaries).  Thread 0 streams the tap's weight chunk(s) with cp.async.bulk.
+//   warp 4     MMA issuer: per tap and class, KC x {1|3} tcgen05.mma (M=128, N=Cout) into TMEM accumulators.
 //   warps 5-8  epilogue: tcgen05.ld -> +bias -> ReLU -> +residual -> bf16 hi[/lo] -> 16-byte global stores, overlapped
-//              with the next tile's main loop through the second accumulator.
+//              with the next tile's main loop when a second accumulator set fits in TMEM.
 #include <string.h>
 
 #include <vector>
@@ -34,8 +39,8 @@ constexpr int G_HEADER_BYTES = 1024;
 
 struct GemmConvParams {
   const __nv_bfloat16* x;
-  const uint8_t* wchunks;  // weight chunks, one per tap (all precision terms)
-  const int4* taps;        // (dz, dy, dx, chunk index) per tap, classes concatenated
+  const uint8_t* wchunks;  // weight chunk groups: NACC chunk slots per tap, each chunk holds all precision terms
+  const int4* taps;        // (dz, dy, dx, group index | class mask << 16) per tap, classes concatenated
   const float* bias;
   const __nv_bfloat16* res;
   __nv_bfloat16* y;
@@ -65,15 +70,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-template <int COUT, int TERMS, int KC>
-// small configurations (<= 8 gather registers-vectors per tap) fit twice on an SM: 2 CTAs hide each other's latencies
-__global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32) ? 2 : 1) conv3d_gemm_kernel(const GemmConvParams p) {
+template <int COUT, int NACC>
+struct GemmTmem {
+  static constexpr int kBufs = (2 * NACC * COUT <= 512) ? 2 : 1;
+  static constexpr uint32_t kCols = (kBufs * NACC * COUT < 32) ? 32 : kBufs * NACC * COUT;
+};
+
+// small class-mode configurations (<= 8 gather vectors per tap, <= 32 output channels) fit twice on an SM
+template <int COUT, int TERMS, int KC, int NACC>
+__global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32 && GemmTmem<COUT, NACC>::kCols <= 256) ? 2 : 1)
+conv3d_gemm_kernel(const GemmConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   GemmSmemHeader* hdr = reinterpret_cast<GemmSmemHeader*>(smem);
   uint8_t* stages = smem + G_HEADER_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int CGI = 2 * KC;
-  constexpr uint32_t tmem_cols = 2 * COUT < 32 ? 32 : 2 * COUT;
+  constexpr int NBUF = GemmTmem<COUT, NACC>::kBufs;
+  constexpr uint32_t tmem_cols = GemmTmem<COUT, NACC>::kCols;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&hdr->full[i]), GM); mbar_init(smem_u32(&hdr->empty[i]), 1); }
@@ -95,8 +108,6 @@ __global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32)
     const long long HWin = (long long)p.Hin * p.Win, DHWin = HWin * p.Din;
     const uint32_t row_off = (uint32_t)(r >> 3) * 128 + (uint32_t)(r & 7) * 16;
     uint32_t s = 0, ph = 0;
-    // flat iterator over this CTA's (tile, tap) pairs: the loads of the NEXT pair -- which may belong to the next
-    // tile -- are in flight while the current pair waits for its ring stage and is stored (software pipeline)
     struct Cursor {
       int tile, ti, t_end, iz0, iy0, ix0;
       bool valid;
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32)
     };
     Cursor cur;
     cur.tile = blockIdx.x;
-    cur.ti = cur.t_end = 0;
+    cur.ti = cur.t_end = cur.iz0 = cur.iy0 = cur.ix0 = 0;
     cur.valid = false;
     cur.xn = p.x;
     open_tile(cur);
@@ -155,8 +166,10 @@ __global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32)
       uint8_t* st = stages + (size_t)s * p.stage_bytes;
       if (r == 0) {
         const uint32_t full = smem_u32(&hdr->full[s]);
-        mbar_expect_tx_only(full, (uint32_t)p.wchunk_bytes);
-        bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)tp.w * p.wchunk_bytes, (uint32_t)p.wchunk_bytes, full);
+        const uint32_t group = (uint32_t)tp.w & 0xffffu;
+        const uint32_t bytes = (NACC == 1 ? 1u : (uint32_t)__popc((uint32_t)tp.w >> 16)) * (uint32_t)p.wchunk_bytes;
+        mbar_expect_tx_only(full, bytes);
+        bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)group * NACC * p.wchunk_bytes, bytes, full);
       }
 #pragma unroll
       for (int i = 0; i < TERMS * CGI; ++i) *reinterpret_cast<int4*>(st + i * 2048 + row_off) = v[i];
@@ -177,32 +190,42 @@ __global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32)
     const uint64_t b_proto = make_smem_desc(0, (COUT / 8) * 128, 128);
     const uint32_t a_hi = (uint32_t)(a_proto >> 32), b_hi = (uint32_t)(b_proto >> 32);
     const uint32_t stages16 = smem_u32(stages) / 16, stage16 = p.stage_bytes / 16, aw16 = p.a_stage_bytes / 16;
+    const uint32_t wchunk16 = p.wchunk_bytes / 16;
     constexpr uint32_t idesc = make_idesc(COUT);
     uint32_t s = 0, ph = 0, u = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++u) {
       const int cls = tile / p.tiles_per_cls;
       const int t0 = p.cls_tap_begin[cls], t1 = p.cls_tap_begin[cls + 1];
-      const uint32_t buf = u & 1;
-      mbar_wait(smem_u32(&hdr->acc_empty[buf]), ((u >> 1) & 1) ^ 1);
+      const uint32_t buf = u % NBUF;
+      mbar_wait(smem_u32(&hdr->acc_empty[buf]), (((u / NBUF) & 1) ^ 1));
       tc_fence_after();
-      const uint32_t d = tmem_base + buf * COUT;
+      const uint32_t d0 = tmem_base + buf * NACC * COUT;
+      uint32_t touched = 0;  // accumulators that already hold a partial sum in this tile
       for (int ti = t0; ti < t1; ++ti) {
+        const uint32_t mask = NACC == 1 ? 1u : ((uint32_t)__ldg(&p.taps[ti].w) >> 16);
         mbar_wait(smem_u32(&hdr->full[s]), ph);
         tc_fence_after();
         const uint32_t a_lo0 = (uint32_t)a_proto + stages16 + s * stage16;
-        const uint32_t b_lo0 = (uint32_t)b_proto + stages16 + s * stage16 + aw16;
+        uint32_t b_lo0 = (uint32_t)b_proto + stages16 + s * stage16 + aw16;
         if (elect_one()) {
 #pragma unroll
-          for (int kc = 0; kc < KC; ++kc)
+          for (int c = 0; c < NACC; ++c) {
+            if (!((mask >> c) & 1)) continue;
+            const uint32_t fresh = ((touched >> c) & 1) ^ 1;
 #pragma unroll
-            for (int pr = 0; pr < npairs; ++pr) {
-              const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-              umma_bf16_lh(d, a_lo0 + (ta * CGI + 2 * kc) * (2048 / 16), a_hi, b_lo0 + tb * b_term16 + kc * b_kc16, b_hi, idesc,
-                           (ti == t0 && kc == 0 && pr == 0) ? 0u : 1u);
-            }
+            for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+              for (int pr = 0; pr < npairs; ++pr) {
+                const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+                umma_bf16_lh(d0 + c * COUT, a_lo0 + (ta * CGI + 2 * kc) * (2048 / 16), a_hi, b_lo0 + tb * b_term16 + kc * b_kc16, b_hi,
+                             idesc, (fresh && kc == 0 && pr == 0) ? 0u : 1u);
+              }
+            b_lo0 += wchunk16;  // next chunk slot of this tap's group
+          }
           umma_commit(smem_u32(&hdr->empty[s]));
           if (ti == t1 - 1) umma_commit(smem_u32(&hdr->acc_full[buf]));
         }
+        touched |= mask;
         __syncwarp();
         if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
       }
@@ -217,63 +240,71 @@ __global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32)
     const long long HWo = (long long)p.Hout * p.Wout, DHWo = HWo * p.Dout;
     uint32_t u = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++u) {
-      const int cls = tile / p.tiles_per_cls, t = tile - cls * p.tiles_per_cls;
-      const uint32_t buf = u & 1;
-      mbar_wait(smem_u32(&hdr->acc_full[buf]), (u >> 1) & 1);
+      const int tcls = tile / p.tiles_per_cls, t = tile - tcls * p.tiles_per_cls;
+      const uint32_t buf = u % NBUF;
+      mbar_wait(smem_u32(&hdr->acc_full[buf]), (u / NBUF) & 1);
       tc_fence_after();
-      uint32_t rg[COUT];
-#pragma unroll
-      for (int c = 0; c < COUT; c += 16) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * COUT + c, rg + c);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[buf]));
       uint32_t L = (uint32_t)t * GM + row;
-      if (L >= (uint32_t)p.rows_per_cls) continue;
+      const bool valid = L < (uint32_t)p.rows_per_cls;
+      if (!valid) L = 0;
       const int ox = (int)(L % (uint32_t)p.Wc); L /= (uint32_t)p.Wc;
       const int oy = (int)(L % (uint32_t)p.Hc); L /= (uint32_t)p.Hc;
       const int oz = (int)(L % (uint32_t)p.Dc);
       const int n = (int)(L / (uint32_t)p.Dc);
-      const int Pz = (cls >> 2) & 1, Py = (cls >> 1) & 1, Px = cls & 1;
-      const long long vox = (long long)(oz * p.s_out + Pz) * HWo + (long long)(oy * p.s_out + Py) * p.Wout + (ox * p.s_out + Px);
-      float v[COUT];
+#pragma unroll 1
+      for (int c = 0; c < NACC; ++c) {
+        uint32_t rg[COUT];
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) {
-        v[c] = __uint_as_float(rg[c]) + bias_r[c];
-        if (p.relu) v[c] = fmaxf(v[c], 0.f);
-      }
-      if (p.res) {
-#pragma unroll
-        for (int tt = 0; tt < TERMS; ++tt)
-#pragma unroll
-          for (int cg = 0; cg < COUT / 8; ++cg) {
-            const long long e = tt * p.term_stride_out + (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
-            const int4 qv = __ldg(reinterpret_cast<const int4*>(p.res + e));
-            unpack_bf16x8_add(qv, v + cg * 8);
-          }
-      }
-#pragma unroll
-      for (int cg = 0; cg < COUT / 8; ++cg) {
-        const long long e = (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
-        float* vv = v + cg * 8;
-        __nv_bfloat16 hi[8];
-        int4 qh;
-        uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hi[i] = __float2bfloat16_rn(vv[i]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 t2 = __halves2bfloat162(hi[2 * i], hi[2 * i + 1]);
-          qh32[i] = *reinterpret_cast<uint32_t*>(&t2);
+        for (int k = 0; k < COUT; k += 16) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * NACC + c) * COUT + k, rg + k);
+        tmem_ld_wait();
+        if (c == NACC - 1) {  // every accumulator of this buffer is in registers: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[buf]));
         }
-        *reinterpret_cast<int4*>(p.y + e) = qh;
-        if (TERMS == 2) {
-          int4 ql;
-          uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+        if (!valid) continue;
+        const int cls = NACC == 1 ? tcls : c;
+        const int Pz = (cls >> 2) & 1, Py = (cls >> 1) & 1, Px = cls & 1;
+        const long long vox = (long long)(oz * p.s_out + Pz) * HWo + (long long)(oy * p.s_out + Py) * p.Wout + (ox * p.s_out + Px);
+        float v[COUT];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            ql32[i] = pack_bf16x2(vv[2 * i] - __bfloat162float(hi[2 * i]), vv[2 * i + 1] - __bfloat162float(hi[2 * i + 1]));
-          *reinterpret_cast<int4*>(p.y + p.term_stride_out + e) = ql;
+        for (int k = 0; k < COUT; ++k) {
+          v[k] = __uint_as_float(rg[k]) + bias_r[k];
+          if (p.relu) v[k] = fmaxf(v[k], 0.f);
+        }
+        if (p.res) {
+#pragma unroll
+          for (int tt = 0; tt < TERMS; ++tt)
+#pragma unroll
+            for (int cg = 0; cg < COUT / 8; ++cg) {
+              const long long e = tt * p.term_stride_out + (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
+              const int4 qv = __ldg(reinterpret_cast<const int4*>(p.res + e));
+              unpack_bf16x8_add(qv, v + cg * 8);
+            }
+        }
+#pragma unroll
+        for (int cg = 0; cg < COUT / 8; ++cg) {
+          const long long e = (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
+          float* vv = v + cg * 8;
+          __nv_bfloat16 hi[8];
+          int4 qh;
+          uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hi[i] = __float2bfloat16_rn(vv[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 t2 = __halves2bfloat162(hi[2 * i], hi[2 * i + 1]);
+            qh32[i] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          *reinterpret_cast<int4*>(p.y + e) = qh;
+          if (TERMS == 2) {
+            int4 ql;
+            uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              ql32[i] = pack_bf16x2(vv[2 * i] - __bfloat162float(hi[2 * i]), vv[2 * i + 1] - __bfloat162float(hi[2 * i + 1]));
+            *reinterpret_cast<int4*>(p.y + p.term_stride_out + e) = ql;
+          }
         }
       }
     }
@@ -291,29 +322,29 @@ __global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32)
 // host side: tap tables + weight image
 // --------------------------------------------------------------------------------------------------------
 struct TapTable {
-  int ncls = 1, s_in = 1, s_out = 1;
+  int ncls = 1, s_in = 1, s_out = 1, nacc = 1;
   int begin[9] = {0};
-  std::vector<int4> taps;  // (dz,dy,dx, kernel tap index (kz*k+ky)*k+kx)
+  std::vector<int4> taps;                 // (dz,dy,dx, group | mask << 16)
+  std::vector<std::vector<int>> kernels;  // per tap: kernel tap index (kz*k+ky)*k+kx of each chunk slot
 };
 
 static inline int round_up_i(int a, int m) { return (a + m - 1) / m * m; }
 
 // Even spatial dims are assumed for stride 2 (TF SAME pad_before then does not depend on the size).
-static bool build_taps(int k, int stride, int transposed, TapTable& T) {
+static bool build_taps(int k, int stride, int transposed, bool shift_mode, TapTable& T) {
   if (k < 1 || k > 9 || !(k & 1) || (stride != 1 && stride != 2)) return false;
   int nt[2] = {0, 0}, tk[2][9], toff[2][9];
+  const int pb = stride == 1 ? (k - 1) / 2 : (k - 2) / 2;  // SAME, even sizes: total = k - stride, before = total / 2
   if (!transposed) {
-    const int pb = stride == 1 ? (k - 1) / 2 : (k - 2) / 2;  // SAME, even sizes: total = k - stride, before = total / 2
     T.ncls = 1; T.s_in = stride; T.s_out = 1;
     nt[0] = k;
     for (int j = 0; j < k; ++j) { tk[0][j] = j; toff[0][j] = j - pb; }
   } else {
-    const int pb = stride == 1 ? (k - 1) / 2 : (k - 2) / 2;
     T.ncls = stride == 1 ? 1 : 8; T.s_in = 1; T.s_out = stride;
     for (int P = 0; P < stride; ++P) {
       int cnt = 0;
       for (int j = 0; j < k; ++j) {
-        const int num = P + pb - j;
+        const int num = P + pb - j;  // output p = i*s + j - pb  =>  i = (p + pb - j)/s
         if (((num % stride) + stride) % stride != 0) continue;
         tk[P][cnt] = j; toff[P][cnt] = num / stride; ++cnt;
       }
@@ -321,15 +352,52 @@ static bool build_taps(int k, int stride, int transposed, TapTable& T) {
     }
   }
   T.taps.clear();
-  for (int cls = 0; cls < T.ncls; ++cls) {
-    const int Pz = (cls >> 2) & 1, Py = (cls >> 1) & 1, Px = cls & 1;
-    T.begin[cls] = (int)T.taps.size();
-    for (int jz = 0; jz < nt[Pz]; ++jz)
-      for (int jy = 0; jy < nt[Py]; ++jy)
-        for (int jx = 0; jx < nt[Px]; ++jx)
-          T.taps.push_back(make_int4(toff[Pz][jz], toff[Py][jy], toff[Px][jx], (tk[Pz][jz] * k + tk[Py][jy]) * k + tk[Px][jx]));
+  T.kernels.clear();
+  if (!(shift_mode && transposed && stride == 2)) {
+    T.nacc = 1;
+    for (int cls = 0; cls < T.ncls; ++cls) {
+      const int Pz = (cls >> 2) & 1, Py = (cls >> 1) & 1, Px = cls & 1;
+      T.begin[cls] = (int)T.taps.size();
+      for (int jz = 0; jz < nt[Pz]; ++jz)
+        for (int jy = 0; jy < nt[Py]; ++jy)
+          for (int jx = 0; jx < nt[Px]; ++jx) {
+            const int g = (int)T.taps.size();
+            T.taps.push_back(make_int4(toff[Pz][jz], toff[Py][jy], toff[Px][jx], g | (1 << 16)));
+            T.kernels.push_back({(tk[Pz][jz] * k + tk[Py][jy]) * k + tk[Px][jx]});
+          }
+    }
+    T.begin[T.ncls] = (int)T.taps.size();
+    return true;
   }
-  T.begin[T.ncls] = (int)T.taps.size();
+  // shift mode: one tap per distinct input offset vector; mask = classes that have a kernel tap at that offset
+  T.nacc = 8;
+  int omin = 0, omax = 0;
+  for (int P = 0; P < 2; ++P)
+    for (int j = 0; j < nt[P]; ++j) { omin = toff[P][j] < omin ? toff[P][j] : omin; omax = toff[P][j] > omax ? toff[P][j] : omax; }
+  auto tap_of = [&](int P, int off) {  // kernel index of parity P at input offset off, or -1
+    for (int j = 0; j < nt[P]; ++j)
+      if (toff[P][j] == off) return tk[P][j];
+    return -1;
+  };
+  for (int oz = omin; oz <= omax; ++oz)
+    for (int oy = omin; oy <= omax; ++oy)
+      for (int ox = omin; ox <= omax; ++ox) {
+        int mask = 0;
+        std::vector<int> ks;
+        for (int cls = 0; cls < 8; ++cls) {
+          const int kz = tap_of((cls >> 2) & 1, oz), ky = tap_of((cls >> 1) & 1, oy), kx = tap_of(cls & 1, ox);
+          if (kz < 0 || ky < 0 || kx < 0) continue;
+          mask |= 1 << cls;
+          ks.push_back((kz * k + ky) * k + kx);
+        }
+        if (!mask) continue;
+        const int g = (int)T.taps.size();
+        T.taps.push_back(make_int4(oz, oy, ox, g | (mask << 16)));
+        T.kernels.push_back(ks);
+      }
+  T.ncls = 8;
+  T.begin[0] = 0;
+  for (int i = 1; i < 9; ++i) T.begin[i] = (int)T.taps.size();
   return true;
 }
 
@@ -347,19 +415,19 @@ static float bf2f(uint16_t h) {
   return f;
 }
 
-// image = [int32 header: magic, ntaps, ncls, begin[9], wchunk_bytes, taps_offset, chunks_offset, ...pad to 128 B]
-//         [int4 taps (chunk index = position)] [pad to 128] [chunks: ntaps x (terms x [kc][kcore][Cout_p/8][8 n][8 k] bf16)]
-constexpr int kImgMagic = 0x47454d31;  // "GEM1"
+// image = [int32 header (128 B)] [int4 taps] [pad to 128] [chunk groups: ntaps x nacc slots x
+//          (terms x [kc][kcore][Cout_p/8][8 n][8 k] bf16)]
+constexpr int kImgMagic = 0x47454d32;  // "GEM2"
 constexpr int kImgHeaderBytes = 128;
 
-template <int COUT, int TERMS, int KC>
+template <int COUT, int TERMS, int KC, int NACC>
 static int launch_gemm(const GemmConvParams& p, size_t smem, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_gemm_kernel<COUT, TERMS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_gemm_kernel<COUT, TERMS, KC, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv3d_gemm_kernel<COUT, TERMS, KC><<<grid, G_THREADS, smem, st>>>(p);
+  conv3d_gemm_kernel<COUT, TERMS, KC, NACC><<<grid, G_THREADS, smem, st>>>(p);
   return check_launch("conv3d_gemm_kernel");
 }
 
@@ -369,42 +437,51 @@ using namespace pccgeo;
 
 extern "C" long long pccgeo_gemm_pack_weights_host(const float* w, void* out, int cin, int cout, int k, int stride,
                                                    int transposed, int terms) {
-  TapTable T;
-  if (cin <= 0 || cout <= 0 || (terms != 1 && terms != 2) || !build_taps(k, stride, transposed, T)) {
+  if (cin <= 0 || cout <= 0 || (terms != 1 && terms != 2)) {
     set_error("gemm_pack_weights: bad argument");
     return PCCGEO_EINVAL;
   }
   const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16), KC = cip / 16;
-  const int ntaps = (int)T.taps.size();
   const long long per_term = (long long)KC * 2 * (cop / 8) * 128;
   const long long wchunk = per_term * terms;
+  // shift mode needs (A tile + 8 chunk slots) twice in shared memory
+  const long long a_stage = (long long)terms * (cip / 8) * 2048;
+  const bool shift_mode = transposed && stride == 2 && 2 * (a_stage + 8 * wchunk) + G_HEADER_BYTES <= 227 * 1024;
+  TapTable T;
+  if (!build_taps(k, stride, transposed, shift_mode, T)) {
+    set_error("gemm_pack_weights: unsupported kernel %d / stride %d", k, stride);
+    return PCCGEO_EINVAL;
+  }
+  const int ntaps = (int)T.taps.size();
   const long long taps_off = kImgHeaderBytes;
   const long long chunks_off = (taps_off + (long long)ntaps * 16 + 127) / 128 * 128;
-  const long long total = chunks_off + wchunk * ntaps;
+  const long long total = chunks_off + wchunk * T.nacc * ntaps;
   if (!out) return total;
   if (!w) { set_error("gemm_pack_weights: null weights"); return PCCGEO_EINVAL; }
   uint8_t* img = (uint8_t*)out;
   memset(img, 0, (size_t)total);
   int32_t* h = (int32_t*)img;
   h[0] = kImgMagic; h[1] = ntaps; h[2] = T.ncls;
-  for (int i = 0; i < 9; ++i) h[3 + i] = i <= T.ncls ? T.begin[i] : ntaps;
+  for (int i = 0; i < 9; ++i) h[3 + i] = T.begin[i];
   h[12] = (int32_t)wchunk; h[13] = (int32_t)taps_off; h[14] = (int32_t)chunks_off;
   h[15] = cin; h[16] = cout; h[17] = k; h[18] = stride; h[19] = transposed; h[20] = terms; h[21] = T.s_in; h[22] = T.s_out;
+  h[23] = T.nacc;
   int4* taps = (int4*)(img + taps_off);
   for (int i = 0; i < ntaps; ++i) {
     taps[i] = T.taps[i];
-    const int kidx = T.taps[i].w;
-    taps[i].w = i;  // chunk index
-    uint16_t* o = (uint16_t*)(img + chunks_off + wchunk * i);
-    for (int co = 0; co < cout; ++co)
-      for (int ci = 0; ci < cin; ++ci) {
-        const float val = w[((long long)kidx * cin + ci) * cout + co];
-        const int kc = ci / 16, kk = ci % 16, kcore = kk >> 3, ki = kk & 7;
-        const long long idx = ((((long long)kc * 2 + kcore) * (cop / 8) + (co >> 3)) * 8 + (co & 7)) * 8 + ki;
-        const uint16_t hi = f2bf(val);
-        o[idx] = hi;
-        if (terms == 2) o[per_term / 2 + idx] = f2bf(val - bf2f(hi));
-      }
+    for (size_t slot = 0; slot < T.kernels[i].size(); ++slot) {
+      const int kidx = T.kernels[i][slot];
+      uint16_t* o = (uint16_t*)(img + chunks_off + wchunk * ((long long)i * T.nacc + (long long)slot));
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci) {
+          const float val = w[((long long)kidx * cin + ci) * cout + co];
+          const int kc = ci / 16, kk = ci % 16, kcore = kk >> 3, ki = kk & 7;
+          const long long idx = ((((long long)kc * 2 + kcore) * (cop / 8) + (co >> 3)) * 8 + (co & 7)) * 8 + ki;
+          const uint16_t hi = f2bf(val);
+          o[idx] = hi;
+          if (terms == 2) o[per_term / 2 + idx] = f2bf(val - bf2f(hi));
+        }
+    }
   }
   return total;
 }
@@ -416,12 +493,12 @@ extern "C" int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const vo
   const int32_t* hh = (const int32_t*)wimg_header_host;
   PCCGEO_REQUIRE(hh[0] == kImgMagic, "conv3d_gemm: bad weight image");
   PCCGEO_REQUIRE(hh[15] == cin && hh[16] == cout, "conv3d_gemm: weight image is %dx%d, layer is %dx%d", hh[15], hh[16], cin, cout);
-  const int k = hh[17], stride = hh[18], transposed = hh[19], terms = hh[20];
+  const int stride = hh[18], transposed = hh[19], terms = hh[20], nacc = hh[23];
   PCCGEO_REQUIRE(n > 0 && d > 0 && h > 0 && wd > 0, "conv3d_gemm: bad shape");
   PCCGEO_REQUIRE(stride == 1 || transposed || (d % 2 == 0 && h % 2 == 0 && wd % 2 == 0), "conv3d_gemm: stride-2 conv needs even dims");
-  (void)k;
   const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16), KC = cip / 16;
   PCCGEO_REQUIRE((cop == 16 || cop == 32 || cop == 64) && (KC == 1 || KC == 2 || KC == 4), "conv3d_gemm: channels %d -> %d unsupported", cin, cout);
+  PCCGEO_REQUIRE(nacc == 1 || nacc == 8, "conv3d_gemm: bad weight image (nacc)");
   GemmConvParams p{};
   p.x = (const __nv_bfloat16*)xb;
   p.taps = (const int4*)((const uint8_t*)wimg_dev + hh[13]);
@@ -437,13 +514,14 @@ extern "C" int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const vo
   p.rows_per_cls = (long long)n * p.Dc * p.Hc * p.Wc;
   PCCGEO_REQUIRE(p.rows_per_cls < (1LL << 31) - GM, "conv3d_gemm: too many output voxels per launch (%lld)", p.rows_per_cls);
   p.tiles_per_cls = (int)((p.rows_per_cls + GM - 1) / GM);
-  p.total_tiles = p.tiles_per_cls * p.ncls;
+  p.total_tiles = p.tiles_per_cls * (nacc == 8 ? 1 : p.ncls);
   p.term_stride_in = (long long)n * cip * d * h * wd;
   p.term_stride_out = (long long)n * cop * p.Dout * p.Hout * p.Wout;
   p.wchunk_bytes = hh[12];
   p.a_stage_bytes = terms * p.CGi * 2048;
-  p.stage_bytes = (p.a_stage_bytes + p.wchunk_bytes + 127) & ~127;
-  const int ctas_per_sm = (terms * 2 * KC <= 8 && cop <= 32) ? 2 : 1;
+  p.stage_bytes = (p.a_stage_bytes + nacc * p.wchunk_bytes + 127) & ~127;
+  const int tmem_cols = (2 * nacc * cop <= 512 ? 2 : 1) * nacc * cop;
+  const int ctas_per_sm = (terms * 2 * KC <= 8 && cop <= 32 && tmem_cols <= 256) ? 2 : 1;
   const int avail = (ctas_per_sm == 2 ? 110 : 227) * 1024 - G_HEADER_BYTES;
   p.nstage = avail / p.stage_bytes;
   if (p.nstage > G_MAX_STAGES) p.nstage = G_MAX_STAGES;
@@ -451,7 +529,8 @@ extern "C" int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const vo
   const size_t smem = G_HEADER_BYTES + (size_t)p.nstage * p.stage_bytes;
   int grid = p.total_tiles < 148 * ctas_per_sm ? p.total_tiles : 148 * ctas_per_sm;
   cudaStream_t st = (cudaStream_t)stream;
-#define PCCGEO_DISPATCH(CO, T, K) if (cop == CO && terms == T && KC == K) return launch_gemm<CO, T, K>(p, smem, grid, st);
+#define PCCGEO_DISPATCH(CO, T, K) \
+  if (cop == CO && terms == T && KC == K) return nacc == 8 ? launch_gemm<CO, T, K, 8>(p, smem, grid, st) : launch_gemm<CO, T, K, 1>(p, smem, grid, st);
   PCCGEO_DISPATCH(16, 1, 1) PCCGEO_DISPATCH(16, 1, 2) PCCGEO_DISPATCH(16, 1, 4)
   PCCGEO_DISPATCH(32, 1, 1) PCCGEO_DISPATCH(32, 1, 2) PCCGEO_DISPATCH(32, 1, 4)
   PCCGEO_DISPATCH(64, 1, 1) PCCGEO_DISPATCH(64, 1, 2) PCCGEO_DISPATCH(64, 1, 4)
