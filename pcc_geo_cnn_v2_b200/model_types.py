@@ -65,10 +65,10 @@ class CompressionModel:
         self.data_format = data_format
         self.batch_size = batch_size
         import os
-        # host threads per range-coder / point-extraction call; half the cores, because `pipeline_depth` batches are
-        # coded concurrently (measured on the 16-core B200 host: depth 3 x 8 threads is the sweet spot)
-        self.coder_threads = max(1, (os.cpu_count() or 2) // 2)
-        self.pipeline_depth = 3  # batches in flight (worker threads / CUDA streams) in the block loops
+        # host threads per range-coder / point-extraction call: a quarter of the cores, because `pipeline_depth` batches
+        # are coded concurrently (measured on the 16-core B200 host: depth 4 x 4 threads is the sweet spot)
+        self.coder_threads = max(1, (os.cpu_count() or 4) // 4)
+        self.pipeline_depth = 4  # batches in flight (worker threads / CUDA streams) in the block loops
         self.x = self.x_hat = self.strings = self.debug_tensors = None
         self.x_shape = None
 
@@ -104,27 +104,43 @@ class CompressionModel:
         so the host stages of batch i overlap the GPU stages of batch i+1.  ctypes / torch release the GIL in the heavy
         calls; kernels are per-sample deterministic, so results do not depend on the schedule."""
         if len(batches) <= 1 or self.pipeline_depth <= 1:
+            self._warmed = True
             return [fn(b) for b in batches]
-        import threading
         from concurrent.futures import ThreadPoolExecutor
-        first = fn(batches[0])  # warms the per-layer device caches single-threaded
-        local = threading.local()
+        first = []
+        if not getattr(self, '_warmed', False):  # fill the per-layer device caches single-threaded, once per model
+            first = [fn(batches[0])]
+            batches = batches[1:]
+            self._warmed = True
         dev = torch.cuda.current_device()
-        main_stream = torch.cuda.current_stream()
+        stream = torch.cuda.current_stream()
 
         def run(b):
+            # all workers enqueue on ONE stream: the GPU runs the batches FIFO, so batch i's results (async D2H into
+            # pinned buffers + an event) arrive while batch i+1 is still computing and the workers never fall in lockstep
             torch.cuda.set_device(dev)
-            if not hasattr(local, 'stream'):
-                local.stream = torch.cuda.Stream()
-                local.stream.wait_stream(main_stream)
-            with torch.cuda.stream(local.stream):
-                out = fn(b)
-                local.stream.synchronize()
-            return out
+            with torch.cuda.stream(stream):
+                return fn(b)
 
         with ThreadPoolExecutor(max_workers=self.pipeline_depth) as pool:
-            rest = list(pool.map(run, batches[1:]))
-        return [first] + rest
+            rest = list(pool.map(run, batches))
+        return first + rest
+
+    @staticmethod
+    def _d2h(*tensors):
+        """Enqueue async device->pinned-host copies on the current stream; returns (host tensors, event)."""
+        outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+        for o, t in zip(outs, tensors):
+            o.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return outs, ev
+
+    @staticmethod
+    def _wait(pending):
+        outs, ev = pending
+        ev.synchronize()
+        return [o.numpy() for o in outs]
 
     def _chunks(self, items):
         return [items[i:i + self.batch_size] for i in range(0, len(items), self.batch_size)]
@@ -146,15 +162,17 @@ class CompressionModel:
         def run(span):
             chunk = blocks[span[0]:span[1]]
             x = ops.densify(self._h2d(blocks_to_coords(chunk)), len(chunk), *dims)
-            dev = self._encode_device(x)
+            pend = {}
+            # the symbol D2H is enqueued BEFORE synthesis is launched: range coding overlaps the synthesis kernels
+            dev = self._encode_device(x, lambda d: pend.__setitem__('sym', self._d2h(*self._latent_tensors(d))))
             pts = None
-            bits = None
             if thr_idx is not None:
                 t = self._h2d(threshold_f32(self.thresholds, thr_idx[span[0]:span[1]]))
                 bits, _ = ops.threshold_pack(dev['x_hat'], t)
-            strings = self._encode_host(dev)
-            if bits is not None:
-                pts = ops.bits_to_points(bits.cpu().numpy(), dims, self.coder_threads)
+                pend['bits'] = self._d2h(bits)
+            strings = self._encode_host(dev, self._wait(pend['sym']))
+            if thr_idx is not None:
+                pts = ops.bits_to_points(self._wait(pend['bits'])[0], dims, self.coder_threads)
             return strings, (dev['x_hat'] if keep_x_hat else None), pts
 
         res = self._map_batches(run, spans)
@@ -226,7 +244,7 @@ class CompressionModel:
             idx = np.asarray([int(c[1]) for c in chunk], np.int64)
             x_hat, dbg = self._decode_batch(strings, dims)
             bits, _ = ops.threshold_pack(x_hat, self._h2d(threshold_f32(self.thresholds, idx)))
-            pts = ops.bits_to_points(bits.cpu().numpy(), dims, self.coder_threads)
+            pts = ops.bits_to_points(self._wait(self._d2h(bits))[0], dims, self.coder_threads)
             return pts, [dbg if debug else None] * len(chunk)
 
         res = self._map_batches(run, self._chunks(list(blocks)))
@@ -277,16 +295,25 @@ class CompressionModelV1(CompressionModel):
     def decompress(self):  # model_types.py:297-309
         pass
 
-    def _encode_device(self, x):
+    def _encode_device(self, x, after_latents=None):
         y = self.analysis_transform(x)
         y_sym, y_hat = self.entropy_bottleneck.quantize(y)
+        dev = {'y_sym': y_sym, 'y_hat': y_hat}
+        if after_latents is not None:
+            after_latents(dev)
         x_hat = self.synthesis_transform(y_hat)
         self.x, self.x_hat = x, x_hat
         self.debug_tensors = {'y_hat': y_hat, 'x_hat': x_hat}
-        return {'y_sym': y_sym, 'y_hat': y_hat, 'x_hat': x_hat}
+        dev['x_hat'] = x_hat
+        return dev
 
-    def _encode_host(self, dev):
-        ys = self.entropy_bottleneck.encode_symbols(dev['y_sym'].cpu().numpy(), self.coder_threads)
+    @staticmethod
+    def _latent_tensors(dev):
+        return (dev['y_sym'],)
+
+    def _encode_host(self, dev, host=None):
+        y_sym = host[0] if host is not None else dev['y_sym'].cpu().numpy()
+        ys = self.entropy_bottleneck.encode_symbols(y_sym, self.coder_threads)
         return [(s,) for s in ys]
 
     def _decode_batch(self, strings_list, dims):
@@ -343,22 +370,31 @@ class CompressionModelV2(CompressionModel):
     def decompress(self):  # model_types.py:393-411
         pass
 
-    def _encode_device(self, x):
+    def _encode_device(self, x, after_latents=None):
         y = self.analysis_transform(x)
         z = self.hyper_analysis_transform(y)
         z_sym, z_hat = self.entropy_bottleneck.quantize(z)
         sigma_hat = self.hyper_synthesis_transform(z_hat)
         cb = GaussianConditional(sigma_hat, self.scale_table, data_format=self.data_format)
         y_sym, y_hat, idx = cb.quantize(y)
+        dev = {'y': y, 'z': z, 'z_sym': z_sym, 'z_hat': z_hat, 'sigma_hat': sigma_hat, 'y_sym': y_sym, 'y_hat': y_hat,
+               'indexes': idx, 'cb': cb}
+        if after_latents is not None:
+            after_latents(dev)
         x_hat = self.synthesis_transform(y_hat)
         self.x, self.x_hat = x, x_hat
         self.debug_tensors = {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat}
-        return {'y': y, 'z': z, 'z_sym': z_sym, 'z_hat': z_hat, 'sigma_hat': sigma_hat, 'y_sym': y_sym, 'y_hat': y_hat,
-                'indexes': idx, 'x_hat': x_hat, 'cb': cb}
+        dev['x_hat'] = x_hat
+        return dev
 
-    def _encode_host(self, dev):
-        zs = self.entropy_bottleneck.encode_symbols(dev['z_sym'].cpu().numpy(), self.coder_threads)
-        ys = dev['cb'].encode_symbols(dev['y_sym'].cpu().numpy(), dev['indexes'].cpu().numpy(), self.coder_threads)
+    @staticmethod
+    def _latent_tensors(dev):
+        return (dev['z_sym'], dev['y_sym'], dev['indexes'])
+
+    def _encode_host(self, dev, host=None):
+        z_sym, y_sym, idx = host if host is not None else [t.cpu().numpy() for t in self._latent_tensors(dev)]
+        zs = self.entropy_bottleneck.encode_symbols(z_sym, self.coder_threads)
+        ys = dev['cb'].encode_symbols(y_sym, idx, self.coder_threads)
         return list(zip(ys, zs))  # (y_string, z_string): model_types.py:389
 
     def _decode_batch(self, strings_list, dims):
@@ -369,7 +405,7 @@ class CompressionModelV2(CompressionModel):
         sigma_hat = self.hyper_synthesis_transform(z_hat)
         cb = GaussianConditional(sigma_hat, self.scale_table, data_format=self.data_format)
         idx = cb.indexes()
-        ysym = cb.decode_symbols([s[0] for s in strings_list], idx.cpu().numpy(), self.coder_threads)
+        ysym = cb.decode_symbols([s[0] for s in strings_list], self._wait(self._d2h(idx))[0], self.coder_threads)
         y_hat = ops.i32_to_f32(self._h2d(ysym))
         x_hat = self.synthesis_transform(y_hat)
         self.x_hat = x_hat
