@@ -140,6 +140,35 @@ int pccgeo_threshold_pack(const float* x_hat, const float* thresholds, uint32_t*
 int pccgeo_focal_loss(const float* x_true, const float* x_pred, float gamma, float alpha, double* out,
                       double* partials, long long count, void* stream);
 
+/* ---- training path (tr_train.py; reference src/model_types.py:327-369, TF autodiff + two AdamOptimizers) ---------
+ * fp32, deterministic.  Data gradients of a conv are pccgeo_conv3d_f32 with conv <-> transposed conv swapped and the
+ * tap-major weights' last two axes swapped; the entry points below add what has no forward counterpart. */
+/* dx = dy where y > 0 else 0 (Relu backward; y = the layer's post-activation output) */
+int pccgeo_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream);
+/* out = alpha*a + beta*b (b may be NULL): ResidualLayer add (src/model_transforms.py:35) and gradient accumulation */
+int pccgeo_axpby(const float* a, const float* b, float alpha, float beta, float* out, long long n, void* stream);
+/* d(scale * focal_loss)/d y_pred (src/utils/focal_loss.py:5-12; clip passes gradient on [1e-3,.999] only) */
+int pccgeo_focal_loss_bwd(const float* x_true, const float* x_pred, float gamma, float alpha, float scale, float* dx_pred,
+                          long long n, void* stream);
+/* d(c * sum ln p)/d values and /d sigma of the Gaussian conditional, tfc lower_bound gradient semantics */
+int pccgeo_gc_likelihood_bwd(const float* values, const float* sigma, float scale_min, float c, float* dvalues,
+                             float* dsigma, long long n, void* stream);
+/* d(c * sum ln p)/d values of the entropy bottleneck + per-channel gradients w.r.t. the first 44 entries of the packed
+ * parameter block (softplus'ed matrices, biases, tanh'ed factors): dparams (C,44).  ws: pccgeo_eb_bwd_ws_doubles(C). */
+size_t pccgeo_eb_bwd_ws_doubles(int c);
+int pccgeo_eb_likelihood_bwd(const float* values, const float* eb_params, float c, float* dvalues, float* dparams,
+                             double* ws, int n, int ch, int spatial, void* stream);
+/* weight gradient of a 'same' conv / transposed conv in the tap-major layout (k^3, Cin, Cout) of pccgeo_conv3d_f32.
+ * x: layer input (N,Cin,D,H,W); g: gradient w.r.t. the pre-activation output.  ws: pccgeo_wgrad_ws_floats(). */
+size_t pccgeo_wgrad_ws_floats(int cin, int cout, int k);
+int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw, float* ws, int n, int cin, int d, int h, int wd,
+                            int cout, int k, int stride, int transposed, void* stream);
+/* db[c] = sum over batch and voxels of g; ws: pccgeo_reduce_ws_doubles() doubles */
+int pccgeo_bias_grad_f32(const float* g, float* db, double* ws, int n, int c, long long spatial, void* stream);
+/* tf.train.AdamOptimizer step t (1-based): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps) */
+int pccgeo_adam_step(float* theta, const float* grad, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                     long long step, long long n, void* stream);
+
 /* ---- range coder (HOST) ---------------------------------------------------------------------------
  * Replaces tfc's range_coding_ops.unbounded_index_range_encode / _decode (precision 16, overflow_width 4;
  * src/utils/patch_gaussian_conditional.py:27-31 and EntropyBottleneck/GaussianConditional.compress/.decompress).

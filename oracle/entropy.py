@@ -26,6 +26,26 @@ LIKELIHOOD_BOUND = 1e-9
 RANGE_CODER_PRECISION = 16
 
 
+class _LowerBound(torch.autograd.Function):
+    """tfc.math_ops.lower_bound: max(x, bound) with the 'identity_if_towards' gradient -- the gradient passes when
+    x >= bound or when it is negative (a descent step would move x up, towards the bound)."""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        ctx.save_for_backward(x)
+        ctx.bound = bound
+        return torch.clamp(x, min=bound)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return torch.where((x >= ctx.bound) | (g < 0), g, torch.zeros_like(g)), None
+
+
+def lower_bound(x, bound):
+    return _LowerBound.apply(x, float(bound))
+
+
 def eb_init(channels, rng, dtype=np.float32):
     """Variables as tfc creates them: matrix_i (C, r[i+1], r[i]) = ln(expm1(1/scale/r[i+1])),
     bias_i ~ U(-.5,.5), factor_i = 0, quantiles = (-init_scale, 0, init_scale)."""
@@ -44,6 +64,8 @@ def eb_init(channels, rng, dtype=np.float32):
 
 
 def _t(a, dtype):
+    if torch.is_tensor(a):  # keeps autograd leaves intact (gradient tests)
+        return a.to(dtype)
     return torch.as_tensor(np.asarray(a)).to(dtype)
 
 
@@ -63,9 +85,9 @@ def eb_likelihood_c1m(p, values, dtype=torch.float32):
     """values: (C,1,M) already noised / dequantised.  |sigmoid(s*u) - sigmoid(s*l)|, floored at 1e-9."""
     lower = eb_logits_cumulative(p, values - 0.5, dtype)
     upper = eb_logits_cumulative(p, values + 0.5, dtype)
-    sign = -torch.sign(lower + upper)
+    sign = -torch.sign(lower + upper).detach()
     lik = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
-    return torch.clamp(lik, min=LIKELIHOOD_BOUND)
+    return lower_bound(lik, LIKELIHOOD_BOUND)
 
 
 def eb_medians(p):
@@ -216,7 +238,7 @@ def gc_tables(scale_table):
 def gc_bound_scale(sigma, scale_table):
     """scale_bound=None -> lower-bound the scale at scale_table[0] (patch :57-60)."""
     lo = np.float32(scale_table[0])
-    return torch.clamp(sigma, min=float(lo))
+    return lower_bound(sigma, float(lo))
 
 
 def gc_indexes(sigma, scale_table):
@@ -232,7 +254,7 @@ def gc_likelihood(values, sigma, scale_table, dtype=torch.float32):
     s = gc_bound_scale(sigma.to(dtype), scale_table).to(dtype)
     v = torch.abs(values.to(dtype))
     lik = _phi((0.5 - v) / s) - _phi((-0.5 - v) / s)
-    return torch.clamp(lik, min=LIKELIHOOD_BOUND)
+    return lower_bound(lik, LIKELIHOOD_BOUND)
 
 
 def gc_forward(y, sigma, scale_table, training, noise=None, dtype=torch.float32):

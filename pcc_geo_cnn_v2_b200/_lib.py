@@ -36,6 +36,16 @@ SIGNATURES = {
     'pccgeo_densify': (i32, [vp, i64, vp, i32, i32, i32, i32, vp]),
     'pccgeo_threshold_pack': (i32, [vp, vp, vp, vp, i32, i64, vp]),
     'pccgeo_focal_loss': (i32, [vp, vp, f32, f32, vp, vp, i64, vp]),
+    'pccgeo_relu_bwd': (i32, [vp, vp, vp, i64, vp]),
+    'pccgeo_axpby': (i32, [vp, vp, f32, f32, vp, i64, vp]),
+    'pccgeo_focal_loss_bwd': (i32, [vp, vp, f32, f32, f32, vp, i64, vp]),
+    'pccgeo_gc_likelihood_bwd': (i32, [vp, vp, f32, f32, vp, vp, i64, vp]),
+    'pccgeo_eb_bwd_ws_doubles': (C.c_size_t, [i32]),
+    'pccgeo_eb_likelihood_bwd': (i32, [vp, vp, f32, vp, vp, vp, i32, i32, i32, vp]),
+    'pccgeo_wgrad_ws_floats': (C.c_size_t, [i32, i32, i32]),
+    'pccgeo_conv3d_wgrad_f32': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_bias_grad_f32': (i32, [vp, vp, vp, i32, i32, i64, vp]),
+    'pccgeo_adam_step': (i32, [vp, vp, vp, vp, f32, f32, f32, f32, i64, i64, vp]),
     'pccgeo_range_encode_host': (i32, [vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, vp, i64, vp, i32]),
     'pccgeo_range_decode_host': (i32, [vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, vp, i32]),
     'pccgeo_pmf_to_quantized_cdf_host': (i32, [vp, i32, i32, vp]),

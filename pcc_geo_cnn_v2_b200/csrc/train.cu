@@ -1,0 +1,422 @@
+// Backward / optimiser kernels of the tr_train.py path (reference src/model_types.py:327-369: focal loss + mbpov loss,
+// two Adam optimisers; TF autodiff -> cuDNN backward kernels in the reference).  fp32, deterministic (fixed-order
+// two-stage reductions, no fp atomics).  Data gradients of the convolutions reuse pccgeo_conv3d_f32 with the roles of
+// conv / transposed conv swapped; this file adds what has no forward counterpart.
+#include "common.cuh"
+
+namespace pccgeo {
+
+// ---- elementwise ---------------------------------------------------------------------------------------------------
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, float beta, float* __restrict__ out,
+                             long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = alpha * a[i] + (b ? beta * b[i] : 0.f);
+}
+
+// d focal_loss / d y_pred (src/utils/focal_loss.py:5-12); K.clip passes gradient on [1e-3, .999] only; tf.where routes it
+// through the selected branch only.  scale multiplies the result (lambda).
+__global__ void focal_bwd_kernel(const float* __restrict__ xt, const float* __restrict__ xp, float gamma, float alpha, float scale,
+                                 float* __restrict__ dxp, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float t = xt[i], p = xp[i];
+    float g = 0.f;
+    if (p >= 1e-3f && p <= .999f) {
+      if (t == 1.f) {
+        // -alpha * (1-p)^gamma * ln p
+        g = -alpha * (-gamma * powf(1.f - p, gamma - 1.f) * logf(p) + powf(1.f - p, gamma) / p);
+      } else if (t == 0.f) {
+        // -(1-alpha) * p^gamma * ln(1-p)
+        g = -(1.f - alpha) * (gamma * powf(p, gamma - 1.f) * logf(1.f - p) - powf(p, gamma) / (1.f - p));
+      }
+    }
+    dxp[i] = scale * g;
+  }
+}
+
+// ---- Gaussian conditional: d(c * sum ln p)/dv and /dsigma -------------------------------------------------------------
+// p = Phi(u) - Phi(l), u = (.5-|v|)/s, l = (-.5-|v|)/s, s = lower_bound(sigma, smin), p = lower_bound(p, 1e-9).
+// tfc lower_bound gradient ("identity_if_towards"): pass if input >= bound or the gradient is negative.
+__global__ void gc_bwd_kernel(const float* __restrict__ v, const float* __restrict__ sigma, float smin, float c,
+                              float* __restrict__ dv, float* __restrict__ dsigma, long long n) {
+  const double kInvSqrt2 = 0.70710678118654752440, kInvSqrt2Pi = 0.39894228040143267794;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double sg = (double)sigma[i];
+    const double s = sg > (double)smin ? sg : (double)smin;
+    const double val = (double)v[i], a = fabs(val);
+    const double u = (0.5 - a) / s, l = (-0.5 - a) / s;
+    const double p = 0.5 * (erfc(-kInvSqrt2 * u) - erfc(-kInvSqrt2 * l));
+    const double pb = p > 1e-9 ? p : 1e-9;
+    double gp = (double)c / pb;               // dL/dp_bounded
+    if (!(p >= 1e-9 || gp < 0.0)) gp = 0.0;   // lower_bound on the likelihood
+    const double phu = kInvSqrt2Pi * exp(-0.5 * u * u), phl = kInvSqrt2Pi * exp(-0.5 * l * l);
+    const double sgn = val > 0.0 ? 1.0 : (val < 0.0 ? -1.0 : 0.0);
+    dv[i] = (float)(gp * (-(sgn) / s) * (phu - phl));
+    double gs = gp * (-(u * phu - l * phl) / s);  // dL/ds
+    if (!(sg >= (double)smin || gs < 0.0)) gs = 0.0;  // lower_bound on the scale
+    dsigma[i] = (float)gs;
+  }
+}
+
+// ---- entropy bottleneck: d(c * sum ln p)/dv and per-channel parameter gradients ---------------------------------------
+// Parameters are the packed block of include/pccgeo.h (softplus'ed matrices M, biases B, tanh'ed factors F).  The kernel
+// returns gradients w.r.t. M, B, F (43 values per channel; the host applies softplus'/tanh' for the raw variables).
+struct EbFwd {
+  float t[3][3];   // pre-gate activations of the three hidden layers
+  float h[3][3];   // gated outputs  h = t + F * tanh(t)
+  float out;
+};
+
+__device__ __forceinline__ float eb_forward(const float* __restrict__ q, float v, EbFwd& f) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    f.t[0][i] = q[i] * v + q[24 + i];
+    f.h[0][i] = f.t[0][i] + q[34 + i] * tanhf(f.t[0][i]);
+  }
+#pragma unroll
+  for (int l = 1; l < 3; ++l) {
+    const float* M = q + (l == 1 ? 3 : 12);
+    const float* B = q + (l == 1 ? 27 : 30);
+    const float* F = q + (l == 1 ? 37 : 40);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      f.t[l][i] = M[i * 3] * f.h[l - 1][0] + M[i * 3 + 1] * f.h[l - 1][1] + M[i * 3 + 2] * f.h[l - 1][2] + B[i];
+      f.h[l][i] = f.t[l][i] + F[i] * tanhf(f.t[l][i]);
+    }
+  }
+  f.out = q[21] * f.h[2][0] + q[22] * f.h[2][1] + q[23] * f.h[2][2] + q[33];
+  return f.out;
+}
+
+// accumulate g * d(out)/d(params) into acc[43] and return g * d(out)/dv
+__device__ __forceinline__ float eb_backward(const float* __restrict__ q, float v, const EbFwd& f, float g, float* acc) {
+  float dh[3], dt[3];
+  // output layer: out = M3 . h2 + b3
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { acc[21 + i] += g * f.h[2][i]; dh[i] = g * q[21 + i]; }
+  acc[33] += g;
+#pragma unroll
+  for (int l = 2; l >= 1; --l) {
+    const float* M = q + (l == 1 ? 3 : 12);
+    const float* F = q + (l == 1 ? 37 : 40);
+    const int mo = l == 1 ? 3 : 12, bo = l == 1 ? 27 : 30, fo = l == 1 ? 37 : 40;
+    float dprev[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float th = tanhf(f.t[l][i]);
+      acc[fo + i] += dh[i] * th;
+      dt[i] = dh[i] * (1.f + F[i] * (1.f - th * th));
+      acc[bo + i] += dt[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        acc[mo + i * 3 + j] += dt[i] * f.h[l - 1][j];
+        dprev[j] += dt[i] * M[i * 3 + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dh[j] = dprev[j];
+  }
+  float dv = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float th = tanhf(f.t[0][i]);
+    acc[34 + i] += dh[i] * th;
+    dt[i] = dh[i] * (1.f + q[34 + i] * (1.f - th * th));
+    acc[24 + i] += dt[i];
+    acc[i] += dt[i] * v;
+    dv += dt[i] * q[i];
+  }
+  return dv;
+}
+
+constexpr int kEbGradN = 44;  // gradients w.r.t. params [0:44) of the packed block ([43] = median: unused, kept 0)
+
+// grid (chunks, C): block partial sums of the 44 gradients -> partials[(c * chunks + chunk) * 44 + k]
+__global__ void eb_bwd_kernel(const float* __restrict__ vals, const float* __restrict__ params, float cscale, float* __restrict__ dv,
+                              double* __restrict__ partials, int N, int C, int S) {
+  __shared__ double sm[32];
+  __shared__ float q[PCCGEO_EB_PARAM_STRIDE];
+  const int c = blockIdx.y;
+  if (threadIdx.x < PCCGEO_EB_PARAM_STRIDE) q[threadIdx.x] = params[c * PCCGEO_EB_PARAM_STRIDE + threadIdx.x];
+  __syncthreads();
+  float acc[kEbGradN];
+#pragma unroll
+  for (int k = 0; k < kEbGradN; ++k) acc[k] = 0.f;
+  const long long total = (long long)N * S;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(e / S), i = (int)(e % S);
+    const long long idx = ((long long)n * C + c) * S + i;
+    const float v = vals[idx];
+    EbFwd fl, fu;
+    const float lo = eb_forward(q, v - 0.5f, fl), up = eb_forward(q, v + 0.5f, fu);
+    const float tt = lo + up;
+    const float s = tt > 0.f ? -1.f : (tt < 0.f ? 1.f : 0.f);
+    const float su = 1.f / (1.f + expf(-s * up)), sl = 1.f / (1.f + expf(-s * lo));
+    const float diff = su - sl;
+    const float p = fabsf(diff);
+    const float pb = fmaxf(p, 1e-9f);
+    float gp = cscale / pb;
+    if (!(p >= 1e-9f || gp < 0.f)) gp = 0.f;
+    const float sd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    const float gu = gp * sd * s * su * (1.f - su);     // dL/d up
+    const float gl = -gp * sd * s * sl * (1.f - sl);    // dL/d lo
+    float g = eb_backward(q, v + 0.5f, fu, gu, acc);
+    g += eb_backward(q, v - 0.5f, fl, gl, acc);
+    dv[idx] = g;
+  }
+#pragma unroll 1
+  for (int k = 0; k < kEbGradN; ++k) {
+    const double r = block_sum((double)acc[k], sm);
+    if (threadIdx.x == 0) partials[((long long)c * gridDim.x + blockIdx.x) * kEbGradN + k] = r;
+  }
+}
+
+__global__ void eb_bwd_finish_kernel(const double* __restrict__ partials, int chunks, float* __restrict__ dparams) {
+  const int c = blockIdx.x, k = threadIdx.x;
+  if (k >= kEbGradN) return;
+  double s = 0.0;
+  for (int j = 0; j < chunks; ++j) s += partials[((long long)c * chunks + j) * kEbGradN + k];
+  dparams[c * kEbGradN + k] = (float)s;
+}
+
+// ---- convolution weight / bias gradients -----------------------------------------------------------------------------
+// Unified form (conv and transposed conv): dW[t,ci,co] = sum_{n,b} x[n,ci, b*sx + ox_t] * g[n,co, b*sy + oy_t] over base
+// positions b of a (Bd,Bh,Bw) grid; out-of-range positions contribute zero.  grid (taps, splits); each block reduces its
+// slice of (n, b) into a Cin x Cout partial; a second kernel adds the splits in order.
+struct WgradParams {
+  const float* x;
+  const float* g;
+  float* partial;  // (taps, splits, Cin, Cout)
+  int N, Cin, Cout, K;
+  int Xd, Xh, Xw, Gd, Gh, Gw, Bd, Bh, Bw;
+  int sx, sy, pb, transposed;
+  int splits;
+};
+
+constexpr int WG_VC = 32;      // voxels per smem chunk
+constexpr int WG_THREADS = 256;
+
+__global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradParams p) {
+  extern __shared__ float smem[];
+  float* xs = smem;                      // [Cin][WG_VC]
+  float* gs = smem + p.Cin * WG_VC;      // [Cout][WG_VC]
+  const int t = blockIdx.x, split = blockIdx.y;
+  const int kz = t / (p.K * p.K), ky = (t / p.K) % p.K, kx = t % p.K;
+  const int oxz = p.transposed ? 0 : kz - p.pb, oxy = p.transposed ? 0 : ky - p.pb, oxx = p.transposed ? 0 : kx - p.pb;
+  const int ogz = p.transposed ? kz - p.pb : 0, ogy = p.transposed ? ky - p.pb : 0, ogx = p.transposed ? kx - p.pb : 0;
+  const long long nb = (long long)p.Bd * p.Bh * p.Bw, total = nb * p.N;
+  const long long per = (total + p.splits - 1) / p.splits;
+  const long long lo = per * split, hi = lo + per < total ? lo + per : total;
+  const int pairs = p.Cin * p.Cout;
+  constexpr int MAXP = 16;  // pairs per thread (Cin*Cout <= 4096)
+  // gradient sums cancel heavily (|sum| << sum|.|): each 32-voxel chunk is accumulated in fp32, the running sum in double
+  double acc[MAXP];
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) acc[i] = 0.0;
+  const long long XHW = (long long)p.Xh * p.Xw, XDHW = XHW * p.Xd, GHW = (long long)p.Gh * p.Gw, GDHW = GHW * p.Gd;
+  for (long long base = lo; base < hi; base += WG_VC) {
+    __syncthreads();
+    // stage WG_VC base positions: a thread owns one voxel column (decoded once) and walks the channel rows
+    {
+      const int vv = threadIdx.x & (WG_VC - 1);
+      const long long L = base + vv;
+      const bool live = L < hi;
+      long long xoff = -1, goff = -1;  // element offsets of channel 0, or -1 when out of range
+      if (live) {
+        const int n = (int)(L / nb);
+        const long long r = L % nb;
+        const int bz = (int)(r / ((long long)p.Bh * p.Bw)), by = (int)((r / p.Bw) % p.Bh), bx = (int)(r % p.Bw);
+        int z = bz * p.sx + oxz, y = by * p.sx + oxy, x = bx * p.sx + oxx;
+        if (z >= 0 && z < p.Xd && y >= 0 && y < p.Xh && x >= 0 && x < p.Xw)
+          xoff = (long long)n * p.Cin * XDHW + z * XHW + (long long)y * p.Xw + x;
+        z = bz * p.sy + ogz; y = by * p.sy + ogy; x = bx * p.sy + ogx;
+        if (z >= 0 && z < p.Gd && y >= 0 && y < p.Gh && x >= 0 && x < p.Gw)
+          goff = (long long)n * p.Cout * GDHW + z * GHW + (long long)y * p.Gw + x;
+      }
+      for (int ch = threadIdx.x / WG_VC; ch < p.Cin + p.Cout; ch += WG_THREADS / WG_VC) {
+        float val = 0.f;
+        if (ch < p.Cin) { if (xoff >= 0) val = p.x[xoff + (long long)ch * XDHW]; }
+        else if (goff >= 0) val = p.g[goff + (long long)(ch - p.Cin) * GDHW];
+        smem[ch * WG_VC + vv] = val;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+      const int pr = threadIdx.x + i * WG_THREADS;
+      if (pr < pairs) {
+        const float* xr = xs + (pr / p.Cout) * WG_VC;
+        const float* gr = gs + (pr % p.Cout) * WG_VC;
+        float a = 0.f;
+#pragma unroll
+        for (int vv = 0; vv < WG_VC; ++vv) a = fmaf(xr[vv], gr[vv], a);
+        acc[i] += (double)a;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXP; ++i) {
+    const int pr = threadIdx.x + i * WG_THREADS;
+    if (pr < pairs) p.partial[((long long)t * p.splits + split) * pairs + pr] = (float)acc[i];
+  }
+}
+
+__global__ void wgrad_finish_kernel(const float* __restrict__ partial, int splits, int pairs, float* __restrict__ dw, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / pairs, pr = i % pairs;
+    double s = 0.0;
+    for (int j = 0; j < splits; ++j) s += (double)partial[(t * splits + j) * pairs + pr];
+    dw[i] = (float)s;
+  }
+}
+
+// db[c] = sum_{n,v} g[n,c,v]; grid (chunks, C) -> partials[c*chunks + chunk]; finish adds in order
+__global__ void bias_grad_kernel(const float* __restrict__ g, double* __restrict__ partials, int N, int C, long long S) {
+  __shared__ double sm[32];
+  const int c = blockIdx.y;
+  double acc = 0.0;
+  const long long total = (long long)N * S;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long n = e / S, i = e % S;
+    acc += (double)g[(n * C + c) * S + i];
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) partials[(long long)c * gridDim.x + blockIdx.x] = acc;
+}
+__global__ void bias_grad_finish_kernel(const double* __restrict__ partials, int chunks, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= (int)gridDim.x * (int)blockDim.x) return;
+  double s = 0.0;
+  for (int j = 0; j < chunks; ++j) s += partials[(long long)c * chunks + j];
+  db[c] = (float)s;
+}
+
+// TF1 AdamOptimizer: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v updates; theta -= lr_t * m / (sqrt(v) + eps)
+__global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+                            float lr_t, float b1, float b2, float eps, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = grad[i];
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+static int grid1d(long long n, int threads, int cap) {
+  long long b = (n + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+static int same_pb(int n, int k, int s) {
+  int out = (n + s - 1) / s, total = (out - 1) * s + k - n;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+}  // namespace pccgeo
+
+using namespace pccgeo;
+
+extern "C" int pccgeo_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream) {
+  PCCGEO_REQUIRE(dy && y && dx && n > 0, "relu_bwd: bad argument");
+  relu_bwd_kernel<<<grid1d(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(dy, y, dx, n);
+  return check_launch("relu_bwd_kernel");
+}
+
+extern "C" int pccgeo_axpby(const float* a, const float* b, float alpha, float beta, float* out, long long n, void* stream) {
+  PCCGEO_REQUIRE(a && out && n > 0, "axpby: bad argument");
+  axpby_kernel<<<grid1d(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(a, b, alpha, beta, out, n);
+  return check_launch("axpby_kernel");
+}
+
+extern "C" int pccgeo_focal_loss_bwd(const float* x_true, const float* x_pred, float gamma, float alpha, float scale, float* dx_pred,
+                                     long long n, void* stream) {
+  PCCGEO_REQUIRE(x_true && x_pred && dx_pred && n > 0, "focal_loss_bwd: bad argument");
+  focal_bwd_kernel<<<grid1d(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(x_true, x_pred, gamma, alpha, scale, dx_pred, n);
+  return check_launch("focal_bwd_kernel");
+}
+
+extern "C" int pccgeo_gc_likelihood_bwd(const float* values, const float* sigma, float scale_min, float c, float* dvalues,
+                                        float* dsigma, long long n, void* stream) {
+  PCCGEO_REQUIRE(values && sigma && dvalues && dsigma && n > 0, "gc_likelihood_bwd: bad argument");
+  gc_bwd_kernel<<<grid1d(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(values, sigma, scale_min, c, dvalues, dsigma, n);
+  return check_launch("gc_bwd_kernel");
+}
+
+extern "C" size_t pccgeo_eb_bwd_ws_doubles(int c) { return (size_t)c * 16 * kEbGradN; }
+
+extern "C" int pccgeo_eb_likelihood_bwd(const float* values, const float* eb_params, float c, float* dvalues, float* dparams,
+                                        double* ws, int n, int ch, int spatial, void* stream) {
+  PCCGEO_REQUIRE(values && eb_params && dvalues && dparams && ws && n > 0 && ch > 0 && spatial > 0, "eb_likelihood_bwd: bad argument");
+  const int chunks = 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  eb_bwd_kernel<<<dim3(chunks, ch), 128, 0, st>>>(values, eb_params, c, dvalues, ws, n, ch, spatial);
+  int rc = check_launch("eb_bwd_kernel");
+  if (rc) return rc;
+  eb_bwd_finish_kernel<<<ch, 64, 0, st>>>(ws, chunks, dparams);
+  return check_launch("eb_bwd_finish_kernel");
+}
+
+extern "C" size_t pccgeo_wgrad_ws_floats(int cin, int cout, int k) {
+  const int taps = k * k * k;
+  int splits = (592 + taps - 1) / taps;
+  return (size_t)taps * splits * cin * cout;
+}
+
+extern "C" int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw, float* ws, int n, int cin, int d, int h, int wd,
+                                       int cout, int k, int stride, int transposed, void* stream) {
+  PCCGEO_REQUIRE(x && g && dw && ws && n > 0 && cin > 0 && cout > 0, "conv3d_wgrad: bad argument");
+  PCCGEO_REQUIRE(cin * cout <= 4096, "conv3d_wgrad: Cin*Cout %d > 4096", cin * cout);
+  PCCGEO_REQUIRE(k >= 1 && k <= 9 && (stride == 1 || stride == 2), "conv3d_wgrad: unsupported geometry");
+  WgradParams p{};
+  p.x = x; p.g = g; p.partial = ws; p.N = n; p.Cin = cin; p.Cout = cout; p.K = k; p.transposed = transposed;
+  p.Xd = d; p.Xh = h; p.Xw = wd;
+  if (!transposed) {
+    p.Gd = (d + stride - 1) / stride; p.Gh = (h + stride - 1) / stride; p.Gw = (wd + stride - 1) / stride;
+    p.Bd = p.Gd; p.Bh = p.Gh; p.Bw = p.Gw; p.sx = stride; p.sy = 1;
+    p.pb = same_pb(d, k, stride);
+    PCCGEO_REQUIRE(same_pb(h, k, stride) == p.pb && same_pb(wd, k, stride) == p.pb, "conv3d_wgrad: dims with different SAME padding");
+  } else {
+    p.Gd = d * stride; p.Gh = h * stride; p.Gw = wd * stride;
+    p.Bd = d; p.Bh = h; p.Bw = wd; p.sx = 1; p.sy = stride;
+    p.pb = same_pb(d * stride, k, stride);
+  }
+  const int taps = k * k * k;
+  p.splits = (592 + taps - 1) / taps;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)(cin + cout) * WG_VC * sizeof(float);
+  wgrad_kernel<<<dim3(taps, p.splits), WG_THREADS, smem, st>>>(p);
+  int rc = check_launch("wgrad_kernel");
+  if (rc) return rc;
+  const long long total = (long long)taps * cin * cout;
+  wgrad_finish_kernel<<<grid1d(total, 256, 148 * 8), 256, 0, st>>>(ws, p.splits, cin * cout, dw, total);
+  return check_launch("wgrad_finish_kernel");
+}
+
+extern "C" int pccgeo_bias_grad_f32(const float* g, float* db, double* ws, int n, int c, long long spatial, void* stream) {
+  PCCGEO_REQUIRE(g && db && ws && n > 0 && c > 0 && spatial > 0, "bias_grad: bad argument");
+  int chunks = kReduceBlocks / c;
+  if (chunks > 16) chunks = 16;
+  PCCGEO_REQUIRE(chunks >= 1, "bias_grad: too many channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  bias_grad_kernel<<<dim3(chunks, c), 256, 0, st>>>(g, ws, n, c, spatial);
+  int rc = check_launch("bias_grad_kernel");
+  if (rc) return rc;
+  bias_grad_finish_kernel<<<1, c, 0, st>>>(ws, chunks, db);
+  return check_launch("bias_grad_finish_kernel");
+}
+
+extern "C" int pccgeo_adam_step(float* theta, const float* grad, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                                long long step, long long n, void* stream) {
+  PCCGEO_REQUIRE(theta && grad && m && v && n > 0 && step >= 1, "adam_step: bad argument");
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  adam_kernel<<<grid1d(n, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, (float)lr_t, beta1, beta2, eps, n);
+  return check_launch("adam_kernel");
+}

@@ -343,7 +343,7 @@ class TransformType(Enum):  # model_transforms.py:161-169
 # ---------------------------------------------------------------------------------------------------------
 # tracing + execution
 # ---------------------------------------------------------------------------------------------------------
-def trace(layer):
+def trace(layer, fuse_residual=True):
     """Flatten a layer tree into steps.  Value ids: 0 is the input.
     ('conv', layer, src, dst, res) with res = id of the residual operand fused into the epilogue (or None);
     ('add', a, b, dst); ('concat', a, b, dst)."""
@@ -366,7 +366,7 @@ def trace(layer):
                 t = rec(sub, t)
             if l.residual_mode == 'add':
                 last = steps[-1]
-                if len(l._layers) > 1 and last[0] == 'conv' and last[3] == t and last[4] is None:
+                if fuse_residual and len(l._layers) > 1 and last[0] == 'conv' and last[3] == t and last[4] is None:
                     last[4] = t1  # fuse: out = t1 + relu(conv(...))
                     return t
                 dst = new_id()

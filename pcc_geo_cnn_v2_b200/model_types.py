@@ -263,7 +263,11 @@ class CompressionModel:
         self.merged_summary = {'loss': self.train_loss, 'fl': self.train_fl, 'mbpov/total': self.train_mbpov,
                                'num_occupied_voxels': n_occ}
         self.step = getattr(self, 'step', 0)
-        self.train_op = None  # backward/optimizer: not part of this round (DESIGN.md "Out of scope / next")
+        # sess.run(m.train_op) of the reference == m.train_op(x): forward + backward + both Adam steps + table refresh
+        from .training import Trainer
+        if getattr(self, 'trainer', None) is None:
+            self.trainer = Trainer(self, gamma, alpha, lmbda)
+        self.train_op = self.trainer.step
         return mb
 
 

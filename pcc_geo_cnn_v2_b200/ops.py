@@ -225,6 +225,72 @@ def focal_loss_sum(x_true, x_pred, gamma, alpha):
     return out
 
 
+# ---- training path ---------------------------------------------------------------------------------------
+def relu_bwd(dy, y):
+    out = torch.empty_like(dy)
+    L.check(L.lib().pccgeo_relu_bwd(L.ptr(dy), L.ptr(y), L.ptr(out), dy.numel(), L.stream_ptr()), 'relu_bwd')
+    return out
+
+
+def axpby(a, b=None, alpha=1.0, beta=1.0):
+    out = torch.empty_like(a)
+    L.check(L.lib().pccgeo_axpby(L.ptr(a), L.ptr(b), float(alpha), float(beta), L.ptr(out), a.numel(), L.stream_ptr()), 'axpby')
+    return out
+
+
+def focal_loss_bwd(x_true, x_pred, gamma, alpha, scale):
+    out = torch.empty_like(x_pred)
+    L.check(L.lib().pccgeo_focal_loss_bwd(L.ptr(_f32c(x_true)), L.ptr(_f32c(x_pred)), float(gamma), float(alpha), float(scale),
+                                          L.ptr(out), x_pred.numel(), L.stream_ptr()), 'focal_loss_bwd')
+    return out
+
+
+def gc_likelihood_bwd(values, sigma, scale_min, c):
+    dv, ds = torch.empty_like(values), torch.empty_like(values)
+    L.check(L.lib().pccgeo_gc_likelihood_bwd(L.ptr(_f32c(values)), L.ptr(_f32c(sigma)), float(scale_min), float(c), L.ptr(dv),
+                                             L.ptr(ds), values.numel(), L.stream_ptr()), 'gc_likelihood_bwd')
+    return dv, ds
+
+
+def eb_likelihood_bwd(values, eb_params, c):
+    """-> (d values, d params (C,44) w.r.t. softplus'ed matrices / biases / tanh'ed factors of the packed block)"""
+    _f32c(values)
+    n, ch = values.shape[:2]
+    sp = values[0, 0].numel()
+    dv = torch.empty_like(values)
+    dp = torch.empty((ch, 44), device=values.device, dtype=torch.float32)
+    ws = torch.empty(int(L.lib().pccgeo_eb_bwd_ws_doubles(ch)), device=values.device, dtype=torch.float64)
+    L.check(L.lib().pccgeo_eb_likelihood_bwd(L.ptr(values), L.ptr(eb_params), float(c), L.ptr(dv), L.ptr(dp), L.ptr(ws), n, ch, sp,
+                                             L.stream_ptr()), 'eb_likelihood_bwd')
+    return dv, dp
+
+
+def conv3d_wgrad_f32(x, g, cout, k, stride, transposed):
+    """-> dW tap-major (k^3, Cin, Cout) of a 'same' conv / transposed conv with input x and pre-activation gradient g"""
+    _f32c(x)
+    _f32c(g)
+    n, cin, d, h, w = x.shape
+    dw = torch.empty((k ** 3, cin, cout), device=x.device, dtype=torch.float32)
+    ws = torch.empty(int(L.lib().pccgeo_wgrad_ws_floats(cin, cout, k)), device=x.device, dtype=torch.float32)
+    L.check(L.lib().pccgeo_conv3d_wgrad_f32(L.ptr(x), L.ptr(g), L.ptr(dw), L.ptr(ws), n, cin, d, h, w, cout, k, stride,
+                                            int(transposed), L.stream_ptr()), 'conv3d_wgrad_f32')
+    return dw
+
+
+def bias_grad_f32(g):
+    _f32c(g)
+    n, c = g.shape[:2]
+    db = torch.empty(c, device=g.device, dtype=torch.float32)
+    L.check(L.lib().pccgeo_bias_grad_f32(L.ptr(g), L.ptr(db), L.ptr(reduce_ws(g.device)), n, c, g[0, 0].numel(), L.stream_ptr()),
+            'bias_grad_f32')
+    return db
+
+
+def adam_step(theta, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    L.check(L.lib().pccgeo_adam_step(L.ptr(theta), L.ptr(grad), L.ptr(m), L.ptr(v), float(lr), float(beta1), float(beta2), float(eps),
+                                     int(step), theta.numel(), L.stream_ptr()), 'adam_step')
+
+
 # ---- host range coder ------------------------------------------------------------------------------------
 def range_encode(symbols, sym_offsets, tables, indexes=None, channel_stride=0, threads=0):
     """symbols int32 (host numpy, concatenated streams); returns list of bytes, one per stream."""

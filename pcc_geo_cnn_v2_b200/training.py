@@ -1,0 +1,235 @@
+"""The tr_train.py hot loop (reference src/model_types.py:250-281 / 327-369, src/tr_train.py:91-134) on the GPU:
+
+    trainer = Trainer(model, gamma, alpha, lmbda)      # == model.train(x, gamma, alpha, lmbda) building the graph
+    out = trainer.step(x)                              # == sess.run(train_op): forward, backward, both Adam steps,
+                                                       #    entropy-bottleneck table refresh
+
+Forward and backward run as fp32 libpccgeo kernels with saved activations (no autograd): data gradients of the convs
+are the forward conv kernels with conv <-> transposed conv swapped, weight / bias gradients, ReLU masks, focal-loss and
+likelihood backward are the kernels of csrc/train.cu.  Both optimisers follow TF1's AdamOptimizer
+(lr_t = lr*sqrt(1-b2^t)/(1-b1^t), theta -= lr_t*m/(sqrt(v)+eps)): Adam(1e-4) on every trainable of the main loss, Adam(1e-3)
+on the entropy bottleneck's quantiles (auxiliary loss).  Whole-batch sums everywhere (FL is sum-reduced and mbpov divides
+by the batch's occupied-voxel count), so multi-GPU training must all-reduce sums, not average per-rank losses.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .entropy_models import GaussianConditional
+from .model_transforms import trace
+
+
+def _softplus(a):
+    return np.logaddexp(0.0, a)
+
+
+def _sigmoid(a):
+    return 1.0 / (1.0 + np.exp(-a))
+
+
+class _HostAdam:
+    """TF1-form Adam on small host arrays (entropy-bottleneck variables)."""
+
+    def __init__(self, arrays, lr):
+        self.lr, self.t = lr, 0
+        self.m = [np.zeros_like(a, np.float64) for a in arrays]
+        self.v = [np.zeros_like(a, np.float64) for a in arrays]
+
+    def step(self, arrays, grads, b1=0.9, b2=0.999, eps=1e-8):
+        self.t += 1
+        lr_t = self.lr * math.sqrt(1 - b2 ** self.t) / (1 - b1 ** self.t)
+        for a, g, m, v in zip(arrays, grads, self.m, self.v):
+            g = np.asarray(g, np.float64)
+            m *= b1
+            m += (1 - b1) * g
+            v *= b2
+            v += (1 - b2) * g * g
+            a -= (lr_t * m / (np.sqrt(v) + eps)).astype(a.dtype)
+
+
+class Trainer:
+    def __init__(self, model, gamma=2, alpha=0.9, lmbda=1e-4, lr=1e-4, aux_lr=1e-3):
+        self.model, self.gamma, self.alpha, self.lmbda, self.lr = model, gamma, alpha, lmbda, lr
+        self.v2 = hasattr(model, 'hyper_analysis_transform')
+        self.transforms = model.transforms()
+        self.traces = {k: trace(t, fuse_residual=False) for k, t in self.transforms.items()}
+        self.params = {}   # layer -> dict(w, b, mw, vw, mb, vb) device fp32, tap-major weights
+        self.t = 0
+        eb = model.entropy_bottleneck
+        self._eb_arrays = lambda: eb.matrices + eb.biases + eb.factors
+        self.eb_adam = None
+        self.aux_adam = None
+        self.aux_lr = aux_lr
+
+    # -- parameters ------------------------------------------------------------------------------------
+    def _p(self, layer, in_channels):
+        if layer not in self.params:
+            layer.build(in_channels)
+            w = layer.dev('w_tap').clone()
+            b = layer.dev('bias')
+            p = {'w': w, 'b': None if b is None else b.clone(), 'mw': torch.zeros_like(w), 'vw': torch.zeros_like(w)}
+            if b is not None:
+                p['mb'], p['vb'] = torch.zeros_like(b), torch.zeros_like(b)
+            self.params[layer] = p
+        return self.params[layer]
+
+    def sync_to_model(self):
+        """Copy the trained device parameters back into the layers (Keras layouts) so the codec path sees them."""
+        for layer, p in self.params.items():
+            w = p['w'].cpu().numpy().reshape(layer.k, layer.k, layer.k, layer.in_channels, layer.filters)
+            if layer.transposed:
+                w = w.transpose(0, 1, 2, 4, 3)
+            layer.set_weights(np.ascontiguousarray(w), None if p['b'] is None else p['b'].cpu().numpy())
+        self.model.entropy_bottleneck._invalidate()
+
+    # -- forward / backward through one transform --------------------------------------------------------
+    def _forward(self, name, x):
+        steps, out_id = self.traces[name]
+        vals = {0: x}
+        for s in steps:
+            if s[0] == 'conv':
+                _, layer, src, dst, _ = s
+                p = self._p(layer, vals[src].shape[1])
+                vals[dst] = ops.conv3d_f32(vals[src], p['w'], p['b'], layer.filters, layer.k, layer.stride, layer.transposed, layer.relu)
+            elif s[0] == 'add':
+                vals[s[3]] = ops.axpby(vals[s[1]], vals[s[2]], 1.0, 1.0)
+            else:
+                raise NotImplementedError("residual_mode='concat' is not used by any reference config; training supports 'add'")
+        return vals[out_id], (steps, out_id, vals)
+
+    def _backward(self, tape, g_out, grads, need_input_grad=True):
+        steps, out_id, vals = tape
+        g = {out_id: g_out}
+
+        def accumulate(vid, t):
+            g[vid] = t if vid not in g else ops.axpby(g[vid], t, 1.0, 1.0)
+
+        for s in reversed(steps):
+            if s[0] == 'add':
+                gd = g.pop(s[3])
+                accumulate(s[1], gd)
+                accumulate(s[2], gd)
+                continue
+            _, layer, src, dst, _ = s
+            gd = g.pop(dst)
+            if layer.relu:
+                gd = ops.relu_bwd(gd, vals[dst])
+            p = self.params[layer]
+            x_in = vals[src]
+            grads[layer] = {'w': ops.conv3d_wgrad_f32(x_in, gd, layer.filters, layer.k, layer.stride, layer.transposed),
+                            'b': ops.bias_grad_f32(gd) if p['b'] is not None else None}
+            if src != 0 or need_input_grad:
+                # data gradient = the adjoint layer: conv <-> transposed conv, tap-major weights with the channel axes swapped
+                w_t = p['w'].transpose(1, 2).contiguous()
+                gx = ops.conv3d_f32(gd, w_t, None, layer.in_channels, layer.k, layer.stride, not layer.transposed, False, g.pop(src, None))
+                g[src] = gx
+        return g.get(0)
+
+    # -- entropy bottleneck helpers (host float64; C x 3 values) ----------------------------------------
+    def _aux_loss_and_grad(self):
+        """EntropyBottleneck.losses[0] = sum |logits(quantiles) - (-T,0,T)| and its gradient w.r.t. the quantiles
+        (matrices / biases / factors are stop-gradient'ed in tfc)."""
+        eb = self.model.entropy_bottleneck
+        q = eb.quantiles.astype(np.float64)             # (C,1,3)
+        target = math.log(2.0 / eb.tail_mass - 1.0)
+        tgt = np.array([-target, 0.0, target])
+        logits = q
+        dl = np.ones_like(q)                            # d logits / d q, carried through the chain (per element)
+        for i in range(len(eb.matrices)):
+            M = _softplus(eb.matrices[i].astype(np.float64))
+            pre = np.matmul(M, logits) + eb.biases[i].astype(np.float64)
+            dpre = np.matmul(M, dl) if i > 0 else M * dl  # first layer: (C,3,1) x (C,1,3)
+            if i < len(eb.factors):
+                F = np.tanh(eb.factors[i].astype(np.float64))
+                th = np.tanh(pre)
+                logits = pre + F * th
+                dl = dpre * (1.0 + F * (1.0 - th * th))
+            else:
+                logits, dl = pre, dpre
+        diff = logits - tgt
+        return float(np.abs(diff).sum()), (np.sign(diff) * dl).astype(np.float64)
+
+    def _eb_raw_grads(self, dparams):
+        """kernel gradients w.r.t. softplus(M), B, tanh(F) (C,44) -> gradients of the raw tfc variables."""
+        eb = self.model.entropy_bottleneck
+        C = eb.channels
+        d = dparams.cpu().numpy().astype(np.float64)
+        spl = [d[:, 0:3].reshape(C, 3, 1), d[:, 3:12].reshape(C, 3, 3), d[:, 12:21].reshape(C, 3, 3), d[:, 21:24].reshape(C, 1, 3)]
+        gm = [g * _sigmoid(m.astype(np.float64)) for g, m in zip(spl, eb.matrices)]
+        gb = [d[:, 24:27].reshape(C, 3, 1), d[:, 27:30].reshape(C, 3, 1), d[:, 30:33].reshape(C, 3, 1), d[:, 33:34].reshape(C, 1, 1)]
+        gf = [d[:, 34 + 3 * i:37 + 3 * i].reshape(C, 3, 1) * (1.0 - np.tanh(eb.factors[i].astype(np.float64)) ** 2) for i in range(3)]
+        return gm + gb + gf
+
+    # -- one step ----------------------------------------------------------------------------------------
+    def forward_backward(self, x, noise_y=None, noise_z=None):
+        """Returns (values dict, grads dict): loss / fl / mbpov as python floats; grads[layer] = {'w','b'} (tap-major),
+        grads['entropy_bottleneck'] = list of raw-variable gradients (matrices, biases, factors)."""
+        m = self.model
+        x = x.contiguous().float()
+        eb = m.entropy_bottleneck
+        grads = {}
+        y, tape_a = self._forward('analysis', x)
+        n_occ = float(x.sum(dtype=torch.float64))
+        c = 1.0 / (-math.log(2.0) * n_occ)                 # d mbpov / d (sum ln p)
+        if noise_y is None:
+            noise_y = torch.rand_like(y) - 0.5
+        y_tilde = ops.axpby(y, noise_y.contiguous().float(), 1.0, 1.0)
+        ebp = eb.device_params()
+        if self.v2:
+            z, tape_ha = self._forward('hyper_analysis', y)
+            if noise_z is None:
+                noise_z = torch.rand_like(z) - 0.5
+            z_tilde = ops.axpby(z, noise_z.contiguous().float(), 1.0, 1.0)
+            _, sum_z = ops.eb_likelihood(z_tilde, ebp, want_likelihood=False)
+            sigma, tape_hs = self._forward('hyper_synthesis', z_tilde)
+            smin = float(np.float32(m.scale_table[0]))
+            _, sum_y = ops.gc_likelihood(y_tilde, sigma, smin, want_likelihood=False)
+        else:
+            _, sum_y = ops.eb_likelihood(y_tilde, ebp, want_likelihood=False)
+        x_tilde, tape_s = self._forward('synthesis', y_tilde)
+        fl = float(ops.focal_loss_sum(x, x_tilde, self.gamma, self.alpha)[0])
+        mb_y = float(sum_y[0]) * c
+        mb_z = float(sum_z[0]) * c if self.v2 else 0.0
+        values = {'fl': fl, 'mbpov_y': mb_y, 'mbpov_z': mb_z, 'mbpov': mb_y + mb_z, 'loss': self.lmbda * fl + mb_y + mb_z,
+                  'num_occupied_voxels': n_occ, 'x_tilde': x_tilde, 'y': y}
+        # ---- backward
+        g_xt = ops.focal_loss_bwd(x, x_tilde, self.gamma, self.alpha, self.lmbda)
+        g_y = self._backward(tape_s, g_xt, grads)
+        if self.v2:
+            dv, dsig = ops.gc_likelihood_bwd(y_tilde, sigma, smin, c)
+            g_y = ops.axpby(g_y, dv, 1.0, 1.0)
+            g_z = self._backward(tape_hs, dsig, grads)
+            dz, dpar = ops.eb_likelihood_bwd(z_tilde, ebp, c)
+            g_z = ops.axpby(g_z, dz, 1.0, 1.0)
+            g_y = ops.axpby(g_y, self._backward(tape_ha, g_z, grads), 1.0, 1.0)
+        else:
+            dv, dpar = ops.eb_likelihood_bwd(y_tilde, ebp, c)
+            g_y = ops.axpby(g_y, dv, 1.0, 1.0)
+        self._backward(tape_a, g_y, grads, need_input_grad=False)
+        grads['entropy_bottleneck'] = self._eb_raw_grads(dpar)
+        return values, grads
+
+    def step(self, x, noise_y=None, noise_z=None):
+        """sess.run(train_op): main Adam step, auxiliary Adam step on the quantiles, CDF-table refresh."""
+        values, grads = self.forward_backward(x, noise_y, noise_z)
+        self.t += 1
+        for layer, p in self.params.items():
+            gl = grads[layer]
+            ops.adam_step(p['w'], gl['w'], p['mw'], p['vw'], self.lr, self.t)
+            if p['b'] is not None:
+                ops.adam_step(p['b'], gl['b'], p['mb'], p['vb'], self.lr, self.t)
+        eb = self.model.entropy_bottleneck
+        arrays = self._eb_arrays()
+        if self.eb_adam is None:
+            self.eb_adam = _HostAdam(arrays, self.lr)
+            self.aux_adam = _HostAdam([eb.quantiles], self.aux_lr)
+        aux, gq = self._aux_loss_and_grad()
+        self.eb_adam.step(arrays, grads['entropy_bottleneck'])
+        self.aux_adam.step([eb.quantiles], [gq])
+        eb._invalidate()
+        eb.updates[0]()                                   # entropy_bottleneck.updates[0]: refresh the quantised CDFs
+        values['aux_loss'] = aux
+        values['step'] = self.t
+        return values
