@@ -91,3 +91,26 @@ def test_pmf_to_quantized_cdf_cpp_matches_oracle():
         p = rng.random(n) ** 6
         p /= p.sum() * rng.uniform(0.9, 1.1)
         assert np.array_equal(ops.pmf_to_quantized_cdf(p), E.pmf_to_quantized_cdf(p))
+
+
+def test_long_tail_of_near_certain_symbols_round_trips(gc_tab):
+    """Regression: (a) thousands of ~probability-1 symbols cost nothing; (b) a tail of symbols whose CDF lower bound is 0
+    (the leftmost bin of a narrow table) emits only zero bytes, which the encoder strips -- the decoder must read implicit
+    zeros far past the end of the string (it once flagged more than 8 such bytes as a corrupt stream)."""
+    rng = np.random.default_rng(11)
+    head = 300
+    sym = np.zeros(30000, np.int32)
+    idx = np.zeros(30000, np.int32)                       # scale index 0 (sigma 0.11): p(0) ~ 1
+    idx[:head] = rng.integers(20, 40, size=head)
+    sym[:head] = np.rint(rng.normal(size=head) * 20).astype(np.int32)
+    sym[-60:] = gc_tab['offset'][0]                       # value 0 of table 0: lower bound 0, ~2 zero bytes each
+    offs = np.array([0, len(sym)], np.int64)
+    s = ops.range_encode(sym, offs, gc_tab, indexes=idx)
+    assert len(s[0]) < 1500                               # neither the certain symbols nor the zero-byte tail add length
+    assert np.array_equal(ops.range_decode(s, offs, gc_tab, indexes=idx), sym)
+    small = slice(0, 3000)
+    want = RC.unbounded_index_range_encode(sym[small], idx[small], gc_tab['cdf'], gc_tab['cdf_length'], gc_tab['offset'])
+    got = ops.range_encode(sym[small], np.array([0, 3000], np.int64), gc_tab, indexes=idx[small])[0]
+    assert got == want
+    assert np.array_equal(RC.unbounded_index_range_decode(want, idx[small], gc_tab['cdf'], gc_tab['cdf_length'], gc_tab['offset']),
+                          sym[small])
