@@ -38,7 +38,7 @@ LAYER_MMAC = 1811.94  # s.b2.t1 / s.b2.t2: 16->16 channels, 64^3 voxels, 27 taps
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--blocks', type=int, default=32, help='blocks per step per GPU')
