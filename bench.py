@@ -288,7 +288,7 @@ def main():
     del xin
 
     # ---- e2e through the public API: host blocks in, strings out, strings in, host points out ----
-    EB = 4  # batches per e2e step: the block loops pipeline batches (host coding of batch i overlaps GPU work of batch i+1)
+    EB = 8  # batches per e2e step: the block loops pipeline batches (host coding of batch i overlaps GPU work of batch i+1)
     e2e_blocks = blocks * EB
 
     def e2e_step():

@@ -82,12 +82,19 @@ struct Decoder {
       range <<= 8;
     }
   }
-  inline int decode(const int32_t* cdf, int n, int precision) {
+  // lut (optional, 256 entries): lut[b] = largest symbol s with cdf[s] <= (b << (precision-8)); the search then scans
+  // forward from there -- for the peaked tables of this codec that is 0-2 steps instead of an 11-step binary search.
+  inline int decode(const int32_t* cdf, int n, int precision, const uint16_t* lut = nullptr) {
     const uint32_t r = range >> precision;
     uint32_t value = code / r;
     const uint32_t maxv = (1u << precision) - 1;
     if (value > maxv) value = maxv;
     int lo = 0, hi = n;
+    if (lut) {
+      lo = lut[value >> (precision - 8)];
+      while (lo + 1 < n && (uint32_t)cdf[lo + 1] <= value) ++lo;
+      hi = lo + 1;
+    }
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
       if ((uint32_t)cdf[mid] <= value) lo = mid; else hi = mid;
@@ -120,6 +127,7 @@ struct Tables {
   int rows;
   int index_mode;
   long long channel_stride;
+  const uint16_t* lut = nullptr;  // (rows, 256) decoder search accelerators, or null
   inline int index(const int32_t* idx, long long pos) const {
     return index_mode == 0 ? idx[pos] : (int)((pos / channel_stride) % rows);
   }
@@ -169,7 +177,7 @@ bool decode_stream(const Tables& t, const uint8_t* b, const uint8_t* e, const in
     if (row_i < 0 || row_i >= t.rows) return false;
     const int32_t* row = t.cdf + (long long)row_i * t.cdf_stride;
     const int32_t max_value = t.cdf_length[row_i] - 2;
-    long long value = dec.decode(row, max_value + 1, kPrecision);
+    long long value = dec.decode(row, max_value + 1, kPrecision, t.lut ? t.lut + (long long)row_i * 256 : nullptr);
     if (value == max_value) {
       int widths = 0;
       for (;;) {
@@ -263,6 +271,19 @@ extern "C" int pccgeo_range_decode_host(const uint8_t* bytes, const long long* b
   static const uint8_t kEmpty = 0;
   const uint8_t* base = bytes ? bytes : &kEmpty;
   Tables t{cdf, cdf_stride, cdf_length, offset, rows, index_mode, channel_stride};
+  // per-row search accelerators: lut[r][b] = largest s in [0, n) with cdf[s] <= b << 8
+  std::vector<uint16_t> lut((size_t)rows * 256);
+  for (int r = 0; r < rows; ++r) {
+    const int32_t* row = cdf + (long long)r * cdf_stride;
+    const int n = cdf_length[r] - 1;  // symbols incl. the escape slot
+    int s = 0;
+    for (int b = 0; b < 256; ++b) {
+      const int32_t v = b << (kPrecision - 8);
+      while (s + 1 < n && row[s + 1] <= v) ++s;
+      lut[(size_t)r * 256 + b] = (uint16_t)s;
+    }
+  }
+  t.lut = lut.data();
   std::atomic<int> bad{0};
   parallel_for(nstreams, threads, [&](int i) {
     const long long a = sym_offsets[i], b = sym_offsets[i + 1];

@@ -35,14 +35,16 @@ def sparse_to_dense(block, x_shape, data_format='channels_first'):
 
 def blocks_to_coords(blocks):
     """list of (n_i, >=3) arrays -> one int16 (sum n_i, 4) array of (block, z, y, x) rows."""
-    rows = []
-    for j, b in enumerate(blocks):
-        b = np.asarray(b)
-        c = np.empty((len(b), 4), np.int16)
-        c[:, 0] = j
-        c[:, 1:] = b[:, :3].astype(np.int16)
-        rows.append(c)
-    return np.ascontiguousarray(np.concatenate(rows, axis=0)) if rows else np.zeros((0, 4), np.int16)
+    if not len(blocks):
+        return np.zeros((0, 4), np.int16)
+    lens = [len(b) for b in blocks]
+    out = np.empty((sum(lens), 4), np.int16)
+    out[:, 0] = np.repeat(np.arange(len(blocks), dtype=np.int16), lens)
+    pos = 0
+    for b, n in zip(blocks, lens):  # one slice assignment per block (float -> int16 cast inside numpy)
+        out[pos:pos + n, 1:] = np.asarray(b)[:, :3]
+        pos += n
+    return out
 
 
 def bits_to_points(bits_host, shape):
