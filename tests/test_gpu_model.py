@@ -69,7 +69,7 @@ def test_blocks_shape_contracts_on_gpu():
         MT.AnalysisBlock(1, data_format='channels_last')(torch.zeros((1, 8, 8, 8, 1)))   # CPU tensor: no fallback
 
 
-@pytest.mark.parametrize('fixture', sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, '*.npz'))))
+@pytest.mark.parametrize('fixture', sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, 'c[0-9]*_*.npz'))))
 @pytest.mark.parametrize('precision', ['bf16x3', 'fp32'])
 def test_golden_fixture(fixture, precision):
     g = np.load(os.path.join(GOLDEN, fixture))
