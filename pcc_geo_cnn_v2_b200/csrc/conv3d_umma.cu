@@ -20,6 +20,12 @@
 //               A-operand shared-memory reads -- the bound for small Cout -- by 3x.
 //   warps 2..9  epilogue: two groups of four warps (one per TMEM lane quadrant) alternate over finished planes:
 //               tcgen05.ld -> +bias -> ReLU -> +residual -> bf16 (hi[/lo]) -> 16-byte coalesced global stores.
+// UP = 2 (stride-2 transposed conv, SynthesisBlock's first layer): output o = 2*i + j per dimension (TF 'SAME', even sizes),
+//   so even outputs take taps j=0 (input i) and j=2 (input i-1), odd outputs tap j=1 (input i).  The M tile is 128 INPUT
+//   voxels; the four (y,x) parity classes of an output plane sit side by side in one TMEM slot (4*Cout columns), input
+//   plane z feeds output planes 2z, 2z+1, 2z+2 (taps kz = 0,1,2) and ONE MMA per input shift (dy,dx) in {0,-1}^2 carries
+//   all 3 planes x 4 classes (N = 12*Cout; classes that have no tap at that shift get zero weights) -- 4 MMAs per
+//   k-chunk and precision pair instead of the 27 small ones of the gather kernel.
 // Precision terms: terms=1 plain bf16 operands; terms=2 splits activations and weights into hi+lo bf16 and
 // issues a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into the same fp32 accumulator (fp32-class accuracy, 3x MMA work).
 #include <cuda.h>
@@ -71,9 +77,12 @@ struct __align__(8) SmemHeader {
 constexpr int HEADER_BYTES = 1024;
 static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "header too large");
 
-template <int COUT, int TERMS, int KC>  // padded output channels (16,32,64); precision terms (1,2); Cin/16 (1,2,4)
+// padded output channels (16,32,64); precision terms (1,2); Cin/16 (1,2,4); UP = 1 (stride 1) or 2 (stride-2 transposed)
+template <int COUT, int TERMS, int KC, int UP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvParams p) {
+  constexpr int SC = UP == 2 ? 4 * COUT : COUT;   // TMEM columns of one output-plane slot
+  constexpr int NSHIFT = UP == 2 ? 4 : 9;         // distinct (y,x) input shifts = MMAs per k-chunk and precision pair
   extern __shared__ __align__(1024) uint8_t smem[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,7 +90,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
   uint8_t* wsm = smem + HEADER_BYTES;
   const int stage_bytes = p.terms * p.CGi * PLANE_CG_BYTES;
   uint8_t* stages = wsm + ((wbytes_all + 127) & ~127);
-  const int tmem_cols = p.nslots * COUT;                      // power of two >= 32 (host guarantees)
+  const int tmem_cols = p.nslots * SC;                        // power of two >= 32 (host guarantees)
 
   // ---- one-time setup ----
   if (warp == 0 && lane == 0) {
@@ -128,10 +137,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
     // branches on data: per input plane we precompute <= 2 accumulator segments (split only where the TMEM ring
     // wraps) and every descriptor is a 64-bit add on a per-plane base.
     const uint32_t lbo_a = p.swap ? ROW_PITCH : PLANE_CG_BYTES, sbo_a = p.swap ? PLANE_CG_BYTES : ROW_PITCH;
-    constexpr uint32_t b_kcore = 3 * (COUT / 8) * 128;  // bytes between the two K core matrices of a B tile
+    constexpr uint32_t b_kcore = 3 * (SC / 8) * 128;  // bytes between the two K core matrices of a B tile
     const uint32_t lbo_b = p.swap ? 128 : b_kcore, sbo_b = p.swap ? b_kcore : 128;
-    constexpr uint32_t b_tile16 = 2 * b_kcore / 16;     // one (ky,kx,kc) tile, in 16-byte units
-    constexpr uint32_t b_plane16 = (COUT / 8) * 128 / 16;  // one stacked z-tap (COUT rows), in 16-byte units
+    constexpr uint32_t b_tile16 = 2 * b_kcore / 16;     // one (shift,kc) tile, in 16-byte units
+    constexpr uint32_t b_plane16 = (SC / 8) * 128 / 16; // one stacked output plane (SC rows), in 16-byte units
     constexpr int npairs = TERMS == 2 ? 3 : 1;
     const uint32_t slot_mask = p.nslots - 1;             // nslots is a power of two
     const uint64_t bdesc0 = make_smem_desc(smem_u32(wsm), lbo_b, sbo_b);
@@ -140,22 +149,25 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
     const uint32_t a_hi = (uint32_t)(adesc_proto >> 32), a_lo_proto = (uint32_t)adesc_proto;
     const uint32_t a_term16 = p.CGi * PLANE_CG_BYTES / 16, w_term16 = p.wbytes_term / 16;
     const uint32_t stage16 = stage_bytes / 16, stages16 = smem_u32(stages) / 16;
+    const int Dout = D * UP;
     uint32_t s = 0, in_phase = 0;  // input stage ring position / phase
     uint32_t g0 = 0;               // running output-plane counter at the start of this item
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += D) {
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += Dout) {
       for (int z = 0; z < D; ++z) {
         mbar_wait(smem_u32(&hdr->in_full[s]), in_phase);
-        const int pa = z > 0 ? z - 1 : 0, pb = z + 1 < D ? z + 1 : D - 1;  // output planes touched by input plane z
-        // planes touched for the first time by this input plane: z+1 (if it exists), and plane 0 when z == 0.  Their
-        // TMEM slots were zeroed by the epilogue when it drained the previous tenant (or at kernel start), so every MMA
-        // below accumulates and all MMAs of a plane have one shape: no accumulate=0 special cases that drain the pipe.
-        if (z == 0) {
-          const uint32_t g = g0;
-          mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), (g >> p.slot_shift) & 1);
-        }
-        if (z + 1 < D) {
-          const uint32_t g = g0 + z + 1;
-          mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), (g >> p.slot_shift) & 1);
+        // output planes touched by input plane z: pfirst .. pfirst+2, clipped to the volume
+        const int pfirst = UP == 2 ? 2 * z : z - 1;
+        const int pa = pfirst > 0 ? pfirst : 0, pb = pfirst + 2 < Dout ? pfirst + 2 : Dout - 1;
+        // planes touched for the first time by this input plane (UP=1: z+1; UP=2: 2z+1, 2z+2; plus plane 0 when z == 0).
+        // Their TMEM slots were zeroed by the epilogue when it drained the previous tenant (or at kernel start), so every
+        // MMA below accumulates and all MMAs of a plane have one shape: no accumulate=0 special cases that drain the pipe.
+        auto wait_empty = [&](uint32_t g) { mbar_wait(smem_u32(&hdr->acc_empty[g & slot_mask]), (g >> p.slot_shift) & 1); };
+        if (z == 0) wait_empty(g0);
+        if (UP == 2) {
+          wait_empty(g0 + 2 * z + 1);
+          if (z + 1 < D) wait_empty(g0 + 2 * z + 2);
+        } else {
+          if (z + 1 < D) wait_empty(g0 + z + 1);
         }
         tc_fence_after();
         const uint32_t a_lo0 = a_lo_proto + stages16 + s * stage16;
@@ -163,36 +175,39 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
         const uint32_t slot_a = (g0 + pa) & slot_mask;
         const int nplanes = pb - pa + 1;
         const int n0 = min(nplanes, (int)(p.nslots - slot_a));   // planes before the wrap
-        const uint32_t j0 = pa - (z - 1);                         // stacked-tap index of plane pa (0 or 1)
-        const uint32_t seg_d0 = tmem_base + slot_a * COUT, seg_b0 = b_lo0 + j0 * b_plane16, seg_i0 = make_idesc(n0 * COUT);
-        const uint32_t seg_d1 = tmem_base, seg_b1 = b_lo0 + (j0 + n0) * b_plane16, seg_i1 = make_idesc((nplanes - n0) * COUT);
+        const uint32_t j0 = pa - pfirst;                          // stacked index of plane pa
+        const uint32_t seg_d0 = tmem_base + slot_a * SC, seg_b0 = b_lo0 + j0 * b_plane16, seg_i0 = make_idesc(n0 * SC);
+        const uint32_t seg_d1 = tmem_base, seg_b1 = b_lo0 + (j0 + n0) * b_plane16, seg_i1 = make_idesc((nplanes - n0) * SC);
         const bool two = n0 < nplanes;
         if (elect_one()) {
           if (!two) {
 #pragma unroll
-            for (int kyx = 0; kyx < 9; ++kyx) {
-              const uint32_t a_kyx16 = ((kyx / 3) * ROW_PITCH + (kyx % 3) * 16) / 16;
+            for (int sh = 0; sh < NSHIFT; ++sh) {
+              // UP=1: taps (ky,kx) read the halo'd plane at (ky,kx); UP=2: shifts (dy,dx) in {0,-1} read it at (1+dy,1+dx)
+              const uint32_t a_sh16 = UP == 2 ? ((1 - sh / 2) * ROW_PITCH + (1 - sh % 2) * 16) / 16
+                                              : ((sh / 3) * ROW_PITCH + (sh % 3) * 16) / 16;
 #pragma unroll
               for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
                 for (int pr = 0; pr < npairs; ++pr) {
                   const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-                  umma_bf16_lh(seg_d0, a_lo0 + a_kyx16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16), a_hi,
-                               seg_b0 + tb * w_term16 + (uint32_t)(kyx * KC + kc) * b_tile16, b_hi, seg_i0, 1u);
+                  umma_bf16_lh(seg_d0, a_lo0 + a_sh16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16), a_hi,
+                               seg_b0 + tb * w_term16 + (uint32_t)(sh * KC + kc) * b_tile16, b_hi, seg_i0, 1u);
                 }
               }
             }
           } else {
 #pragma unroll
-            for (int kyx = 0; kyx < 9; ++kyx) {
-              const uint32_t a_kyx16 = ((kyx / 3) * ROW_PITCH + (kyx % 3) * 16) / 16;
+            for (int sh = 0; sh < NSHIFT; ++sh) {
+              const uint32_t a_sh16 = UP == 2 ? ((1 - sh / 2) * ROW_PITCH + (1 - sh % 2) * 16) / 16
+                                              : ((sh / 3) * ROW_PITCH + (sh % 3) * 16) / 16;
 #pragma unroll
               for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
                 for (int pr = 0; pr < npairs; ++pr) {
                   const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-                  const uint32_t a_lo = a_lo0 + a_kyx16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16);
-                  const uint32_t b_off = tb * w_term16 + (uint32_t)(kyx * KC + kc) * b_tile16;
+                  const uint32_t a_lo = a_lo0 + a_sh16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16);
+                  const uint32_t b_off = tb * w_term16 + (uint32_t)(sh * KC + kc) * b_tile16;
                   umma_bf16_lh(seg_d0, a_lo, a_hi, seg_b0 + b_off, b_hi, seg_i0, 1u);
                   umma_bf16_lh(seg_d1, a_lo, a_hi, seg_b1 + b_off, b_hi, seg_i1, 1u);
                 }
@@ -200,8 +215,14 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
             }
           }
           umma_commit(smem_u32(&hdr->in_empty[s]));  // input stage may be refilled once these MMAs retire
-          if (z >= 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z - 1) & slot_mask]));
-          if (z == D - 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z) & slot_mask]));
+          if (UP == 2) {
+            // planes 2z and 2z+1 are complete (2z+2 still needs tap 0 of input plane z+1)
+            umma_commit(smem_u32(&hdr->acc_full[(g0 + 2 * z) & slot_mask]));
+            umma_commit(smem_u32(&hdr->acc_full[(g0 + 2 * z + 1) & slot_mask]));
+          } else {
+            if (z >= 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z - 1) & slot_mask]));
+            if (z == D - 1) umma_commit(smem_u32(&hdr->acc_full[(g0 + z) & slot_mask]));
+          }
         }
         __syncwarp();
         if (++s == (uint32_t)p.nstage) { s = 0; in_phase ^= 1; }
@@ -217,75 +238,80 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
     float bias_r[COUT];
 #pragma unroll
     for (int c = 0; c < COUT; ++c) bias_r[c] = (p.bias && c < p.cout_real) ? __ldg(p.bias + c) : 0.f;
-    const long long HW = (long long)p.H * p.W, DHW = HW * D;
+    const int Dout = D * UP, Wo = p.W * UP;
+    const long long HWo = (long long)p.H * UP * Wo, DHWo = HWo * Dout;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     // zero every accumulator slot this group owns (slot parity == group) and publish it as empty: completes phase 0 of
     // acc_empty, which is what the MMA issuer waits for before the first use of a slot
     for (int slot = grp; slot < p.nslots; slot += 2) {
 #pragma unroll
-      for (int c = 0; c < COUT; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * COUT + c);
+      for (int c = 0; c < SC; c += 16) tmem_st16_zero(lane_base + (uint32_t)slot * SC + c);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[slot]));
     }
     uint32_t g0 = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += D) {
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, g0 += Dout) {
       const int xt = item % p.xtiles, yt = (item / p.xtiles) % p.ytiles, n = item / (p.xtiles * p.ytiles);
-      const long long vox0 = (long long)(yt * TY + yl) * p.W + (xt * TX + xl);
-      for (int pl = 0; pl < D; ++pl) {
+      const long long vox0 = (long long)((yt * TY + yl) * UP) * Wo + (xt * TX + xl) * UP;
+      for (int pl = 0; pl < Dout; ++pl) {
         const uint32_t g = g0 + pl;
         if ((int)(g & 1) != grp) continue;
         const int slot = g & (p.nslots - 1);
         mbar_wait(smem_u32(&hdr->acc_full[slot]), (g >> p.slot_shift) & 1);
         tc_fence_after();
-        uint32_t r[COUT];
+        uint32_t r[SC];
 #pragma unroll
-        for (int c = 0; c < COUT; c += 16) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * COUT + c, r + c);
+        for (int c = 0; c < SC; c += 16) tmem_ld16(lane_base + (uint32_t)slot * SC + c, r + c);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < COUT; c += 16) tmem_st16_zero(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)slot * COUT + c);
+        for (int c = 0; c < SC; c += 16) tmem_st16_zero(lane_base + (uint32_t)slot * SC + c);
         tmem_st_wait();  // the slot is handed back zeroed: its next tenant only ever accumulates
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[slot]));  // accumulator slot is free again
-        float v[COUT];
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-          v[c] = __uint_as_float(r[c]) + bias_r[c];
-          if (p.relu) v[c] = fmaxf(v[c], 0.f);
-        }
-        const long long vox = (long long)pl * HW + vox0;
-        if (p.res) {
-          for (int t = 0; t < p.terms; ++t)
+        for (int cls = 0; cls < SC / COUT; ++cls) {   // UP=2: (y,x) parity classes of this input voxel's 2x2 outputs
+          float v[COUT];
 #pragma unroll
-            for (int cg = 0; cg < COUT / 8; ++cg) {
-              const long long e = t * p.term_stride_out + (((long long)n * p.CGo + cg) * DHW + vox) * 8;
-              const int4 qv = __ldg(reinterpret_cast<const int4*>(p.res + e));
-              unpack_bf16x8_add(qv, v + cg * 8);
-            }
-        }
-#pragma unroll
-        for (int cg = 0; cg < COUT / 8; ++cg) {
-          const long long e = (((long long)n * p.CGo + cg) * DHW + vox) * 8;
-          float* vv = v + cg * 8;
-          __nv_bfloat16 hi[8];
-          int4 qh;
-          uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) hi[i] = __float2bfloat16_rn(vv[i]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 t2 = __halves2bfloat162(hi[2 * i], hi[2 * i + 1]);
-            qh32[i] = *reinterpret_cast<uint32_t*>(&t2);
+          for (int c = 0; c < COUT; ++c) {
+            v[c] = __uint_as_float(r[cls * COUT + c]) + bias_r[c];
+            if (p.relu) v[c] = fmaxf(v[c], 0.f);
           }
-          *reinterpret_cast<int4*>(p.y + e) = qh;
-          if (TERMS == 2) {
-            int4 ql;
-            uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+          const long long vox = (long long)pl * HWo + vox0 + (UP == 2 ? (long long)(cls >> 1) * Wo + (cls & 1) : 0);
+          if (p.res) {
+            for (int t = 0; t < p.terms; ++t)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              ql32[i] = pack_bf16x2(vv[2 * i] - __bfloat162float(hi[2 * i]), vv[2 * i + 1] - __bfloat162float(hi[2 * i + 1]));
-            *reinterpret_cast<int4*>(p.y + p.term_stride_out + e) = ql;
+              for (int cg = 0; cg < COUT / 8; ++cg) {
+                const long long e = t * p.term_stride_out + (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
+                const int4 qv = __ldg(reinterpret_cast<const int4*>(p.res + e));
+                unpack_bf16x8_add(qv, v + cg * 8);
+              }
+          }
+#pragma unroll
+          for (int cg = 0; cg < COUT / 8; ++cg) {
+            const long long e = (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
+            float* vv = v + cg * 8;
+            __nv_bfloat16 hi[8];
+            int4 qh;
+            uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hi[i] = __float2bfloat16_rn(vv[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 t2 = __halves2bfloat162(hi[2 * i], hi[2 * i + 1]);
+              qh32[i] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            *reinterpret_cast<int4*>(p.y + e) = qh;
+            if (TERMS == 2) {
+              int4 ql;
+              uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                ql32[i] = pack_bf16x2(vv[2 * i] - __bfloat162float(hi[2 * i]), vv[2 * i + 1] - __bfloat162float(hi[2 * i + 1]));
+              *reinterpret_cast<int4*>(p.y + p.term_stride_out + e) = ql;
+            }
           }
         }
       }
@@ -387,16 +413,16 @@ static float bf16_to_f32_host(uint16_t h) {
   return f;
 }
 
-template <int COUT, int TERMS, int KC>
+template <int COUT, int TERMS, int KC, int UP>
 static int launch_umma(const CUtensorMap& tmap, const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
   static bool attr_set = false;
   static size_t attr_smem = 0;
   if (!attr_set || smem > attr_smem) {
-    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<COUT, TERMS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<COUT, TERMS, KC, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
     attr_smem = 227 * 1024;
   }
-  conv3d_umma_kernel<COUT, TERMS, KC><<<grid, NUM_THREADS, smem, st>>>(tmap, p);
+  conv3d_umma_kernel<COUT, TERMS, KC, UP><<<grid, NUM_THREADS, smem, st>>>(tmap, p);
   return check_launch("conv3d_umma_kernel");
 }
 
@@ -432,44 +458,65 @@ extern "C" int pccgeo_blocked_to_f32(const void* xb, float* x, int n, int c, int
   return check_launch("blocked_to_f32_kernel");
 }
 
-// B image, per precision term: [kyx (9)][kc (Cin_p/16)][kcore (2)][ngroup (3*Cout_p/8)][8 n][8 k] bf16, where
-// n = j*Cout_p + co stacks the three z-taps (j=0: kz=2, j=1: kz=1, j=2: kz=0) and k = channel kc*16 + kcore*8 + ki.
+// B image, per precision term: [shift][kc (Cin_p/16)][kcore (2)][ngroup (3*SC/8)][8 n][8 k] bf16, k = channel kc*16 + kcore*8 + ki.
+//   stride 1 (UP=1): shift = ky*3+kx (9), SC = Cout_p, n = j*SC + co stacks the three z-taps (j=0: kz=2, j=1: kz=1, j=2: kz=0).
+//   stride-2 transposed (UP=2): shift = sy*2+sx (4) with input offset -sy / -sx, SC = 4*Cout_p,
+//     n = j*SC + (yc*2+xc)*Cout_p + co: output plane 2z+j takes tap kz = j; output parity class (yc,xc) takes tap
+//     k = 0 at offset 0 / k = 2 at offset -1 when even, k = 1 at offset 0 when odd (zero rows where a class has no tap).
 extern "C" long long pccgeo_umma_pack_weights_host(const float* w, void* out, int cin, int cout, int stride, int transposed,
                                                    int terms) {
   if (cin <= 0 || cout <= 0 || (terms != 1 && terms != 2)) { set_error("umma_pack_weights: bad argument"); return PCCGEO_EINVAL; }
-  if (stride != 1) { set_error("umma_pack_weights: stride %d not supported by the tensor-core path yet", stride); return PCCGEO_EINVAL; }
+  const bool up2 = stride == 2 && transposed;
+  if (stride != 1 && !up2) { set_error("umma_pack_weights: stride-%d forward convs are not supported by the TMA kernel", stride); return PCCGEO_EINVAL; }
   const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16), KC = cip / 16;
-  const long long per_term = 9LL * KC * 2 * (3 * cop / 8) * 64 * 2;
+  const int SC = up2 ? 4 * cop : cop, nshift = up2 ? 4 : 9;
+  const long long per_term = (long long)nshift * KC * 2 * (3 * SC / 8) * 64 * 2;
   if (!out) return per_term * terms;
   if (!w) { set_error("umma_pack_weights: null weights"); return PCCGEO_EINVAL; }
   uint16_t* o = (uint16_t*)out;
   memset(o, 0, (size_t)per_term * terms);
-  for (int kyx = 0; kyx < 9; ++kyx)
-    for (int kc = 0; kc < KC; ++kc)
+  auto put = [&](int sh, int nrow, int ci, float val) {
+    const int kc = ci / 16, kk = ci % 16, kcore = kk >> 3, ki = kk & 7;
+    const long long idx = ((((long long)(sh * KC + kc) * 2 + kcore) * (3 * SC / 8) + (nrow >> 3)) * 8 + (nrow & 7)) * 8 + ki;
+    const uint16_t hi = f32_to_bf16_rn_host(val);
+    o[idx] = hi;
+    if (terms == 2) o[per_term / 2 + idx] = f32_to_bf16_rn_host(val - bf16_to_f32_host(hi));
+  };
+  if (!up2) {
+    for (int kyx = 0; kyx < 9; ++kyx)
       for (int j = 0; j < 3; ++j)
         for (int co = 0; co < cout; ++co)
-          for (int kk = 0; kk < 16; ++kk) {
-            const int ci = kc * 16 + kk;
-            if (ci >= cin) continue;
+          for (int ci = 0; ci < cin; ++ci) {
             int kz = 2 - j, ky = kyx / 3, kx = kyx % 3;
             if (transposed) { kz = 2 - kz; ky = 2 - ky; kx = 2 - kx; }  // stride-1 transposed conv == conv with flipped taps
-            const float val = w[((long long)((kz * 3 + ky) * 3 + kx) * cin + ci) * cout + co];
-            const int nrow = j * cop + co, kcore = kk >> 3, ki = kk & 7;
-            const long long idx = ((((long long)(kyx * KC + kc) * 2 + kcore) * (3 * cop / 8) + (nrow >> 3)) * 8 + (nrow & 7)) * 8 + ki;
-            const uint16_t hi = f32_to_bf16_rn_host(val);
-            o[idx] = hi;
-            if (terms == 2) o[per_term / 2 + idx] = f32_to_bf16_rn_host(val - bf16_to_f32_host(hi));
+            put(kyx, j * cop + co, ci, w[((long long)((kz * 3 + ky) * 3 + kx) * cin + ci) * cout + co]);
           }
+  } else {
+    // tap of output parity c at input offset -s: (c=0,s=0) -> 0, (c=0,s=1) -> 2, (c=1,s=0) -> 1, (c=1,s=1) -> none
+    auto tap = [](int c, int s) { return c == 0 ? (s == 0 ? 0 : 2) : (s == 0 ? 1 : -1); };
+    for (int sy = 0; sy < 2; ++sy)
+      for (int sx = 0; sx < 2; ++sx)
+        for (int j = 0; j < 3; ++j)
+          for (int yc = 0; yc < 2; ++yc)
+            for (int xc = 0; xc < 2; ++xc) {
+              const int ky = tap(yc, sy), kx = tap(xc, sx);
+              if (ky < 0 || kx < 0) continue;
+              for (int co = 0; co < cout; ++co)
+                for (int ci = 0; ci < cin; ++ci)
+                  put(sy * 2 + sx, j * SC + (yc * 2 + xc) * cop + co, ci, w[((long long)((j * 3 + ky) * 3 + kx) * cin + ci) * cout + co]);
+            }
+  }
   return per_term * terms;
 }
 
 extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
                                   int n, int cin, int d, int h, int wd, int cout, int stride, int transposed, int relu,
                                   int terms, void* stream) {
-  (void)transposed;  // taps are already flipped in the packed image
   PCCGEO_REQUIRE(xb && wpacked && yb, "conv3d_umma: null pointer");
   PCCGEO_REQUIRE(terms == 1 || terms == 2, "conv3d_umma: terms must be 1 or 2");
-  PCCGEO_REQUIRE(stride == 1, "conv3d_umma: stride %d not supported by the tensor-core path yet", stride);
+  const bool up2 = stride == 2 && transposed;  // stride 1: taps are already flipped in the packed image
+  PCCGEO_REQUIRE(stride == 1 || up2, "conv3d_umma: stride-%d forward convs are not supported by the TMA kernel", stride);
+  PCCGEO_REQUIRE(!up2 || !residual_b, "conv3d_umma: no fused residual for stride-2 transposed layers");
   PCCGEO_REQUIRE(n > 0 && d > 0 && h % TY == 0 && wd % TX == 0 && h > 0 && wd > 0, "conv3d_umma: H must be a multiple of 16 and W of 8 (got %dx%dx%d)", d, h, wd);
   const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16);
   PCCGEO_REQUIRE(cop == 16 || cop == 32 || cop == 64, "conv3d_umma: Cout %d unsupported", cout);
@@ -481,11 +528,13 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   p.bias = bias; p.res = (const __nv_bfloat16*)residual_b; p.y = (__nv_bfloat16*)yb; p.wimg = (const uint8_t*)wpacked;
   p.N = n; p.D = d; p.H = h; p.W = wd; p.CGi = cip / 8; p.CGo = cop / 8; p.terms = terms; p.relu = relu; p.cout_real = cout;
   p.ytiles = h / TY; p.xtiles = wd / TX; p.items = n * p.ytiles * p.xtiles;
-  p.wbytes_term = 9 * (cip / 16) * 2 * (3 * cop / 8) * 128;
+  const int SC = up2 ? 4 * cop : cop;
+  PCCGEO_REQUIRE(3 * SC <= 256, "conv3d_umma: %d output channels are too many for one stride-2 transposed MMA", cout);
+  p.wbytes_term = (up2 ? 4 : 9) * (cip / 16) * 2 * (3 * SC / 8) * 128;
   p.swap = g_opt_swap_lbo_sbo;
-  p.term_stride_out = (long long)n * cop * d * h * wd;
-  // TMEM ring: up to 256 columns (leaves room for a second CTA per SM), power of two, >= 4 planes
-  p.nslots = 256 / cop;
+  p.term_stride_out = (long long)n * cop * d * h * wd * (up2 ? 8 : 1);
+  // TMEM ring: power of two, >= 4 planes; stride 1 uses up to 256 columns, the stride-2 transposed form all 512
+  p.nslots = (up2 ? 512 : 256) / SC;
   if (p.nslots > MAX_SLOTS) p.nslots = MAX_SLOTS;
   p.slot_shift = 0;
   while ((1 << p.slot_shift) < p.nslots) ++p.slot_shift;
@@ -513,7 +562,15 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   if (g_opt_max_ctas > 0 && grid > g_opt_max_ctas) grid = g_opt_max_ctas;
   cudaStream_t st = (cudaStream_t)stream;
   const int kc = cip / 16;
-#define PCCGEO_DISPATCH(CO, T, K) if (cop == CO && terms == T && kc == K) return launch_umma<CO, T, K>(tmap, p, smem, grid, st);
+  if (up2) {
+#define PCCGEO_DISPATCH_UP2(CO, T, K) if (cop == CO && terms == T && kc == K) return launch_umma<CO, T, K, 2>(tmap, p, smem, grid, st);
+    PCCGEO_DISPATCH_UP2(16, 1, 1) PCCGEO_DISPATCH_UP2(16, 1, 2) PCCGEO_DISPATCH_UP2(16, 1, 4)
+    PCCGEO_DISPATCH_UP2(16, 2, 1) PCCGEO_DISPATCH_UP2(16, 2, 2)
+#undef PCCGEO_DISPATCH_UP2
+    set_error("conv3d_umma: unsupported stride-2 transposed configuration %d -> %d", cin, cout);
+    return PCCGEO_EINVAL;
+  }
+#define PCCGEO_DISPATCH(CO, T, K) if (cop == CO && terms == T && kc == K) return launch_umma<CO, T, K, 1>(tmap, p, smem, grid, st);
   PCCGEO_DISPATCH(16, 1, 1) PCCGEO_DISPATCH(16, 1, 2) PCCGEO_DISPATCH(16, 1, 4)
   PCCGEO_DISPATCH(32, 1, 1) PCCGEO_DISPATCH(32, 1, 2) PCCGEO_DISPATCH(32, 1, 4)
   PCCGEO_DISPATCH(64, 1, 1) PCCGEO_DISPATCH(64, 1, 2) PCCGEO_DISPATCH(64, 1, 4)

@@ -158,11 +158,14 @@ class _ConvBase(Layer):
         return self._dev[key]
 
     def umma_eligible(self, in_shape):
-        """TMA halo-plane kernel: 3x3x3 stride-1 layers with <=32-wide channels on volumes the 16x8 row tile divides."""
+        """TMA halo-plane kernel: 3x3x3 stride-1 layers with <=32-wide channels, and stride-2 transposed layers with
+        <=32 input / <=16 output channels, on volumes the 16x8 row tile divides."""
         n, c, d, h, w = in_shape
         cp, fp = ops.round_up(c, 16), ops.round_up(self.filters, 16)
-        return (self.k == 3 and self.stride == 1 and c >= 8 and cp <= 32 and fp <= 32 and h % 16 == 0 and w % 8 == 0
-                and h * w >= 256)
+        tiled = h % 16 == 0 and w % 8 == 0 and h * w >= 256
+        if self.k == 3 and self.stride == 2 and self.transposed:
+            return c >= 8 and cp <= 32 and fp <= 16 and tiled
+        return self.k == 3 and self.stride == 1 and c >= 8 and cp <= 32 and fp <= 32 and tiled
 
     def gemm_eligible(self, in_shape):
         """gather -> tcgen05 kernel: everything else with >= 8 input channels and <= 64-wide channels."""

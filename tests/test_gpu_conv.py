@@ -111,6 +111,37 @@ def test_umma_full_size_layer_matches_fp32_kernel(terms):
     assert torch.equal(yb, yb2)
 
 
+UMMA_UP2_CASES = [
+    # cin, cout, (D,H,W) of the input, n
+    (32, 16, (4, 16, 8), 1), (32, 16, (16, 16, 16), 2), (16, 16, (1, 16, 8), 1), (32, 16, (7, 32, 24), 3), (24, 12, (5, 16, 8), 2),
+    (32, 16, (32, 32, 32), 2),
+]
+
+
+@pytest.mark.parametrize('terms,tol', [(2, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize('cin,cout,shape,n', UMMA_UP2_CASES)
+def test_umma_stride2_transposed_matches_oracle(cin, cout, shape, n, terms, tol):
+    """SynthesisBlock's first layer (Conv3DTranspose k3 s2 'same', model_transforms.py:78) on the TMA kernel's UP=2 form."""
+    rng = np.random.default_rng(hash((cin, cout, shape, n)) % 2 ** 31)
+    x, kern, bias = _case(rng, True, 3, 2, cin, cout, shape, n)
+    want = _oracle(x, kern, bias, 2, True, True)
+    wp = ops.umma_pack_weights(_tap_major(kern, True).numpy(), cin, cout, 2, True, terms)
+    xb = ops.f32_to_blocked(x.cuda(), terms)
+    yb, shp = ops.conv3d_umma(xb, tuple(x.shape), wp, bias.cuda(), cout, 2, True, True, terms)
+    got = ops.blocked_to_f32(yb, shp, terms)
+    torch.cuda.synchronize()
+    assert shp == tuple(want.shape)
+    err = float((got.cpu().double() - want).abs().max())
+    scale = float(want.abs().max())
+    assert err < tol * scale, f'max err {err:.3e} vs scale {scale:.3e}'
+    # no bias, no relu; deterministic
+    yb2, _ = ops.conv3d_umma(xb, tuple(x.shape), wp, None, cout, 2, True, False, terms)
+    want2 = _oracle(x, kern, None, 2, False, True)
+    assert float((ops.blocked_to_f32(yb2, shp, terms).cpu().double() - want2).abs().max()) < tol * float(want2.abs().max())
+    yb3, _ = ops.conv3d_umma(xb, tuple(x.shape), wp, None, cout, 2, True, False, terms)
+    assert torch.equal(yb2, yb3)
+
+
 GEMM_CASES = [
     # transposed, k, stride, cin, cout, (D,H,W), n
     (False, 3, 1, 64, 64, (8, 8, 8), 3), (False, 3, 1, 64, 64, (4, 4, 4), 5), (True, 3, 1, 64, 64, (16, 16, 16), 1),

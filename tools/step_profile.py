@@ -1,0 +1,57 @@
+"""Per-kernel device time of the bench's device step in steady state (torch.profiler / CUPTI, kernels run back to back with
+warm caches -- unlike ncu, which serialises and flushes).  python tools/step_profile.py [blocks] [precision]"""
+import collections
+import os
+import sys
+
+import numpy as np
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pcc_geo_cnn_v2_b200 as P  # noqa: E402
+from pcc_geo_cnn_v2_b200 import ops, synthetic  # noqa: E402
+from pcc_geo_cnn_v2_b200.entropy_models import GaussianConditional  # noqa: E402
+from pcc_geo_cnn_v2_b200.model_types import blocks_to_coords, threshold_f32  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+P.set_precision(sys.argv[2] if len(sys.argv) > 2 else 'bf16x3')
+m = P.ModelConfigType['c3p'].build(batch_size=B)
+m.set_weights(synthetic.trained_like_weights(m, seed=42))
+m.compress((1, 1, 64, 64, 64))
+m.decompress()
+uniq = synthetic.surface_blocks(min(B, 8), size=64, seed=100)
+blocks = [uniq[i % len(uniq)] for i in range(B)]
+coords = torch.from_numpy(blocks_to_coords(blocks)).cuda()
+thr = torch.from_numpy(threshold_f32(m.thresholds, np.full(B, 128))).cuda()
+
+
+def device_step():
+    x = ops.densify(coords, B, 64, 64, 64)
+    dev = m._encode_device(x)
+    z_hat = ops.eb_dequantize(dev['z_sym'], m.entropy_bottleneck.device_params())
+    sigma = m.hyper_synthesis_transform(z_hat)
+    GaussianConditional(sigma, m.scale_table).indexes()
+    x_hat = m.synthesis_transform(ops.i32_to_f32(dev['y_sym']))
+    return ops.threshold_pack(x_hat, thr)
+
+
+for _ in range(5):
+    device_step()
+torch.cuda.synchronize()
+STEPS = 5
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(STEPS):
+        device_step()
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+agg = collections.OrderedDict()
+per_step = len(evs) // STEPS
+t_first, t_last = evs[0].time_range.start, evs[-1].time_range.end
+print(f'{len(evs)} kernels, {per_step} per step, span {(t_last - t_first) / STEPS:.1f} us per step')
+seq = evs[-per_step:]
+tot = sum(e.time_range.end - e.time_range.start for e in seq)
+print(f'last step: sum of kernel durations {tot:.1f} us, span {seq[-1].time_range.end - seq[0].time_range.start:.1f} us')
+for e in seq:
+    print(f'{e.time_range.end - e.time_range.start:9.1f} us  {e.name[:90]}')
