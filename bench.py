@@ -216,15 +216,14 @@ def main():
 
     def device_step():
         x = ops.densify(coords, B, SIZE, SIZE, SIZE)
-        dev = m._encode_device(x)
+        dev = m._encode_device(x, thresholds=thr, want_x_hat=False)  # as compress_blocks(fixed_threshold=True) runs it
         # decode graph from the (device-resident) symbols
         z_hat = ops.eb_dequantize(dev['z_sym'], m.entropy_bottleneck.device_params())
         sigma = m.hyper_synthesis_transform(z_hat)
         cb = GaussianConditional(sigma, m.scale_table)
         cb.indexes()
         y_hat = ops.i32_to_f32(dev['y_sym'])
-        x_hat = m.synthesis_transform(y_hat)
-        bits, counts = ops.threshold_pack(x_hat, thr)
+        _, bits, counts = m.synthesis_transform.packed(y_hat, thr)  # as decompress_blocks runs it (threshold + pack fused)
         return bits
 
     def barrier():

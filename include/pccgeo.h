@@ -82,6 +82,18 @@ int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, c
                        void* yb, int n, int cin, int d, int h, int wd, int cout, int stride, int transposed,
                        int relu, int terms, void* stream);
 
+/* Last layer of the V2 synthesis transforms, Conv3DTranspose(1, (3,3,3), 'same') + BiasAdd + Relu
+ * (src/model_transforms.py:107,135), fused with what compress_blocks / decompress_blocks do with x_hat: clip to [0,1],
+ * compare with the block's threshold, pack (src/model_types.py:201-202,209,233-234).  Scatter-form tcgen05 kernel: the 27
+ * taps are the MMA N dimension, the partial sums are gathered per output voxel in a fixed order.
+ * w: tap-major fp32 (27, Cin, 1), Cin <= 16.  Outputs (either may be NULL, not both): x_hat fp32 (N,1,D,H,W) after ReLU
+ * (unclipped, as the reference's graph returns it); bits = packed occupancy (N, D*H*W/32) of min(x_hat,1) > thresholds[n]
+ * in argwhere (C) order, bit i of word j = voxel 32*j+i, plus optional per-block popcounts.  H % 16 == 0, W % 8 == 0. */
+long long pccgeo_out1_pack_weights_host(const float* w_host, void* wpacked_host, int cin, int transposed, int terms);
+int pccgeo_conv3d_out1(const void* xb, const void* wpacked, const float* bias, float* x_hat, uint32_t* bits,
+                       const float* thresholds, int32_t* counts, int n, int cin, int d, int h, int wd, int relu,
+                       int terms, void* stream);
+
 /* General tensor-core path (gather-im2col -> tcgen05): any cubic kernel <= 9, stride 1 or 2, conv or transposed conv,
  * 16..64 channels, any volume size (the batch is folded into the GEMM rows).  Same reference call sites as above, plus
  * the 5^3 / 9^3 layers of AnalysisTransformV1 / SynthesisTransformV1 (src/model_transforms.py:41-59).

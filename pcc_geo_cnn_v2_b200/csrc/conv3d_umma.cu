@@ -271,15 +271,40 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&hdr->acc_empty[slot]));  // accumulator slot is free again
+        if constexpr (UP == 2) {
+          // this input voxel's 2x2 outputs of plane pl: for each output row (yc) the two x-neighbours (xc = 0, 1) of one
+          // channel group are 32 contiguous bytes -> one 256-bit store per lane, 8 lanes = one full 256-byte run
 #pragma unroll
-        for (int cls = 0; cls < SC / COUT; ++cls) {   // UP=2: (y,x) parity classes of this input voxel's 2x2 outputs
+          for (int yc = 0; yc < 2; ++yc) {
+            const long long vox = (long long)pl * HWo + vox0 + (long long)yc * Wo;
+#pragma unroll
+            for (int cg = 0; cg < COUT / 8; ++cg) {
+              uint32_t qh[8], ql[8];
+#pragma unroll
+              for (int xc = 0; xc < 2; ++xc)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int col = (yc * 2 + xc) * COUT + cg * 8 + 2 * i;
+                  float v0 = __uint_as_float(r[col]) + bias_r[cg * 8 + 2 * i], v1 = __uint_as_float(r[col + 1]) + bias_r[cg * 8 + 2 * i + 1];
+                  if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                  __nv_bfloat162 t2 = __halves2bfloat162(h0, h1);
+                  qh[xc * 4 + i] = *reinterpret_cast<uint32_t*>(&t2);
+                  if (TERMS == 2) ql[xc * 4 + i] = pack_bf16x2(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+                }
+              const long long e = (((long long)n * p.CGo + cg) * DHWo + vox) * 8;
+              st_global_v8(p.y + e, qh);
+              if (TERMS == 2) st_global_v8(p.y + p.term_stride_out + e, ql);
+            }
+          }
+        } else {
           float v[COUT];
 #pragma unroll
           for (int c = 0; c < COUT; ++c) {
-            v[c] = __uint_as_float(r[cls * COUT + c]) + bias_r[c];
+            v[c] = __uint_as_float(r[c]) + bias_r[c];
             if (p.relu) v[c] = fmaxf(v[c], 0.f);
           }
-          const long long vox = (long long)pl * HWo + vox0 + (UP == 2 ? (long long)(cls >> 1) * Wo + (cls & 1) : 0);
+          const long long vox = (long long)pl * HWo + vox0;
           if (p.res) {
             for (int t = 0; t < p.terms; ++t)
 #pragma unroll

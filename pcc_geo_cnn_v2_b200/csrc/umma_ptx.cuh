@@ -120,6 +120,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// 256-bit global store (sm_100+): 32 contiguous, 32-byte aligned bytes from one lane
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&q)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]),
+               "r"(q[5]), "r"(q[6]), "r"(q[7])
+               : "memory");
+}
 __device__ __forceinline__ void unpack_bf16x8_add(const int4& q, float* v) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll

@@ -149,6 +149,9 @@ class _ConvBase(Layer):
                 terms = int(key[-1])
                 self._dev[key] = ops.gemm_pack_weights(self.tap_major(), self.in_channels, self.filters, self.k, self.stride,
                                                        self.transposed, terms)
+            elif key.startswith('w_out1'):
+                terms = int(key[-1])
+                self._dev[key] = ops.out1_pack_weights(self.tap_major(), self.in_channels, self.transposed, terms)
             elif key.startswith('w_umma'):
                 terms = int(key[-1])
                 self._dev[key] = ops.umma_pack_weights(self.tap_major(), self.in_channels, self.filters, self.stride,
@@ -166,6 +169,13 @@ class _ConvBase(Layer):
         if self.k == 3 and self.stride == 2 and self.transposed:
             return c >= 8 and cp <= 32 and fp <= 16 and tiled
         return self.k == 3 and self.stride == 1 and c >= 8 and cp <= 32 and fp <= 32 and tiled
+
+    def out1_eligible(self, in_shape):
+        """Scatter-form single-output-channel kernel (last layer of the V2 synthesis transforms), fusable with the
+        clip / threshold / bit-pack of the block loops."""
+        n, c, d, h, w = in_shape
+        return (self.k == 3 and self.stride == 1 and self.filters == 1 and 8 <= c <= 16 and h % 16 == 0 and w % 8 == 0
+                and h * w >= 256)
 
     def gemm_eligible(self, in_shape):
         """gather -> tcgen05 kernel: everything else with >= 8 input channels and <= 64-wide channels."""
@@ -211,6 +221,12 @@ class SequentialLayer(Layer):  # model_transforms.py:11-19
         return _run_transform(self, tensor, self.data_format)
 
     __call__ = call
+
+    def packed(self, tensor, thresholds, want_f32=False):
+        """Synthesis + what the block loops do with x_hat (model_types.py:201-202,209,233-234): returns
+        (x_hat fp32 or None, packed occupancy bits of min(x_hat,1) > thresholds[n], per-block counts).  Fused into the
+        last layer's epilogue when that layer is the 3x3x3 single-channel one; otherwise threshold_pack runs after it."""
+        return _run_transform(self, tensor, self.data_format, pack={'thresholds': thresholds, 'want_f32': want_f32})
 
 
 class ResidualLayer(Layer):  # model_transforms.py:22-38
@@ -407,8 +423,9 @@ class _Val:
         return self.blk
 
 
-def run_steps(steps, out_id, x):
-    """Execute traced steps on a channels_first fp32 CUDA tensor."""
+def run_steps(steps, out_id, x, pack=None):
+    """Execute traced steps on a channels_first fp32 CUDA tensor.  pack = {'thresholds', 'want_f32'}: also return the
+    packed thresholded occupancy of the (single-channel) output -> (y or None, bits, counts)."""
     mode = _precision['mode']
     terms = {'bf16x3': 2, 'bf16': 1, 'fp32': 0}[mode]
     vals = {0: _Val(f32=x, shape=tuple(x.shape))}
@@ -424,7 +441,14 @@ def run_steps(steps, out_id, x):
             layer.build(v.shape[1])
             if v.shape[1] != layer.in_channels:
                 raise ValueError(f'layer expects {layer.in_channels} input channels, got {v.shape[1]}')
-            if terms and layer.umma_eligible(v.shape):
+            if terms and res is None and dst == out_id and layer.out1_eligible(v.shape):
+                thr = pack['thresholds'] if pack else None
+                xh, bits, counts = ops.conv3d_out1(v.as_blk(terms), v.shape, layer.dev(f'w_out1{terms}'), layer.dev('bias'),
+                                                   layer.relu, terms, (not pack) or pack['want_f32'], thr)
+                if pack:
+                    return xh, bits, counts
+                vals[dst] = _Val(f32=xh, shape=tuple(xh.shape))
+            elif terms and layer.umma_eligible(v.shape):
                 rb = vals[res].as_blk(terms) if res is not None else None
                 yb, shp = ops.conv3d_umma(v.as_blk(terms), v.shape, layer.dev(f'w_umma{terms}'), layer.dev('bias'),
                                           layer.filters, layer.stride, layer.transposed, layer.relu, terms, rb)
@@ -447,10 +471,14 @@ def run_steps(steps, out_id, x):
             vals[s[3]] = _Val(f32=y, shape=tuple(y.shape))
         for vid in [k for k, li in last_use.items() if li == i and k != out_id]:
             vals.pop(vid, None)
-    return vals[out_id].as_f32()
+    y = vals[out_id].as_f32()
+    if pack:
+        bits, counts = ops.threshold_pack(y, pack['thresholds'])
+        return y, bits, counts
+    return y
 
 
-def _run_transform(layer, tensor, data_format):
+def _run_transform(layer, tensor, data_format, pack=None):
     if not (torch.is_tensor(tensor) and tensor.is_cuda):
         raise TypeError('transforms run on CUDA tensors only (no CPU fallback); move the input to the GPU')
     x = tensor.to(torch.float32)
@@ -460,7 +488,12 @@ def _run_transform(layer, tensor, data_format):
     if not hasattr(layer, '_trace'):
         layer._trace = trace(layer)
     steps, out_id = layer._trace
-    y = run_steps(steps, out_id, x)
+    y = run_steps(steps, out_id, x, pack)
+    if pack:
+        xh, bits, counts = y
+        if xh is not None and data_format == 'channels_last':
+            xh = xh.permute(0, 2, 3, 4, 1).contiguous()
+        return xh, bits, counts
     if data_format == 'channels_last':
         y = y.permute(0, 2, 3, 4, 1).contiguous()
     return y

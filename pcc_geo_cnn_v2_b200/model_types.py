@@ -99,6 +99,13 @@ class CompressionModel:
     def _decode_batch(self, strings_list, x_shape):
         raise NotImplementedError
 
+    def _synthesize(self, y_hat, thresholds, want_x_hat):
+        """x_hat = synthesis(y_hat); with thresholds also the packed occupancy (fused into the last layer when possible)."""
+        if thresholds is None:
+            return self.synthesis_transform(y_hat), None
+        x_hat, bits, _ = self.synthesis_transform.packed(y_hat, thresholds, want_f32=want_x_hat)
+        return x_hat, bits
+
     # -- batch pipeline ------------------------------------------------------------------------------
     def _map_batches(self, fn, batches):
         """Run fn(batch) for every batch, results in order.  With more than one batch, each batch's whole chain
@@ -166,12 +173,12 @@ class CompressionModel:
             x = ops.densify(self._h2d(blocks_to_coords(chunk)), len(chunk), *dims)
             pend = {}
             # the symbol D2H is enqueued BEFORE synthesis is launched: range coding overlaps the synthesis kernels
-            dev = self._encode_device(x, lambda d: pend.__setitem__('sym', self._d2h(*self._latent_tensors(d))))
+            t = self._h2d(threshold_f32(self.thresholds, thr_idx[span[0]:span[1]])) if thr_idx is not None else None
+            dev = self._encode_device(x, lambda d: pend.__setitem__('sym', self._d2h(*self._latent_tensors(d))),
+                                      thresholds=t, want_x_hat=keep_x_hat)
             pts = None
             if thr_idx is not None:
-                t = self._h2d(threshold_f32(self.thresholds, thr_idx[span[0]:span[1]]))
-                bits, _ = ops.threshold_pack(dev['x_hat'], t)
-                pend['bits'] = self._d2h(bits)
+                pend['bits'] = self._d2h(dev['bits'])
             strings = self._encode_host(dev, self._wait(pend['sym']))
             if thr_idx is not None:
                 pts = ops.bits_to_points(self._wait(pend['bits'])[0], dims, self.coder_threads)
@@ -244,9 +251,9 @@ class CompressionModel:
         def run(chunk):
             strings = [c[0] for c in chunk]
             idx = np.asarray([int(c[1]) for c in chunk], np.int64)
-            x_hat, dbg = self._decode_batch(strings, dims)
-            bits, _ = ops.threshold_pack(x_hat, self._h2d(threshold_f32(self.thresholds, idx)))
-            pts = ops.bits_to_points(self._wait(self._d2h(bits))[0], dims, self.coder_threads)
+            x_hat, dbg = self._decode_batch(strings, dims, thresholds=self._h2d(threshold_f32(self.thresholds, idx)),
+                                            want_x_hat=debug)
+            pts = ops.bits_to_points(self._wait(self._d2h(dbg['bits']))[0], dims, self.coder_threads)
             return pts, [dbg if debug else None] * len(chunk)
 
         res = self._map_batches(run, self._chunks(list(blocks)))
@@ -301,16 +308,16 @@ class CompressionModelV1(CompressionModel):
     def decompress(self):  # model_types.py:297-309
         pass
 
-    def _encode_device(self, x, after_latents=None):
+    def _encode_device(self, x, after_latents=None, thresholds=None, want_x_hat=True):
         y = self.analysis_transform(x)
         y_sym, y_hat = self.entropy_bottleneck.quantize(y)
         dev = {'y_sym': y_sym, 'y_hat': y_hat}
         if after_latents is not None:
             after_latents(dev)
-        x_hat = self.synthesis_transform(y_hat)
+        x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
         self.x, self.x_hat = x, x_hat
         self.debug_tensors = {'y_hat': y_hat, 'x_hat': x_hat}
-        dev['x_hat'] = x_hat
+        dev['x_hat'], dev['bits'] = x_hat, bits
         return dev
 
     @staticmethod
@@ -322,14 +329,14 @@ class CompressionModelV1(CompressionModel):
         ys = self.entropy_bottleneck.encode_symbols(y_sym, self.coder_threads)
         return [(s,) for s in ys]
 
-    def _decode_batch(self, strings_list, dims):
+    def _decode_batch(self, strings_list, dims, thresholds=None, want_x_hat=True):
         f = self.num_filters
         shp = (f,) + tuple(d // 8 for d in dims)  # model_types.py:305
         sym = self.entropy_bottleneck.decode_symbols([s[0] for s in strings_list], shp, self.coder_threads)
         y_hat = ops.eb_dequantize(self._h2d(sym), self.entropy_bottleneck.device_params())
-        x_hat = self.synthesis_transform(y_hat)
+        x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
         self.x_hat = x_hat
-        return x_hat, {'y_hat': y_hat, 'x_hat': x_hat}
+        return x_hat, {'y_hat': y_hat, 'x_hat': x_hat, 'bits': bits}
 
 
 class CompressionModelV2(CompressionModel):
@@ -376,7 +383,7 @@ class CompressionModelV2(CompressionModel):
     def decompress(self):  # model_types.py:393-411
         pass
 
-    def _encode_device(self, x, after_latents=None):
+    def _encode_device(self, x, after_latents=None, thresholds=None, want_x_hat=True):
         y = self.analysis_transform(x)
         z = self.hyper_analysis_transform(y)
         z_sym, z_hat = self.entropy_bottleneck.quantize(z)
@@ -387,10 +394,10 @@ class CompressionModelV2(CompressionModel):
                'indexes': idx, 'cb': cb}
         if after_latents is not None:
             after_latents(dev)
-        x_hat = self.synthesis_transform(y_hat)
+        x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
         self.x, self.x_hat = x, x_hat
         self.debug_tensors = {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat}
-        dev['x_hat'] = x_hat
+        dev['x_hat'], dev['bits'] = x_hat, bits
         return dev
 
     @staticmethod
@@ -403,7 +410,7 @@ class CompressionModelV2(CompressionModel):
         ys = dev['cb'].encode_symbols(y_sym, idx, self.coder_threads)
         return list(zip(ys, zs))  # (y_string, z_string): model_types.py:389
 
-    def _decode_batch(self, strings_list, dims):
+    def _decode_batch(self, strings_list, dims, thresholds=None, want_x_hat=True):
         f = self.num_filters
         zshp = (f,) + tuple(d // 16 for d in dims)  # model_types.py:403
         zsym = self.entropy_bottleneck.decode_symbols([s[1] for s in strings_list], zshp, self.coder_threads)
@@ -413,9 +420,9 @@ class CompressionModelV2(CompressionModel):
         idx = cb.indexes()
         ysym = cb.decode_symbols([s[0] for s in strings_list], self._wait(self._d2h(idx))[0], self.coder_threads)
         y_hat = ops.i32_to_f32(self._h2d(ysym))
-        x_hat = self.synthesis_transform(y_hat)
+        x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
         self.x_hat = x_hat
-        return x_hat, {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat}
+        return x_hat, {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat, 'bits': bits}
 
 
 class ModelType(Enum):

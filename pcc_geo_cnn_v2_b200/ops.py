@@ -88,6 +88,35 @@ def conv3d_umma(xb, in_shape, wpacked, bias, cout, stride, transposed, relu, ter
     return out, shp
 
 
+def out1_pack_weights(w_tap_host, cin, transposed, terms):
+    """numpy fp32 (27, Cin, 1) -> device uint8 image for pccgeo_conv3d_out1."""
+    w = np.ascontiguousarray(w_tap_host, np.float32)
+    size = L.lib().pccgeo_out1_pack_weights_host(L.ptr(w), None, cin, int(transposed), terms)
+    if size <= 0:
+        L.check(int(size) if size < 0 else -1, 'out1_pack_weights')
+    img = np.zeros(size, np.uint8)
+    rc = L.lib().pccgeo_out1_pack_weights_host(L.ptr(w), L.ptr(img), cin, int(transposed), terms)
+    if rc < 0:
+        L.check(int(rc), 'out1_pack_weights')
+    return torch.from_numpy(img).cuda()
+
+
+def conv3d_out1(xb, in_shape, wpacked, bias, relu, terms, want_f32=True, thresholds=None):
+    """Single-output-channel 3x3x3 stride-1 layer on a blocked tensor, fused with threshold + bit-pack.
+    Returns (x_hat fp32 (N,1,D,H,W) or None, bits int32 (N, DHW/32) or None, counts int32 (N,) or None)."""
+    L.require_cuda()
+    n, cin, d, h, w = in_shape
+    xh = torch.empty((n, 1, d, h, w), device=xb.device, dtype=torch.float32) if want_f32 else None
+    bits = counts = None
+    if thresholds is not None:
+        assert thresholds.is_cuda and thresholds.dtype == torch.float32 and thresholds.numel() == n
+        bits = torch.empty((n, d * h * w // 32), device=xb.device, dtype=torch.int32)
+        counts = torch.empty(n, device=xb.device, dtype=torch.int32)
+    L.check(L.lib().pccgeo_conv3d_out1(L.ptr(xb), L.ptr(wpacked), L.ptr(bias), L.ptr(xh), L.ptr(bits), L.ptr(thresholds),
+                                       L.ptr(counts), n, cin, d, h, w, int(relu), terms, L.stream_ptr()), 'conv3d_out1')
+    return xh, bits, counts
+
+
 def gemm_pack_weights(w_tap_host, cin, cout, k, stride, transposed, terms):
     """numpy fp32 (k^3, Cin, Cout) -> (device uint8 image, host header bytes) for pccgeo_conv3d_gemm."""
     w = np.ascontiguousarray(w_tap_host, np.float32)

@@ -142,6 +142,43 @@ def test_umma_stride2_transposed_matches_oracle(cin, cout, shape, n, terms, tol)
     assert torch.equal(yb2, yb3)
 
 
+OUT1_CASES = [
+    # transposed, cin, (D,H,W), n
+    (True, 16, (4, 16, 8), 1), (True, 16, (16, 16, 16), 2), (False, 16, (5, 32, 24), 2), (True, 16, (1, 16, 8), 1),
+    (True, 16, (2, 16, 8), 3), (True, 12, (9, 16, 16), 1), (True, 16, (64, 64, 64), 2),
+]
+
+
+@pytest.mark.parametrize('terms,tol', [(2, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize('transposed,cin,shape,n', OUT1_CASES)
+def test_out1_conv_matches_oracle_and_packs_bits(transposed, cin, shape, n, terms, tol):
+    """Last synthesis layer (model_transforms.py:107,135) + clip/threshold/pack (model_types.py:201-202,233-234)."""
+    rng = np.random.default_rng(hash((transposed, cin, shape, n)) % 2 ** 31)
+    x, kern, bias = _case(rng, transposed, 3, 1, cin, 1, shape, n)
+    bias = bias + 0.3
+    want = _oracle(x, kern, bias, 1, True, transposed)
+    wp = ops.out1_pack_weights(_tap_major(kern, transposed).numpy(), cin, transposed, terms)
+    xb = ops.f32_to_blocked(x.cuda(), terms)
+    thr = torch.from_numpy(rng.uniform(0.1, 0.9, size=n).astype(np.float32)).cuda()
+    xh, bits, counts = ops.conv3d_out1(xb, tuple(x.shape), wp, bias.cuda(), True, terms, True, thr)
+    torch.cuda.synchronize()
+    assert tuple(xh.shape) == tuple(want.shape)
+    err = float((xh.cpu().double() - want).abs().max())
+    scale = float(want.abs().max())
+    assert err < tol * scale, f'max err {err:.3e} vs scale {scale:.3e}'
+    # the packed output is exactly threshold_pack of the kernel's own x_hat (bit-exact integer work)
+    bits2, counts2 = ops.threshold_pack(xh, thr)
+    assert torch.equal(bits, bits2) and torch.equal(counts, counts2)
+    # bits-only and f32-only calls agree with the combined one; deterministic
+    _, bits3, counts3 = ops.conv3d_out1(xb, tuple(x.shape), wp, bias.cuda(), True, terms, False, thr)
+    xh3, _, _ = ops.conv3d_out1(xb, tuple(x.shape), wp, bias.cuda(), True, terms, True, None)
+    assert torch.equal(bits, bits3) and torch.equal(counts, counts3) and torch.equal(xh, xh3)
+    # no bias / no relu
+    xh4, _, _ = ops.conv3d_out1(xb, tuple(x.shape), wp, None, False, terms, True, None)
+    want4 = _oracle(x, kern, None, 1, False, transposed)
+    assert float((xh4.cpu().double() - want4).abs().max()) < tol * float(want4.abs().max())
+
+
 GEMM_CASES = [
     # transposed, k, stride, cin, cout, (D,H,W), n
     (False, 3, 1, 64, 64, (8, 8, 8), 3), (False, 3, 1, 64, 64, (4, 4, 4), 5), (True, 3, 1, 64, 64, (16, 16, 16), 1),

@@ -28,12 +28,11 @@ thr = torch.from_numpy(threshold_f32(m.thresholds, np.full(B, 128))).cuda()
 
 def device_step():
     x = ops.densify(coords, B, 64, 64, 64)
-    dev = m._encode_device(x)
+    dev = m._encode_device(x, thresholds=thr, want_x_hat=False)  # as compress_blocks(fixed_threshold=True) runs it
     z_hat = ops.eb_dequantize(dev['z_sym'], m.entropy_bottleneck.device_params())
     sigma = m.hyper_synthesis_transform(z_hat)
     GaussianConditional(sigma, m.scale_table).indexes()
-    x_hat = m.synthesis_transform(ops.i32_to_f32(dev['y_sym']))
-    return ops.threshold_pack(x_hat, thr)
+    return m.synthesis_transform.packed(ops.i32_to_f32(dev['y_sym']), thr)
 
 
 for _ in range(5):
