@@ -203,6 +203,12 @@ int pccgeo_range_decode_host(const uint8_t* bytes, const long long* byte_offsets
  * offsets (n_blocks+1) receives the prefix sum of per-block point counts; pass points == NULL to query sizes only. */
 int pccgeo_bits_to_points_host(const uint32_t* bits, int n_blocks, int d, int h, int w, long long* offsets,
                                float* points, long long capacity_points, int threads);
+
+/* Host half of sparse_to_dense / pc_to_tf for a batch (src/model_types.py:23-39,108-114): per-block point arrays (rows of
+ * >= 3 float32 or float64 coordinates, row pitch row_bytes[b]) -> int16 (sum counts, 4) rows (block, c0, c1, c2), the
+ * input of pccgeo_densify.  Values are truncated like numpy's float -> int16 cast. */
+int pccgeo_blocks_to_coords_host(const void* const* blocks, const long long* counts, const long long* row_bytes,
+                                 int n_blocks, int is_f64, int16_t* out, int threads);
 /* tfc pmf_to_quantized_cdf (precision 16): pmf (len) doubles -> cdf (len+1) int32, HOST */
 int pccgeo_pmf_to_quantized_cdf_host(const double* pmf, int len, int precision, int32_t* cdf);
 

@@ -41,6 +41,7 @@ namespace pccgeo {
 // --------------------------------------------------------------------------------------------------------
 static int g_opt_swap_lbo_sbo = 0;
 static int g_opt_max_ctas = 0;
+static int g_opt_one_cta = 0;
 
 // --------------------------------------------------------------------------------------------------------
 // kernel
@@ -78,8 +79,13 @@ constexpr int HEADER_BYTES = 1024;
 static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "header too large");
 
 // padded output channels (16,32,64); precision terms (1,2); Cin/16 (1,2,4); UP = 1 (stride 1) or 2 (stride-2 transposed)
+// small stride-1 configurations (16 -> 16 channels) fit twice on an SM: two CTAs interleave their MMA streams, which hides
+// part of the fixed per-instruction cost of small-N tcgen05.mma (tools/umma_bench.cu: 57 instead of 68.5 cycles at N = 48)
+template <int COUT, int KC, int UP>
+constexpr int umma_ctas_per_sm() { return (UP == 1 && COUT == 16 && KC == 1) ? 2 : 1; }
+
 template <int COUT, int TERMS, int KC, int UP>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, umma_ctas_per_sm<COUT, KC, UP>())
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvParams p) {
   constexpr int SC = UP == 2 ? 4 * COUT : COUT;   // TMEM columns of one output-plane slot
   constexpr int NSHIFT = UP == 2 ? 4 : 9;         // distinct (y,x) input shifts = MMAs per k-chunk and precision pair
@@ -459,6 +465,7 @@ extern "C" int pccgeo_set_option(const char* name, long long value) {
   if (!name) return PCCGEO_EINVAL;
   if (!strcmp(name, "umma_swap_lbo_sbo")) { g_opt_swap_lbo_sbo = (int)value; return PCCGEO_OK; }
   if (!strcmp(name, "umma_max_ctas")) { g_opt_max_ctas = (int)value; return PCCGEO_OK; }
+  if (!strcmp(name, "umma_one_cta_per_sm")) { g_opt_one_cta = (int)value; return PCCGEO_OK; }
   set_error("set_option: unknown option %s", name);
   return PCCGEO_EINVAL;
 }
@@ -565,7 +572,8 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   while ((1 << p.slot_shift) < p.nslots) ++p.slot_shift;
   const int stage_bytes = terms * p.CGi * PLANE_CG_BYTES;
   const int wall = (p.wbytes_term * terms + 127) & ~127;
-  const int avail = 227 * 1024 - HEADER_BYTES - wall;
+  const int ctas_per_sm = (!up2 && cop == 16 && cip == 16 && !g_opt_one_cta) ? 2 : 1;
+  const int avail = (ctas_per_sm == 2 ? 113 : 227) * 1024 - HEADER_BYTES - wall;
   PCCGEO_REQUIRE(avail >= 3 * stage_bytes, "conv3d_umma: weights (%d B) leave no room for the input pipeline", wall);
   p.nstage = avail / stage_bytes;
   if (p.nstage > MAX_STAGES) p.nstage = MAX_STAGES;
@@ -583,7 +591,7 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PCCGEO_REQUIRE(cr == CUDA_SUCCESS, "conv3d_umma: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-  int grid = p.items < 148 ? p.items : 148;
+  int grid = p.items < 148 * ctas_per_sm ? p.items : 148 * ctas_per_sm;
   if (g_opt_max_ctas > 0 && grid > g_opt_max_ctas) grid = g_opt_max_ctas;
   cudaStream_t st = (cudaStream_t)stream;
   const int kc = cip / 16;

@@ -388,3 +388,37 @@ extern "C" int pccgeo_bits_to_points_host(const uint32_t* bits, int n_blocks, in
   });
   return PCCGEO_OK;
 }
+
+// Host half of sparse_to_dense / pc_to_tf (reference src/model_types.py:23-39,108-114) for a batch: per-block point
+// arrays (rows of >= 3 float32 / float64 coordinates, any row pitch) -> one int16 (sum n_i, 4) array of
+// (block, c0, c1, c2) rows for pccgeo_densify.  offsets[b] = first output row of block b (prefix sum of counts).
+extern "C" int pccgeo_blocks_to_coords_host(const void* const* blocks, const long long* counts, const long long* row_bytes,
+                                            int n_blocks, int is_f64, int16_t* out, int threads) {
+  if (n_blocks < 0 || (n_blocks > 0 && (!blocks || !counts || !row_bytes || !out))) {
+    pccgeo::set_error("blocks_to_coords: bad argument");
+    return PCCGEO_EINVAL;
+  }
+  std::vector<long long> offs(n_blocks + 1, 0);
+  for (int b = 0; b < n_blocks; ++b) {
+    if (counts[b] < 0 || (counts[b] > 0 && !blocks[b])) {
+      pccgeo::set_error("blocks_to_coords: block %d is null", b);
+      return PCCGEO_EINVAL;
+    }
+    offs[b + 1] = offs[b] + counts[b];
+  }
+  parallel_for(n_blocks, threads, [&](int b) {
+    const uint8_t* src = (const uint8_t*)blocks[b];
+    int16_t* o = out + offs[b] * 4;
+    for (long long i = 0; i < counts[b]; ++i, src += row_bytes[b], o += 4) {
+      o[0] = (int16_t)b;
+      if (is_f64) {
+        const double* r = (const double*)src;
+        o[1] = (int16_t)r[0]; o[2] = (int16_t)r[1]; o[3] = (int16_t)r[2];
+      } else {
+        const float* r = (const float*)src;
+        o[1] = (int16_t)r[0]; o[2] = (int16_t)r[1]; o[3] = (int16_t)r[2];
+      }
+    }
+  });
+  return PCCGEO_OK;
+}

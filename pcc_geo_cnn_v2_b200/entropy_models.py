@@ -75,6 +75,8 @@ class EntropyBottleneck:
     def _invalidate(self):
         self._tables = None
         self._dev_params = None
+        from .model_transforms import params_epoch
+        params_epoch[0] += 1
 
     @property
     def channels(self):
@@ -255,6 +257,19 @@ def gaussian_tables(scale_table, tail_mass=2 ** -8):
     return t
 
 
+_scale_table_dev_cache = {}
+
+
+def _scale_table_dev(scale_table):
+    """fp32 device copy of a scale table, uploaded once per table and device (a per-call upload from pageable memory
+    would also be illegal inside CUDA-graph capture)."""
+    key = (scale_table.tobytes(), torch.cuda.current_device())
+    t = _scale_table_dev_cache.get(key)
+    if t is None:
+        t = _scale_table_dev_cache[key] = torch.from_numpy(scale_table.astype(np.float32)).cuda()
+    return t
+
+
 class GaussianConditional:
     """tfc.GaussianConditional(scale, scale_table) with the reference's patch (zero mean, scale_bound=None ->
     scales lower-bounded at scale_table[0], indexes = table search)."""
@@ -268,7 +283,7 @@ class GaussianConditional:
         self.data_format = data_format  # elementwise: only matters for the symbol order of the bitstream
         self._scale_in = scale
         self._scale = scale.to(torch.float32).contiguous()
-        self._table_dev = torch.from_numpy(self.scale_table.astype(np.float32)).cuda()
+        self._table_dev = _scale_table_dev(self.scale_table)
         self._indexes = None
         self.dbg_dec = {}
 

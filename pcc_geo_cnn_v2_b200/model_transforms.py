@@ -82,6 +82,10 @@ class Layer:
         return []
 
 
+# bumped whenever any layer's parameters change: captured CUDA graphs (model_types) hold device pointers of packed weights
+params_epoch = [0]
+
+
 class _ConvBase(Layer):
     transposed = False
 
@@ -113,6 +117,7 @@ class _ConvBase(Layer):
         self.kernel = _seed_state['rng'].uniform(-limit, limit, size=shape).astype(np.float32)
         self.bias = np.zeros((f,), np.float32) if self.use_bias else None
         self._dev = {}
+        params_epoch[0] += 1
 
     def set_weights(self, kernel, bias=None):
         kernel = np.asarray(kernel, np.float32)
@@ -125,6 +130,7 @@ class _ConvBase(Layer):
         else:
             self.bias = None
         self._dev = {}
+        params_epoch[0] += 1
 
     def get_weights(self):
         return {'kernel': self.kernel, 'bias': self.bias}

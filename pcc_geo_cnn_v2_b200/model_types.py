@@ -20,6 +20,7 @@ import torch
 from . import ops
 from .entropy_models import EntropyBottleneck, GaussianConditional, make_scale_table
 from .focal_loss import focal_loss
+from . import model_transforms as _mt
 from .model_transforms import TransformType
 
 logger = logging.getLogger(__name__)
@@ -33,17 +34,26 @@ def sparse_to_dense(block, x_shape, data_format='channels_first'):
     return ops.densify(torch.from_numpy(np.ascontiguousarray(coords)).cuda(), 1, *[int(s) for s in x_shape[2:]])
 
 
-def blocks_to_coords(blocks):
-    """list of (n_i, >=3) arrays -> one int16 (sum n_i, 4) array of (block, z, y, x) rows."""
-    if not len(blocks):
+def blocks_to_coords(blocks, threads=1):
+    """list of (n_i, >=3) arrays -> one int16 (sum n_i, 4) array of (block, z, y, x) rows (C++ host helper)."""
+    n = len(blocks)
+    if not n:
         return np.zeros((0, 4), np.int16)
-    lens = [len(b) for b in blocks]
-    out = np.empty((sum(lens), 4), np.int16)
-    out[:, 0] = np.repeat(np.arange(len(blocks), dtype=np.int16), lens)
-    pos = 0
-    for b, n in zip(blocks, lens):  # one slice assignment per block (float -> int16 cast inside numpy)
-        out[pos:pos + n, 1:] = np.asarray(b)[:, :3]
-        pos += n
+    arrs = [np.asarray(b) for b in blocks]
+    f64 = any(a.dtype == np.float64 for a in arrs)
+    want = np.float64 if f64 else np.float32
+    for i, a in enumerate(arrs):
+        if a.ndim != 2 or a.shape[1] < 3:
+            raise ValueError(f'block {i}: expected (n, >=3) coordinates, got {a.shape}')
+        if a.dtype != want or (len(a) and a.strides[1] != a.itemsize):
+            arrs[i] = np.ascontiguousarray(a, want)
+    counts = np.array([len(a) for a in arrs], np.int64)
+    pitch = np.array([a.strides[0] if len(a) else 0 for a in arrs], np.int64)
+    ptrs = np.array([a.__array_interface__['data'][0] if len(a) else 0 for a in arrs], np.uint64)
+    out = np.empty((int(counts.sum()), 4), np.int16)
+    from . import _lib as L
+    L.check(L.lib().pccgeo_blocks_to_coords_host(L.ptr(ptrs), L.ptr(counts), L.ptr(pitch), n, int(f64), L.ptr(out), int(threads)),
+            'blocks_to_coords')
     return out
 
 
@@ -61,6 +71,77 @@ def threshold_f32(thresholds, idx):
     return t32.astype(np.float32)
 
 
+class _PinnedPool:
+    """Recycled pinned host staging buffers.  cudaHostAlloc costs milliseconds and stalls the driver thread of the block
+    loops (torch's caching host allocator falls back to it whenever every cached block still has a copy in flight), so
+    the pipelines take their staging memory from here: power-of-two byte buffers, handed back explicitly by the consumer
+    (D2H) or after the event behind an H2D copy has fired."""
+
+    def __init__(self):
+        import threading
+        self.free, self.pending, self.lock = {}, [], threading.Lock()
+
+    def get(self, nbytes):
+        cap = 256
+        while cap < nbytes:
+            cap *= 2
+        with self.lock:
+            if self.pending:
+                still = []
+                for buf, ev in self.pending:
+                    if ev.query():
+                        self.free.setdefault(buf.numel(), []).append(buf)
+                    else:
+                        still.append((buf, ev))
+                self.pending = still
+            lst = self.free.get(cap)
+            if lst:
+                return lst.pop()
+        return torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+
+    def put(self, buf):
+        with self.lock:
+            self.free.setdefault(buf.numel(), []).append(buf)
+
+    def put_after(self, buf, event):
+        with self.lock:
+            self.pending.append((buf, event))
+
+
+_pinned = _PinnedPool()
+
+graph_kernel_launches = [0]   # libpccgeo kernels launched through graph replays (bench.py adds them to gpu_launches)
+
+
+class _StageGraph:
+    """fn() captured once into a CUDA graph (after two eager warm-up runs that fill the per-layer device caches); replay()
+    re-runs the whole kernel sequence with ONE launch call -- the Python driver of the block loops then costs microseconds
+    per batch instead of ~60 ctypes launches, and the kernels run back to back without launch gaps.  fn must read its
+    inputs from tensors that outlive the graph (static buffers or outputs of other stage graphs)."""
+
+    def __init__(self, fn):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn()
+            fn()
+        cur.wait_stream(side)
+        side.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        from . import _lib as L
+        l0 = L.lib().pccgeo_launch_count()
+        # thread_local: host workers of the pipeline may call cudaEventSynchronize / pinned allocations meanwhile
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
+            self.out = fn()
+        self.n_kernels = int(L.lib().pccgeo_launch_count() - l0)   # libpccgeo kernels one replay launches
+
+    def replay(self):
+        self.graph.replay()
+        graph_kernel_launches[0] += self.n_kernels
+        return self.out
+
+
 class CompressionModel:
     def __init__(self, n_thresholds=2 ** 8, data_format='channels_first', batch_size=32):
         self.thresholds = np.linspace(0, 1.0, n_thresholds)  # model_types.py:181
@@ -73,6 +154,8 @@ class CompressionModel:
         self.pipeline_depth = 4  # batches in flight (worker threads / CUDA streams) in the block loops
         self.x = self.x_hat = self.strings = self.debug_tensors = None
         self.x_shape = None
+        self.use_graphs = True   # capture the per-batch kernel sequences of the block loops into CUDA graphs
+        self._graphs, self._statics, self._graph_epoch = {}, {}, -1
 
     # -- weights -------------------------------------------------------------------------------------
     def transforms(self):
@@ -106,92 +189,156 @@ class CompressionModel:
         x_hat, bits, _ = self.synthesis_transform.packed(y_hat, thresholds, want_f32=want_x_hat)
         return x_hat, bits
 
+    # -- CUDA-graph stages ---------------------------------------------------------------------------
+    def _stage(self, name, n, dims, fn):
+        """Replay (capturing on first use) the graph of stage `name` for batches of n blocks of size dims."""
+        if self._graph_epoch != _mt.params_epoch[0]:  # parameters changed: packed weights were re-uploaded
+            self._graphs.clear()
+            self._graph_epoch = _mt.params_epoch[0]
+        key = (name, n, tuple(dims), _mt.get_precision(), torch.cuda.current_device())
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = _StageGraph(fn)
+        return g.replay()
+
+    def _static(self, n, dims):
+        """Static device buffers the stage graphs of (n, dims) read their per-batch inputs from."""
+        key = (n, tuple(dims), torch.cuda.current_device())
+        st = self._statics.get(key)
+        if st is None:
+            st = self._statics[key] = {'x': torch.zeros((n, 1) + tuple(dims), device='cuda'),
+                                       'thr': torch.zeros(n, device='cuda'), **self._static_latents(n, dims)}
+        return st
+
+    def device_encode(self, coords_dev, n, dims, thr):
+        """densify -> analysis [-> hyper] -> quantise (latents) -> synthesis + threshold + pack, as stage graphs.
+        coords_dev: CUDA int16 (npts,4); thr: CUDA fp32 (n,) or a host array.  -> (latent dict, bits).  `on_latents`
+        work (the symbol D2H) goes between the two graphs: see encode_blocks."""
+        st = self._static(n, dims)
+        ops.densify(coords_dev, n, *dims, out=st['x'])
+        lat = self._stage('latents', n, dims, lambda: self._latents(st['x']))
+        return lat, st
+
+    def device_synthesis(self, lat, st, n, dims, thr):
+        st['thr'].copy_(thr) if torch.is_tensor(thr) else self._copy_in(st['thr'], thr)
+        return self._stage('synthesis', n, dims, lambda: self._synthesize(lat['y_hat'], st['thr'], False)[1])
+
     # -- batch pipeline ------------------------------------------------------------------------------
-    def _map_batches(self, fn, batches):
-        """Run fn(batch) for every batch, results in order.  With more than one batch, each batch's whole chain
-        (H2D -> kernels -> D2H -> C++ range coding / point extraction) runs in a worker thread on its own CUDA stream,
-        so the host stages of batch i overlap the GPU stages of batch i+1.  ctypes / torch release the GIL in the heavy
-        calls; kernels are per-sample deterministic, so results do not depend on the schedule."""
-        if len(batches) <= 1 or self.pipeline_depth <= 1:
-            self._warmed = True
-            return [fn(b) for b in batches]
-        from concurrent.futures import ThreadPoolExecutor
-        first = []
-        if not getattr(self, '_warmed', False):  # fill the per-layer device caches single-threaded, once per model
-            first = [fn(batches[0])]
-            batches = batches[1:]
-            self._warmed = True
-        dev = torch.cuda.current_device()
-        stream = torch.cuda.current_stream()
+    # The block loops are software pipelines over batches with ONE driver (the calling thread) that owns the CUDA stream
+    # and enqueues every batch's kernels + async pinned copies back to back, and a pool of host workers that run the
+    # C++ stages (coordinate packing, range coding, point extraction; ctypes releases the GIL) as soon as the event
+    # behind their input fires.  The GPU never waits for the host between batches, host coding of batch i overlaps the
+    # kernels of batch i+1..., and results do not depend on the schedule (kernels are per-sample deterministic).
+    def _pool(self):
+        if getattr(self, '_executor', None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._executor = ThreadPoolExecutor(max_workers=max(1, self.pipeline_depth), thread_name_prefix='pccgeo-host')
+        return self._executor
 
-        def run(b):
-            # all workers enqueue on ONE stream: the GPU runs the batches FIFO, so batch i's results (async D2H into
-            # pinned buffers + an event) arrive while batch i+1 is still computing and the workers never fall in lockstep
-            torch.cuda.set_device(dev)
-            with torch.cuda.stream(stream):
-                return fn(b)
-
-        with ThreadPoolExecutor(max_workers=self.pipeline_depth) as pool:
-            rest = list(pool.map(run, batches))
-        return first + rest
+    @staticmethod
+    def _stage_host(arr):
+        """numpy array -> (pinned torch view with the same contents, pool buffer)."""
+        a = np.ascontiguousarray(arr)
+        buf = _pinned.get(max(a.nbytes, 1))
+        t = torch.from_numpy(a)
+        host = buf[:a.nbytes].view(t.dtype).view(t.shape)
+        # plain single-threaded memcpy: torch's CPU copy_ would enter its OpenMP pool, which stalls for milliseconds while the
+        # host workers keep every core busy with range coding
+        np.copyto(host.numpy(), a)
+        return host, buf
 
     @staticmethod
     def _d2h(*tensors):
-        """Enqueue async device->pinned-host copies on the current stream; returns (host tensors, event)."""
-        outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
-        for o, t in zip(outs, tensors):
+        """Enqueue async device->pinned-host copies on the current stream; returns (host tensors, event, pool buffers)."""
+        outs, bufs = [], []
+        for t in tensors:
+            nb = t.numel() * t.element_size()
+            buf = _pinned.get(max(nb, 1))
+            o = buf[:nb].view(t.dtype).view(t.shape)
             o.copy_(t, non_blocking=True)
+            outs.append(o)
+            bufs.append(buf)
         ev = torch.cuda.Event()
         ev.record()
-        return outs, ev
+        return outs, ev, bufs
 
     @staticmethod
     def _wait(pending):
-        outs, ev = pending
-        ev.synchronize()
-        return [o.numpy() for o in outs]
+        pending[1].synchronize()
+        return [o.numpy() for o in pending[0]]
+
+    @staticmethod
+    def _release(pending):
+        """Hand the staging buffers of a finished _d2h back (the numpy views from _wait must not be used afterwards)."""
+        for buf in pending[2]:
+            _pinned.put(buf)
 
     def _chunks(self, items):
         return [items[i:i + self.batch_size] for i in range(0, len(items), self.batch_size)]
 
+    def _copy_in(self, dst, arr):
+        """numpy -> existing CUDA tensor through recycled pinned memory (async on the current stream)."""
+        host, buf = self._stage_host(arr)
+        dst.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _pinned.put_after(buf, ev)
+        return dst
+
     def _h2d(self, arr):
-        """numpy -> CUDA through pinned memory (async on the current stream)."""
-        t = torch.from_numpy(np.ascontiguousarray(arr))
-        return t.pin_memory().cuda(non_blocking=True) if t.numel() else t.cuda()
+        """numpy -> new CUDA tensor through recycled pinned memory (async on the current stream)."""
+        a = np.asarray(arr)
+        dst = torch.empty(a.shape, dtype=torch.from_numpy(np.empty(0, a.dtype)).dtype, device='cuda')
+        return self._copy_in(dst, a) if a.size else dst
 
     # -- public block loops --------------------------------------------------------------------------
     def encode_blocks(self, blocks, x_shape=None, thr_idx=None, keep_x_hat=True):
         """Batched analysis + entropy coding + synthesis.
         Returns (strings per block, x_hat fp32 CUDA (n,1,D,H,W) or None, points per block or None).
-        thr_idx (n,) fixes the per-block threshold so that clip/threshold/bit-pack and the point extraction ride in
-        the same pipelined pass (compress_blocks with fixed_threshold)."""
+        thr_idx (n,) fixes the per-block threshold so that clip/threshold/bit-pack (fused into the last synthesis layer) and
+        the point extraction ride in the same pipelined pass (compress_blocks with fixed_threshold)."""
         dims = [int(s) for s in (x_shape if x_shape is not None else self.x_shape)][-3:]
         spans = [(i, min(i + self.batch_size, len(blocks))) for i in range(0, len(blocks), self.batch_size)]
+        pool = self._pool()
+        coords_f = [pool.submit(blocks_to_coords, blocks[a:b], self.coder_threads) for a, b in spans]
 
-        def run(span):
-            chunk = blocks[span[0]:span[1]]
-            x = ops.densify(self._h2d(blocks_to_coords(chunk)), len(chunk), *dims)
+        def post(dev, pend):
+            strings = self._encode_host(dev, self._wait(pend['sym']))
+            self._release(pend['sym'])
+            pts = None
+            if 'bits' in pend:
+                pts = ops.bits_to_points(self._wait(pend['bits'])[0], dims, self.coder_threads)
+                self._release(pend['bits'])
+            return strings, pts
+
+        post_f, xs = [], []
+        graphs = self.use_graphs and thr_idx is not None and not keep_x_hat
+        for (a, b), cf in zip(spans, coords_f):
+            if len(post_f) >= self.pipeline_depth + 4:  # bound the driver's run-ahead (staging memory in flight)
+                post_f[len(post_f) - self.pipeline_depth - 4].result()
+            if graphs:
+                lat, st = self.device_encode(self._h2d(cf.result()), b - a, dims, None)
+                pend = {'sym': self._d2h(*self._latent_tensors(lat))}
+                pend['bits'] = self._d2h(self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b])))
+                xs.append(None)
+                post_f.append(pool.submit(post, lat, pend))
+                continue
+            x = ops.densify(self._h2d(cf.result()), b - a, *dims)
             pend = {}
+            t = self._h2d(threshold_f32(self.thresholds, thr_idx[a:b])) if thr_idx is not None else None
             # the symbol D2H is enqueued BEFORE synthesis is launched: range coding overlaps the synthesis kernels
-            t = self._h2d(threshold_f32(self.thresholds, thr_idx[span[0]:span[1]])) if thr_idx is not None else None
             dev = self._encode_device(x, lambda d: pend.__setitem__('sym', self._d2h(*self._latent_tensors(d))),
                                       thresholds=t, want_x_hat=keep_x_hat)
-            pts = None
             if thr_idx is not None:
                 pend['bits'] = self._d2h(dev['bits'])
-            strings = self._encode_host(dev, self._wait(pend['sym']))
-            if thr_idx is not None:
-                pts = ops.bits_to_points(self._wait(pend['bits'])[0], dims, self.coder_threads)
-            return strings, (dev['x_hat'] if keep_x_hat else None), pts
-
-        res = self._map_batches(run, spans)
+            xs.append(dev.pop('x_hat'))
+            post_f.append(pool.submit(post, dev, pend))
+        res = [f.result() for f in post_f]
         strings = [s for r in res for s in r[0]]
         x_hat = None
-        if keep_x_hat:
-            xs = [r[1] for r in res]
-            torch.cuda.current_stream().synchronize()
+        if keep_x_hat and xs:
             x_hat = torch.cat(xs) if len(xs) > 1 else xs[0]
-        pts = [q for r in res for q in r[2]] if thr_idx is not None else None
+        pts = [q for r in res for q in r[1]] if thr_idx is not None else None
         return strings, x_hat, pts
 
     def compress_blocks(self, sess, blocks, binstr, points, resolution, level, with_normals=False,
@@ -247,17 +394,60 @@ class CompressionModel:
     def decompress_blocks(self, sess, blocks, x_shape, debug=False):
         """src/model_types.py:220-238: blocks = [(strings, threshold_idx)] -> ([float32 (m,3)], debug list)."""
         dims = tuple(int(s) for s in x_shape)[-3:]
-
-        def run(chunk):
-            strings = [c[0] for c in chunk]
+        chunks = self._chunks(list(blocks))
+        pool = self._pool()
+        strings = [[c[0] for c in chunk] for chunk in chunks]
+        # stage 0 (host): first latent's strings -> symbols; stage 1 (GPU): what the second latent's decoding needs
+        # (hyper-synthesis -> scale indexes); stage 2 (host): second latent; stage 3 (GPU): synthesis + threshold + pack;
+        # stage 4 (host): packed bits -> points
+        f0 = [pool.submit(self._decode_host0, st, dims) for st in strings]
+        ctxs, f2 = [], []
+        graphs = self.use_graphs and not debug
+        for st, f in zip(strings, f0):
+            ctx = self._graph_dev1(f.result(), len(st), dims) if graphs else self._decode_dev1(f.result(), dims)
+            ctxs.append(ctx)
+            f2.append(pool.submit(self._decode_host1, ctx, st))
+        f4, dbgs = [], []
+        for chunk, ctx, f in zip(chunks, ctxs, f2):
+            f.result()
             idx = np.asarray([int(c[1]) for c in chunk], np.int64)
-            x_hat, dbg = self._decode_batch(strings, dims, thresholds=self._h2d(threshold_f32(self.thresholds, idx)),
-                                            want_x_hat=debug)
-            pts = ops.bits_to_points(self._wait(self._d2h(dbg['bits']))[0], dims, self.coder_threads)
-            return pts, [dbg if debug else None] * len(chunk)
+            if graphs:
+                dbg = {'bits': self._graph_dev2(ctx, len(chunk), dims, threshold_f32(self.thresholds, idx))}
+            else:
+                x_hat, dbg = self._decode_dev2(ctx, self._h2d(threshold_f32(self.thresholds, idx)), debug)
+            pend = self._d2h(dbg['bits'])
+            f4.append(pool.submit(self._points_task, pend, dims))
+            dbgs.append([dbg if debug else None] * len(chunk))
+        pts = [f.result() for f in f4]
+        return [p for r in pts for p in r], [d for r in dbgs for d in r]
 
-        res = self._map_batches(run, self._chunks(list(blocks)))
-        return [p for r in res for p in r[0]], [d for r in res for d in r[1]]
+    def _points_task(self, pend, dims):
+        pts = ops.bits_to_points(self._wait(pend)[0], dims, self.coder_threads)
+        self._release(pend)
+        return pts
+
+    def _graph_dev1(self, sym0_host, n, dims):
+        """decode stage 1 as a graph: first latent's symbols (host) -> static buffer -> _dec1_compute."""
+        st = self._static(n, dims)
+        self._copy_in(st['sym0'], sym0_host)
+        ctx = dict(self._stage('dec1', n, dims, lambda: self._dec1_compute(st['sym0'])))
+        if 'indexes' in ctx:
+            ctx['idx_pending'] = self._d2h(ctx['indexes'])
+        return ctx
+
+    def _graph_dev2(self, ctx, n, dims, thr):
+        """decode stage 3 as a graph: [second latent's symbols ->] synthesis + threshold + pack -> bits."""
+        st = self._static(n, dims)
+        if 'ysym' in ctx:
+            st['sym1'].copy_(ctx['ysym']) if torch.is_tensor(ctx['ysym']) else self._copy_in(st['sym1'], ctx['ysym'])
+        st['thr'].copy_(thr) if torch.is_tensor(thr) else self._copy_in(st['thr'], thr)
+        return self._stage('dec2', n, dims, lambda: self._dec2_compute(ctx, st))
+
+    def _decode_batch(self, strings_list, dims, thresholds=None, want_x_hat=True):
+        """One batch through the four decode stages, sequentially."""
+        ctx = self._decode_dev1(self._decode_host0(strings_list, dims), dims)
+        self._decode_host1(ctx, strings_list)
+        return self._decode_dev2(ctx, thresholds, want_x_hat)
 
     # -- training graph (forward values; see DESIGN.md for the backward status) ----------------------
     def _finish_train(self, x, x_tilde, log_sums, gamma, alpha, lmbda):
@@ -308,10 +498,23 @@ class CompressionModelV1(CompressionModel):
     def decompress(self):  # model_types.py:297-309
         pass
 
-    def _encode_device(self, x, after_latents=None, thresholds=None, want_x_hat=True):
+    def _latents(self, x):
         y = self.analysis_transform(x)
         y_sym, y_hat = self.entropy_bottleneck.quantize(y)
-        dev = {'y_sym': y_sym, 'y_hat': y_hat}
+        return {'y_sym': y_sym, 'y_hat': y_hat}
+
+    def _static_latents(self, n, dims):
+        return {'sym0': torch.zeros((n, self.num_filters) + tuple(d // 8 for d in dims), device='cuda', dtype=torch.int32)}
+
+    def _dec1_compute(self, sym0):
+        return {'y_hat': ops.eb_dequantize(sym0, self.entropy_bottleneck.device_params())}
+
+    def _dec2_compute(self, ctx, st):
+        return self._synthesize(ctx['y_hat'], st['thr'], False)[1]  # ctx['y_hat']: static output of the 'dec1' graph
+
+    def _encode_device(self, x, after_latents=None, thresholds=None, want_x_hat=True):
+        dev = self._latents(x)
+        y_hat = dev['y_hat']
         if after_latents is not None:
             after_latents(dev)
         x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
@@ -329,11 +532,18 @@ class CompressionModelV1(CompressionModel):
         ys = self.entropy_bottleneck.encode_symbols(y_sym, self.coder_threads)
         return [(s,) for s in ys]
 
-    def _decode_batch(self, strings_list, dims, thresholds=None, want_x_hat=True):
-        f = self.num_filters
-        shp = (f,) + tuple(d // 8 for d in dims)  # model_types.py:305
-        sym = self.entropy_bottleneck.decode_symbols([s[0] for s in strings_list], shp, self.coder_threads)
-        y_hat = ops.eb_dequantize(self._h2d(sym), self.entropy_bottleneck.device_params())
+    def _decode_host0(self, strings_list, dims):
+        shp = (self.num_filters,) + tuple(d // 8 for d in dims)  # model_types.py:305
+        return self.entropy_bottleneck.decode_symbols([s[0] for s in strings_list], shp, self.coder_threads)
+
+    def _decode_dev1(self, sym, dims):
+        return {'y_hat': ops.eb_dequantize(self._h2d(sym), self.entropy_bottleneck.device_params())}
+
+    def _decode_host1(self, ctx, strings_list):
+        return None
+
+    def _decode_dev2(self, ctx, thresholds=None, want_x_hat=True):
+        y_hat = ctx['y_hat']
         x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
         self.x_hat = x_hat
         return x_hat, {'y_hat': y_hat, 'x_hat': x_hat, 'bits': bits}
@@ -383,15 +593,33 @@ class CompressionModelV2(CompressionModel):
     def decompress(self):  # model_types.py:393-411
         pass
 
-    def _encode_device(self, x, after_latents=None, thresholds=None, want_x_hat=True):
+    def _latents(self, x):
         y = self.analysis_transform(x)
         z = self.hyper_analysis_transform(y)
         z_sym, z_hat = self.entropy_bottleneck.quantize(z)
         sigma_hat = self.hyper_synthesis_transform(z_hat)
         cb = GaussianConditional(sigma_hat, self.scale_table, data_format=self.data_format)
         y_sym, y_hat, idx = cb.quantize(y)
-        dev = {'y': y, 'z': z, 'z_sym': z_sym, 'z_hat': z_hat, 'sigma_hat': sigma_hat, 'y_sym': y_sym, 'y_hat': y_hat,
-               'indexes': idx, 'cb': cb}
+        return {'y': y, 'z': z, 'z_sym': z_sym, 'z_hat': z_hat, 'sigma_hat': sigma_hat, 'y_sym': y_sym, 'y_hat': y_hat,
+                'indexes': idx, 'cb': cb}
+
+    def _static_latents(self, n, dims):
+        f = self.num_filters
+        return {'sym0': torch.zeros((n, f) + tuple(d // 16 for d in dims), device='cuda', dtype=torch.int32),
+                'sym1': torch.zeros((n, f) + tuple(d // 8 for d in dims), device='cuda', dtype=torch.int32)}
+
+    def _dec1_compute(self, zsym):
+        z_hat = ops.eb_dequantize(zsym, self.entropy_bottleneck.device_params())
+        sigma_hat = self.hyper_synthesis_transform(z_hat)
+        cb = GaussianConditional(sigma_hat, self.scale_table, data_format=self.data_format)
+        return {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'cb': cb, 'indexes': cb.indexes()}
+
+    def _dec2_compute(self, ctx, st):
+        return self._synthesize(ops.i32_to_f32(st['sym1']), st['thr'], False)[1]
+
+    def _encode_device(self, x, after_latents=None, thresholds=None, want_x_hat=True):
+        dev = self._latents(x)
+        z_hat, sigma_hat, idx, y_hat = dev['z_hat'], dev['sigma_hat'], dev['indexes'], dev['y_hat']
         if after_latents is not None:
             after_latents(dev)
         x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
@@ -410,19 +638,26 @@ class CompressionModelV2(CompressionModel):
         ys = dev['cb'].encode_symbols(y_sym, idx, self.coder_threads)
         return list(zip(ys, zs))  # (y_string, z_string): model_types.py:389
 
-    def _decode_batch(self, strings_list, dims, thresholds=None, want_x_hat=True):
-        f = self.num_filters
-        zshp = (f,) + tuple(d // 16 for d in dims)  # model_types.py:403
-        zsym = self.entropy_bottleneck.decode_symbols([s[1] for s in strings_list], zshp, self.coder_threads)
-        z_hat = ops.eb_dequantize(self._h2d(zsym), self.entropy_bottleneck.device_params())
-        sigma_hat = self.hyper_synthesis_transform(z_hat)
-        cb = GaussianConditional(sigma_hat, self.scale_table, data_format=self.data_format)
-        idx = cb.indexes()
-        ysym = cb.decode_symbols([s[0] for s in strings_list], self._wait(self._d2h(idx))[0], self.coder_threads)
-        y_hat = ops.i32_to_f32(self._h2d(ysym))
+    def _decode_host0(self, strings_list, dims):
+        zshp = (self.num_filters,) + tuple(d // 16 for d in dims)  # model_types.py:403
+        return self.entropy_bottleneck.decode_symbols([s[1] for s in strings_list], zshp, self.coder_threads)
+
+    def _decode_dev1(self, zsym, dims):
+        ctx = self._dec1_compute(self._h2d(zsym))
+        ctx['idx_pending'] = self._d2h(ctx['indexes'])
+        return ctx
+
+    def _decode_host1(self, ctx, strings_list):
+        pend = ctx.pop('idx_pending')
+        ctx['ysym'] = ctx['cb'].decode_symbols([s[0] for s in strings_list], self._wait(pend)[0], self.coder_threads)
+        self._release(pend)
+
+    def _decode_dev2(self, ctx, thresholds=None, want_x_hat=True):
+        y_hat = ops.i32_to_f32(self._h2d(ctx['ysym']))
         x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
         self.x_hat = x_hat
-        return x_hat, {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat, 'bits': bits}
+        return x_hat, {'z_hat': ctx['z_hat'], 'sigma_hat': ctx['sigma_hat'], 'indexes': ctx['indexes'], 'y_hat': y_hat,
+                       'x_hat': x_hat, 'bits': bits}
 
 
 class ModelType(Enum):

@@ -158,6 +158,32 @@ def test_encode_decode_self_consistency(config, size):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize('config,size', [('c3p', 64), ('c1', 64)])
+def test_graph_pipeline_equals_eager_pipeline(config, size):
+    """The CUDA-graph stage replays of the block loops produce the same bytes and points as the eager launches, over
+    several ragged batches in flight, and survive a parameter change (graphs are re-captured)."""
+    m = _model(config, 7)
+    m.batch_size = 3
+    blocks = synthetic.surface_blocks(8, size=size, seed=21)
+    m.compress((1, 1, size, size, size))
+    out = {}
+    for graphs in (True, False, True):
+        m.use_graphs = graphs
+        dl, meta, _ = m.compress_blocks(None, blocks, None, None, size, 0, fixed_threshold=True)
+        dec, _ = m.decompress_blocks(None, dl[0], (size, size, size))
+        cur = ([s for s, _ in dl[0]], [p.tobytes() for p in meta[0]['x_hat_list']], [p.tobytes() for p in dec])
+        assert out.setdefault('ref', cur) == cur
+    assert m._graphs, 'the graph path did not run'
+    # new parameters -> stale graphs must not be replayed
+    m.use_graphs = True
+    m.set_weights(synthetic.trained_like_weights(m, seed=8))
+    dl2, meta2, _ = m.compress_blocks(None, blocks, None, None, size, 0, fixed_threshold=True)
+    m.use_graphs = False
+    dl3, meta3, _ = m.compress_blocks(None, blocks, None, None, size, 0, fixed_threshold=True)
+    assert [s for s, _ in dl2[0]] == [s for s, _ in dl3[0]] and [s for s, _ in dl2[0]] != out['ref'][0]
+    assert all(np.array_equal(a, b) for a, b in zip(meta2[0]['x_hat_list'], meta3[0]['x_hat_list']))
+
+
 def test_train_forward_matches_oracle():
     """tr_train.py path forward values (model_types.py:327-355): loss = lambda*FL + mbpov with the SAME noise."""
     m = _model('c3p', 21)

@@ -1,6 +1,7 @@
 """Host-side logic of the product (table construction, threshold rounding, block packing, tracing) against the
 oracle -- CPU only, no kernels."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import entropy as E
@@ -97,3 +98,25 @@ def test_bits_to_points_cpp_matches_numpy():
         want = np.argwhere(occ[j]).astype(np.float32)
         assert got[j].dtype == np.float32 and np.array_equal(got[j], want)
         assert np.array_equal(MTY.bits_to_points(words[j], (8, 16, 32)), want)
+
+
+def test_blocks_to_coords_host_helper_matches_numpy():
+    """C++ coordinate packer (host half of sparse_to_dense, model_types.py:108-114) against the numpy statement."""
+    from pcc_geo_cnn_v2_b200.model_types import blocks_to_coords
+    rng = np.random.default_rng(5)
+
+    def ref(blocks):
+        rows = [np.concatenate([np.full((len(b), 1), i, np.int16), np.asarray(b)[:, :3].astype(np.int16)], 1) for i, b in enumerate(blocks)]
+        return np.concatenate(rows) if rows else np.zeros((0, 4), np.int16)
+
+    b32 = [rng.integers(0, 64, size=(n, 3)).astype(np.float32) for n in (5, 0, 1000, 1)]
+    assert np.array_equal(blocks_to_coords(b32, threads=3), ref(b32))
+    with_normals = [np.concatenate([b, rng.normal(size=(len(b), 3)).astype(np.float32)], 1) for b in b32]
+    assert np.array_equal(blocks_to_coords(with_normals), ref(b32))
+    b64 = [b.astype(np.float64) for b in b32]
+    assert np.array_equal(blocks_to_coords(b64, threads=2), ref(b32))
+    mixed = [b32[0], b64[2], np.asfortranarray(with_normals[2]), rng.integers(0, 64, size=(7, 3))]  # dtype / layout mix
+    assert np.array_equal(blocks_to_coords(mixed), ref(mixed))
+    assert blocks_to_coords([]).shape == (0, 4)
+    with pytest.raises(ValueError):
+        blocks_to_coords([np.zeros((4, 2), np.float32)])

@@ -26,14 +26,18 @@ coords = torch.from_numpy(blocks_to_coords(blocks)).cuda()
 thr = torch.from_numpy(threshold_f32(m.thresholds, np.full(B, 128))).cuda()
 
 
-def device_step():
-    x = ops.densify(coords, B, 64, 64, 64)
-    dev = m._encode_device(x, thresholds=thr, want_x_hat=False)  # as compress_blocks(fixed_threshold=True) runs it
-    z_hat = ops.eb_dequantize(dev['z_sym'], m.entropy_bottleneck.device_params())
-    sigma = m.hyper_synthesis_transform(z_hat)
-    GaussianConditional(sigma, m.scale_table).indexes()
-    return m.synthesis_transform.packed(ops.i32_to_f32(dev['y_sym']), thr)
+dims = (64, 64, 64)
 
+
+def device_step():
+    # the per-batch device work of compress_blocks(fixed_threshold=True) + decompress_blocks, inputs resident in HBM:
+    # densify + stage graphs (latents | synthesis+pack) for encode, (hyper-synthesis+indexes | synthesis+pack) for decode
+    lat, st = m.device_encode(coords, B, dims, None)
+    m.device_synthesis(lat, st, B, dims, thr)
+    st['sym0'].copy_(lat['z_sym'])
+    ctx = dict(m._stage('dec1', B, dims, lambda: m._dec1_compute(st['sym0'])))
+    ctx['ysym'] = lat['y_sym']
+    return m._graph_dev2(ctx, B, dims, thr)
 
 for _ in range(5):
     device_step()
