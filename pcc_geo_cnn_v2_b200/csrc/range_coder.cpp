@@ -233,12 +233,14 @@ extern "C" int pccgeo_range_encode_host(const int32_t* symbols, const int32_t* i
     return PCCGEO_EINVAL;
   }
   Tables t{cdf, cdf_stride, cdf_length, offset, rows, index_mode, channel_stride};
-  std::vector<Encoder> encs(nstreams);
+  std::vector<std::vector<uint8_t>> outs(nstreams);
   std::atomic<int> bad{0};
   parallel_for(nstreams, threads, [&](int i) {
     const long long a = sym_offsets[i], b = sym_offsets[i + 1];
-    encs[i].out.reserve((size_t)((b - a) / 4 + 16));
-    if (!encode_stream(t, symbols + a, index_mode == 0 ? indexes + a : nullptr, b - a, encs[i])) bad.store(1);
+    Encoder enc;  // coder state on this thread's stack: neighbouring streams' states must not share cache lines
+    enc.out.reserve((size_t)((b - a) / 2 + 64));
+    if (!encode_stream(t, symbols + a, index_mode == 0 ? indexes + a : nullptr, b - a, enc)) bad.store(1);
+    outs[i] = std::move(enc.out);
   });
   if (bad.load()) {
     pccgeo::set_error("range_encode: table index out of range");
@@ -247,7 +249,7 @@ extern "C" int pccgeo_range_encode_host(const int32_t* symbols, const int32_t* i
   long long pos = 0;
   out_offsets[0] = 0;
   for (int i = 0; i < nstreams; ++i) {
-    pos += (long long)encs[i].out.size();
+    pos += (long long)outs[i].size();
     out_offsets[i + 1] = pos;
   }
   if (!out_bytes || pos > out_capacity) {
@@ -255,7 +257,7 @@ extern "C" int pccgeo_range_encode_host(const int32_t* symbols, const int32_t* i
     return PCCGEO_ENOSPC;
   }
   for (int i = 0; i < nstreams; ++i)
-    if (!encs[i].out.empty()) std::memcpy(out_bytes + out_offsets[i], encs[i].out.data(), encs[i].out.size());
+    if (!outs[i].empty()) std::memcpy(out_bytes + out_offsets[i], outs[i].data(), outs[i].size());
   return PCCGEO_OK;
 }
 

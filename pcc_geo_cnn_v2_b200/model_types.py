@@ -148,10 +148,12 @@ class CompressionModel:
         self.data_format = data_format
         self.batch_size = batch_size
         import os
-        # host threads per range-coder / point-extraction call: a quarter of the cores, because `pipeline_depth` batches
-        # are coded concurrently (measured on the 16-core B200 host: depth 4 x 4 threads is the sweet spot)
-        self.coder_threads = max(1, (os.cpu_count() or 4) // 4)
-        self.pipeline_depth = 4  # batches in flight (worker threads / CUDA streams) in the block loops
+        # host threads: this rank's share of the cores (one process per GPU under torchrun); `pipeline_depth` host workers
+        # run the C++ stages of different batches concurrently, each call with `coder_threads` threads (sweep on the
+        # 16-core B200 host: 3 workers x 8 threads)
+        cores = max(1, (os.cpu_count() or 4) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))
+        self.coder_threads = max(1, cores // 2)
+        self.pipeline_depth = 3
         self.x = self.x_hat = self.strings = self.debug_tensors = None
         self.x_shape = None
         self.use_graphs = True   # capture the per-batch kernel sequences of the block loops into CUDA graphs

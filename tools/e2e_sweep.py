@@ -15,8 +15,9 @@ m.set_weights(synthetic.trained_like_weights(m, seed=42))
 m.compress((1, 1, 64, 64, 64))
 uniq = synthetic.surface_blocks(8, size=64, seed=100)
 blocks = [uniq[i % 8] for i in range(B * NB)]
-for depth, thr in ((1, 0), (2, 0), (3, 0), (4, 0), (3, 8), (4, 4), (6, 4)):
+for depth, thr in ((4, 4), (2, 8), (2, 16), (3, 8), (3, 16), (4, 8), (4, 16), (6, 4), (6, 8)):
     m.pipeline_depth, m.coder_threads = depth, thr
+    m._executor = None
     for _ in range(2):
         dl, _, _ = m.compress_blocks(None, blocks, None, None, 64, 0, fixed_threshold=True)
         m.decompress_blocks(None, dl[0], (64, 64, 64))
