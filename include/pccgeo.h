@@ -82,6 +82,14 @@ int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, c
                        void* yb, int n, int cin, int d, int h, int wd, int cout, int stride, int transposed,
                        int relu, int terms, void* stream);
 
+/* y-stacked variant of pccgeo_conv3d_umma for stride-1 3x3x3 layers with <= 16 input and output channels (the second and
+ * third layer of AnalysisBlock / SynthesisBlock at 16 filters, src/model_transforms.py:62-81): z AND y taps are stacked in
+ * the MMA N dimension (3 MMAs of N=144 per input plane and precision pair instead of 9 of N=48); the epilogue adds the
+ * three row partials.  Own weight image (pccgeo_umma_ys_pack_weights_host).  W % 8 == 0, any H. */
+long long pccgeo_umma_ys_pack_weights_host(const float* w_host, void* wpacked_host, int cin, int cout, int transposed, int terms);
+int pccgeo_conv3d_umma_ys(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
+                          int n, int cin, int d, int h, int wd, int cout, int relu, int terms, void* stream);
+
 /* Last layer of the V2 synthesis transforms, Conv3DTranspose(1, (3,3,3), 'same') + BiasAdd + Relu
  * (src/model_transforms.py:107,135), fused with what compress_blocks / decompress_blocks do with x_hat: clip to [0,1],
  * compare with the block's threshold, pack (src/model_types.py:201-202,209,233-234).  Scatter-form tcgen05 kernel: the 27

@@ -82,6 +82,11 @@ class Layer:
         return []
 
 
+# The y-stacked 16-channel kernel (conv3d_umma_ys.cu) keeps the tensor pipe busier (57 % vs 42 % active) but its heavier
+# epilogue (row shuffles) makes it finish in the same time as the z-stacked kernel on B200 (0.373 vs 0.368 ms):
+# parity-tested, off by default.
+_ys_enabled = [False]
+
 # bumped whenever any layer's parameters change: captured CUDA graphs (model_types) hold device pointers of packed weights
 params_epoch = [0]
 
@@ -155,6 +160,9 @@ class _ConvBase(Layer):
                 terms = int(key[-1])
                 self._dev[key] = ops.gemm_pack_weights(self.tap_major(), self.in_channels, self.filters, self.k, self.stride,
                                                        self.transposed, terms)
+            elif key.startswith('w_ummays'):
+                terms = int(key[-1])
+                self._dev[key] = ops.umma_ys_pack_weights(self.tap_major(), self.in_channels, self.filters, self.transposed, terms)
             elif key.startswith('w_out1'):
                 terms = int(key[-1])
                 self._dev[key] = ops.out1_pack_weights(self.tap_major(), self.in_channels, self.transposed, terms)
@@ -175,6 +183,13 @@ class _ConvBase(Layer):
         if self.k == 3 and self.stride == 2 and self.transposed:
             return c >= 8 and cp <= 32 and fp <= 16 and tiled
         return self.k == 3 and self.stride == 1 and c >= 8 and cp <= 32 and fp <= 32 and tiled
+
+    def ys_eligible(self, in_shape):
+        """y-stacked TMA kernel: 3x3x3 stride-1 layers with 9..16 input and output channels on volumes tall enough for its
+        14-row tiles to pay (H >= 28)."""
+        n, c, d, h, w = in_shape
+        return (self.k == 3 and self.stride == 1 and 8 <= c <= 16 and 8 < self.filters <= 16 and w % 8 == 0 and h >= 28
+                and _ys_enabled[0])
 
     def out1_eligible(self, in_shape):
         """Scatter-form single-output-channel kernel (last layer of the V2 synthesis transforms), fusable with the
@@ -454,6 +469,11 @@ def run_steps(steps, out_id, x, pack=None):
                 if pack:
                     return xh, bits, counts
                 vals[dst] = _Val(f32=xh, shape=tuple(xh.shape))
+            elif terms and layer.ys_eligible(v.shape):
+                rb = vals[res].as_blk(terms) if res is not None else None
+                yb, shp = ops.conv3d_umma_ys(v.as_blk(terms), v.shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'),
+                                             layer.filters, layer.relu, terms, rb)
+                vals[dst] = _Val(blk=yb, shape=shp, terms=terms)
             elif terms and layer.umma_eligible(v.shape):
                 rb = vals[res].as_blk(terms) if res is not None else None
                 yb, shp = ops.conv3d_umma(v.as_blk(terms), v.shape, layer.dev(f'w_umma{terms}'), layer.dev('bias'),

@@ -142,6 +142,38 @@ def test_umma_stride2_transposed_matches_oracle(cin, cout, shape, n, terms, tol)
     assert torch.equal(yb2, yb3)
 
 
+UMMA_YS_CASES = [
+    # transposed, cin, cout, (D,H,W), n
+    (False, 16, 16, (4, 28, 8), 1), (True, 16, 16, (8, 32, 16), 2), (False, 16, 16, (1, 64, 8), 1), (True, 16, 16, (2, 40, 24), 3),
+    (False, 12, 10, (5, 30, 8), 2), (True, 16, 16, (11, 14, 8), 1), (True, 16, 16, (64, 64, 64), 2),
+]
+
+
+@pytest.mark.parametrize('terms,tol', [(2, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize('transposed,cin,cout,shape,n', UMMA_YS_CASES)
+def test_umma_ystacked_conv_matches_oracle(transposed, cin, cout, shape, n, terms, tol):
+    """16-filter stride-1 layers of AnalysisBlock / SynthesisBlock (model_transforms.py:62-81) on the y-stacked kernel,
+    incl. heights that are not multiples of its 14-row tile, fused bias + ReLU + residual."""
+    rng = np.random.default_rng(hash((transposed, cin, cout, shape, n)) % 2 ** 31)
+    x, kern, bias = _case(rng, transposed, 3, 1, cin, cout, shape, n)
+    res = torch.from_numpy(rng.normal(size=(n, cout) + shape).astype(np.float32))
+    want = _oracle(x, kern, bias, 1, True, transposed, res)
+    wp = ops.umma_ys_pack_weights(_tap_major(kern, transposed).numpy(), cin, cout, transposed, terms)
+    xb = ops.f32_to_blocked(x.cuda(), terms)
+    rb = ops.f32_to_blocked(res.cuda(), terms)
+    yb, shp = ops.conv3d_umma_ys(xb, tuple(x.shape), wp, bias.cuda(), cout, True, terms, rb)
+    got = ops.blocked_to_f32(yb, shp, terms)
+    torch.cuda.synchronize()
+    err = float((got.cpu().double() - want).abs().max())
+    scale = float(want.abs().max())
+    assert err < tol * scale, f'max err {err:.3e} vs scale {scale:.3e}'
+    yb2, _ = ops.conv3d_umma_ys(xb, tuple(x.shape), wp, None, cout, False, terms)
+    want2 = _oracle(x, kern, None, 1, False, transposed)
+    assert float((ops.blocked_to_f32(yb2, shp, terms).cpu().double() - want2).abs().max()) < tol * float(want2.abs().max())
+    yb3, _ = ops.conv3d_umma_ys(xb, tuple(x.shape), wp, None, cout, False, terms)
+    assert torch.equal(yb2, yb3)   # deterministic
+
+
 OUT1_CASES = [
     # transposed, cin, (D,H,W), n
     (True, 16, (4, 16, 8), 1), (True, 16, (16, 16, 16), 2), (False, 16, (5, 32, 24), 2), (True, 16, (1, 16, 8), 1),
