@@ -199,6 +199,44 @@ bool decode_stream(const Tables& t, const uint8_t* b, const uint8_t* e, const in
   return true;
 }
 
+// Two independent streams of equal length decoded in lockstep by one thread: the per-symbol dependency chain (divide ->
+// table search -> range update -> renormalise) is latency-bound, so interleaving two chains nearly doubles the symbols per
+// second of an out-of-order core.  Same results as two decode_stream calls.
+bool decode_stream_x2(const Tables& t, const uint8_t* b0, const uint8_t* e0, const uint8_t* b1, const uint8_t* e1,
+                      const int32_t* idx0, const int32_t* idx1, long long n, int32_t* out0, int32_t* out1) {
+  Decoder d0(b0, e0), d1(b1, e1);
+  const uint32_t max_overflow = (1u << kOverflowWidth) - 1;
+  auto escape = [&](Decoder& dec, long long& value, int32_t max_value) -> bool {
+    int widths = 0;
+    for (;;) {
+      const uint32_t v = dec.decode_uniform(kOverflowWidth);
+      widths += (int)v;
+      if (v != max_overflow) break;
+      if (widths > 64) return false;
+    }
+    if (widths > 16) return false;
+    uint64_t overflow = 0;
+    for (int j = 0; j < widths; ++j) overflow |= (uint64_t)dec.decode_uniform(kOverflowWidth) << (j * kOverflowWidth);
+    value = (long long)(overflow >> 1);
+    if (overflow & 1) value = -value - 1; else value += max_value;
+    return true;
+  };
+  for (long long i = 0; i < n; ++i) {
+    const int r0 = t.index(idx0, i), r1 = t.index(idx1, i);
+    if (r0 < 0 || r0 >= t.rows || r1 < 0 || r1 >= t.rows) return false;
+    const int32_t* row0 = t.cdf + (long long)r0 * t.cdf_stride;
+    const int32_t* row1 = t.cdf + (long long)r1 * t.cdf_stride;
+    const int32_t m0 = t.cdf_length[r0] - 2, m1 = t.cdf_length[r1] - 2;
+    long long v0 = d0.decode(row0, m0 + 1, kPrecision, t.lut ? t.lut + (long long)r0 * 256 : nullptr);
+    long long v1 = d1.decode(row1, m1 + 1, kPrecision, t.lut ? t.lut + (long long)r1 * 256 : nullptr);
+    if (v0 == m0 && !escape(d0, v0, m0)) return false;
+    if (v1 == m1 && !escape(d1, v1, m1)) return false;
+    out0[i] = (int32_t)(v0 + t.offset[r0]);
+    out1[i] = (int32_t)(v1 + t.offset[r1]);
+  }
+  return true;
+}
+
 template <class F>
 void parallel_for(int n, int threads, F&& f) {
   if (threads < 1) threads = 1;
@@ -287,11 +325,26 @@ extern "C" int pccgeo_range_decode_host(const uint8_t* bytes, const long long* b
   }
   t.lut = lut.data();
   std::atomic<int> bad{0};
-  parallel_for(nstreams, threads, [&](int i) {
+  // streams are decoded in pairs (two interleaved dependency chains per thread) when neighbours have equal length
+  const int npairs = (nstreams + 1) / 2;
+  parallel_for(npairs, threads, [&](int pi) {
+    const int i = 2 * pi, j = i + 1;
     const long long a = sym_offsets[i], b = sym_offsets[i + 1];
-    if (!decode_stream(t, base + byte_offsets[i], base + byte_offsets[i + 1], index_mode == 0 ? indexes + a : nullptr,
-                       b - a, symbols_out + a))
-      bad.store(1);
+    const int32_t* ia = index_mode == 0 ? indexes + a : nullptr;
+    if (j < nstreams && sym_offsets[j + 1] - sym_offsets[j] == b - a && index_mode == 0) {
+      const long long c = sym_offsets[j];
+      if (!decode_stream_x2(t, base + byte_offsets[i], base + byte_offsets[i + 1], base + byte_offsets[j], base + byte_offsets[j + 1],
+                            ia, indexes + c, b - a, symbols_out + a, symbols_out + c))
+        bad.store(1);
+      return;
+    }
+    if (!decode_stream(t, base + byte_offsets[i], base + byte_offsets[i + 1], ia, b - a, symbols_out + a)) bad.store(1);
+    if (j < nstreams) {
+      const long long c = sym_offsets[j], d = sym_offsets[j + 1];
+      if (!decode_stream(t, base + byte_offsets[j], base + byte_offsets[j + 1], index_mode == 0 ? indexes + c : nullptr, d - c,
+                         symbols_out + c))
+        bad.store(1);
+    }
   });
   if (bad.load()) {
     pccgeo::set_error("range_decode: corrupt stream");
