@@ -5,7 +5,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--blocks B] [--precision bf16x3|bf16|fp32]
 
 One "step" = one batch of B blocks per GPU through encode (densify, analysis, hyper-analysis, quantise, hyper-synthesis,
-scale indexes, synthesis) and decode (dequantise, hyper-synthesis, indexes, synthesis, clip/threshold/bit-pack).
+scale indexes, synthesis + clip/threshold/bit-pack) and decode (dequantise, hyper-synthesis, indexes, synthesis +
+clip/threshold/bit-pack), launched exactly as compress_blocks(fixed_threshold=True) / decompress_blocks launch them:
+densify + four CUDA-graph stage replays.
   value : device-resident throughput -- point coordinates / int32 symbols already in HBM, CUDA events around the K steps
           (the host range coder is not in this region; it is in e2e).
   e2e   : the same metric through the reference-facing API model.compress_blocks()/decompress_blocks() with HOST
