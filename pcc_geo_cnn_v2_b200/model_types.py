@@ -26,6 +26,107 @@ from .model_transforms import TransformType
 logger = logging.getLogger(__name__)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# host glue of the training script (reference src/model_types.py:23-62,65-105,121-125), same names and argument meaning
+# ---------------------------------------------------------------------------------------------------------
+class SparseBlock:
+    """Stand-in for tf.sparse.SparseTensor(indices, ones, dense_shape) as pc_to_tf builds it."""
+
+    def __init__(self, indices, dense_shape):
+        self.indices, self.dense_shape = np.asarray(indices, np.int64), tuple(int(s) for s in dense_shape)
+
+
+def pc_to_tf(points, dense_tensor_shape, data_format):  # model_types.py:23-32
+    x = np.asarray(points, np.int64)
+    assert data_format in ['channels_last', 'channels_first']
+    pad = [[0, 0], [0, 1]] if data_format == 'channels_last' else [[0, 0], [1, 0]]  # the channel index (always 0)
+    return SparseBlock(np.pad(x, pad), dense_tensor_shape)
+
+
+def process_x(x, dense_tensor_shape):  # model_types.py:35-39: sparse -> dense fp32, on the GPU (densify kernel)
+    shape = tuple(int(s) for s in dense_tensor_shape)
+    assert shape == x.dense_shape
+    last = shape[-1] == 1 and shape[0] != 1
+    sp = x.indices[:, :3] if last else x.indices[:, 1:]
+    dims = shape[:3] if last else shape[1:]
+    coords = np.concatenate([np.zeros((len(sp), 1), np.int16), sp.astype(np.int16)], axis=1)
+    dense = ops.densify(torch.from_numpy(np.ascontiguousarray(coords)).cuda() if len(sp) else None, 1, *dims)
+    return dense.reshape(shape)
+
+
+def quantize_tensor(x):  # model_types.py:42-46 (TensorBoard summaries only)
+    return torch.round(torch.clamp(x, 0, 1)).to(torch.uint8)
+
+
+def add_channels(shape, channels, data_format):  # model_types.py:121-125
+    shape = [int(s) for s in shape]
+    return [int(channels)] + shape if data_format == 'channels_first' else shape + [int(channels)]
+
+
+def get_normals_if(x, with_normals):  # model_types.py:117-118
+    return x[:, x.shape[1] - 3:x.shape[1]] if with_normals else None
+
+
+def input_fn(points, batch_size, dense_tensor_shape, data_format, repeat=True, shuffle=True, prefetch_size=1):
+    """model_types.py:49-62 as a Python generator of (B, ...) fp32 CUDA batches: shuffle over the whole set every epoch
+    (numpy's global RNG, seeded by the caller like tr_train.py:20), repeat, batch (the last partial batch is kept, as
+    tf.data's batch()), and `prefetch_size` batches packed (C++ coordinate packer) ahead on a host thread."""
+    import queue
+    import threading
+    points = list(points)
+    shape = tuple(int(s) for s in dense_tensor_shape)
+    last = data_format == 'channels_last'
+    dims = shape[:3] if last else shape[1:]
+
+    def batches():
+        while True:
+            order = np.random.permutation(len(points)) if shuffle else np.arange(len(points))
+            for i in range(0, len(order), batch_size):
+                chunk = [np.asarray(points[j], np.float32) for j in order[i:i + batch_size]]
+                yield len(chunk), blocks_to_coords(chunk)
+            if not repeat:
+                return
+
+    q = queue.Queue(maxsize=max(1, int(prefetch_size)))
+
+    def producer():
+        for item in batches():
+            q.put(item)
+        q.put(None)
+
+    threading.Thread(target=producer, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is None:
+            return
+        n, coords = item
+        x = ops.densify(torch.from_numpy(coords).cuda() if len(coords) else None, n, *dims)
+        yield x.reshape((n,) + shape)
+
+
+def binary_classification_summaries(x_quant, x_tilde_quant):  # model_types.py:91-105
+    xq, xt = x_quant.to(torch.float32), x_tilde_quant.to(torch.float32)
+    tp = torch.count_nonzero(xt * xq).double()
+    tn = torch.count_nonzero((xt - 1) * (xq - 1)).double()
+    fp = torch.count_nonzero(xt * (xq - 1)).double()
+    fn = torch.count_nonzero((xt - 1) * xq).double()
+    precision, recall = tp / (tp + fp), tp / (tp + fn)
+    return {'bc/precision': precision, 'bc/recall': recall, 'bc/accuracy': (tp + tn) / (tp + tn + fp + fn),
+            'bc/specificity': tn / (tn + fp), 'bc/f1_score': (2 * precision * recall) / (precision + recall)}
+
+
+def v1_summaries(train_loss, mbpov_y, mbpov_total, train_fl, log_y_likelihoods, num_occupied_voxels, x, x_tilde,
+                 x_tilde_quant, y, y_likelihoods, y_tilde):  # model_types.py:65-79: name -> scalar / histogram source tensor
+    return {'loss': train_loss, 'mbpov/y': mbpov_y, 'mbpov/total': mbpov_total, 'fl': train_fl,
+            'num_occupied_voxels': num_occupied_voxels, 'y': y, 'y_tilde': y_tilde, 'x': x, 'x_tilde': x_tilde,
+            'x_tilde_quant': x_tilde_quant, 'y_likelihoods': y_likelihoods, 'log_y_likelihoods': log_y_likelihoods}
+
+
+def v2_summaries(log_z_likelihoods, sigma_tilde, train_mbpov_z, z, z_likelihoods, z_tilde):  # model_types.py:82-88
+    return {'z': z, 'z_tilde': z_tilde, 'mbpov/z': train_mbpov_z, 'sigma_tilde': sigma_tilde,
+            'z_likelihoods': z_likelihoods, 'log_z_likelihoods': log_z_likelihoods}
+
+
 def sparse_to_dense(block, x_shape, data_format='channels_first'):
     """src/model_types.py:108-114 on the GPU: (n,3) integer coords -> fp32 occupancy of shape x_shape."""
     assert data_format == 'channels_first'
@@ -461,8 +562,11 @@ class CompressionModel:
         self.train_loss = lmbda * self.train_fl + self.train_mbpov
         self.num_occupied_voxels = n_occ
         self.x_tilde = x_tilde
+        # tf.summary.merge_all() of the reference's graph (model_types.py:271-274,357-362): scalars here, the bc/* scores
+        # of the quantised reconstruction included; histograms are the tensors kept on the model (y, y_tilde, ...)
         self.merged_summary = {'loss': self.train_loss, 'fl': self.train_fl, 'mbpov/total': self.train_mbpov,
-                               'num_occupied_voxels': n_occ}
+                               'num_occupied_voxels': n_occ,
+                               **binary_classification_summaries(quantize_tensor(x), quantize_tensor(x_tilde))}
         self.step = getattr(self, 'step', 0)
         # sess.run(m.train_op) of the reference == m.train_op(x): forward + backward + both Adam steps + table refresh
         from .training import Trainer

@@ -202,3 +202,34 @@ def test_train_forward_matches_oracle():
         assert abs(float(got) - float(want)) < 1e-4 * abs(float(want)), (float(got), float(want))
     rel = (m.y.cpu() - ref['y']).abs().max() / ref['y'].abs().max()
     assert float(rel) < 3e-5
+
+
+def test_training_host_glue_matches_reference_semantics():
+    """input_fn / pc_to_tf / process_x / quantize_tensor / binary_classification_summaries / add_channels
+    (model_types.py:23-62,91-105,121-125) against their numpy statements."""
+    from pcc_geo_cnn_v2_b200 import model_types as MT
+    rng = np.random.default_rng(3)
+    pts = [np.unique(rng.integers(0, 16, size=(n, 3)), axis=0) for n in (40, 7, 120, 1, 64)]
+    for fmt, shape in (('channels_first', (1, 16, 16, 16)), ('channels_last', (16, 16, 16, 1))):
+        dense = MT.process_x(MT.pc_to_tf(pts[0], shape, fmt), shape)
+        want = np.zeros((16, 16, 16), np.float32)
+        want[pts[0][:, 0], pts[0][:, 1], pts[0][:, 2]] = 1
+        assert dense.shape == shape and np.array_equal(dense.cpu().numpy().reshape(16, 16, 16), want)
+        assert MT.add_channels([4, 5, 6], 64, fmt) == ([64, 4, 5, 6] if fmt == 'channels_first' else [4, 5, 6, 64])
+    np.random.seed(42)
+    got = list(MT.input_fn(pts, 2, (1, 16, 16, 16), 'channels_first', repeat=False, shuffle=True))
+    assert [tuple(b.shape) for b in got] == [(2, 1, 16, 16, 16)] * 2 + [(1, 1, 16, 16, 16)]
+    np.random.seed(42)
+    order = np.random.permutation(len(pts))
+    sums = [float(b.sum()) for b in got]
+    assert sums == [float(len(pts[order[0]]) + len(pts[order[1]])), float(len(pts[order[2]]) + len(pts[order[3]])), float(len(pts[order[4]]))]
+    it = MT.input_fn(pts, 3, (1, 16, 16, 16), 'channels_first', repeat=True, shuffle=False)
+    first_epoch = [next(it) for _ in range(2)]
+    assert float(next(it).sum()) == float(first_epoch[0].sum())   # repeats from the start
+    x = torch.tensor([[-0.2, 0.4, 0.5, 0.51, 1.7]], device='cuda')
+    assert MT.quantize_tensor(x).tolist() == [[0, 0, 0, 1, 1]]
+    xq = torch.tensor([1, 1, 0, 0, 1, 0], device='cuda', dtype=torch.uint8)
+    xt = torch.tensor([1, 0, 0, 1, 1, 0], device='cuda', dtype=torch.uint8)
+    bc = MT.binary_classification_summaries(xq, xt)
+    assert abs(float(bc['bc/precision']) - 2 / 3) < 1e-12 and abs(float(bc['bc/recall']) - 2 / 3) < 1e-12
+    assert abs(float(bc['bc/accuracy']) - 4 / 6) < 1e-12 and abs(float(bc['bc/specificity']) - 2 / 3) < 1e-12
