@@ -503,24 +503,31 @@ class CompressionModel:
         # stage 0 (host): first latent's strings -> symbols; stage 1 (GPU): what the second latent's decoding needs
         # (hyper-synthesis -> scale indexes); stage 2 (host): second latent; stage 3 (GPU): synthesis + threshold + pack;
         # stage 4 (host): packed bits -> points
-        f0 = [pool.submit(self._decode_host0, st, dims) for st in strings]
-        ctxs, f2 = [], []
+        # The driver walks the batches with a lag: stage 1 of batch i is enqueued before it waits for stage 2 of batch
+        # i-lag, and the first-latent decodes are submitted only two batches ahead, so that the host work the GPU is waiting
+        # for (batch 0's second latent) is at the front of the workers' queue instead of behind every batch's stage 0.
         graphs = self.use_graphs and not debug
-        for st, f in zip(strings, f0):
-            ctx = self._graph_dev1(f.result(), len(st), dims) if graphs else self._decode_dev1(f.result(), dims)
-            ctxs.append(ctx)
-            f2.append(pool.submit(self._decode_host1, ctx, st))
-        f4, dbgs = [], []
-        for chunk, ctx, f in zip(chunks, ctxs, f2):
-            f.result()
-            idx = np.asarray([int(c[1]) for c in chunk], np.int64)
-            if graphs:
-                dbg = {'bits': self._graph_dev2(ctx, len(chunk), dims, threshold_f32(self.thresholds, idx))}
-            else:
-                x_hat, dbg = self._decode_dev2(ctx, self._h2d(threshold_f32(self.thresholds, idx)), debug)
-            pend = self._d2h(dbg['bits'])
-            f4.append(pool.submit(self._points_task, pend, dims))
-            dbgs.append([dbg if debug else None] * len(chunk))
+        nb, lag, ahead = len(chunks), 2, 2
+        f0 = {i: pool.submit(self._decode_host0, strings[i], dims) for i in range(min(ahead, nb))}
+        ctxs, f2, f4, dbgs = {}, {}, [], []
+        for i in range(nb + lag):
+            if i < nb:
+                ctxs[i] = self._graph_dev1(f0.pop(i).result(), len(strings[i]), dims) if graphs else self._decode_dev1(f0.pop(i).result(), dims)
+                f2[i] = pool.submit(self._decode_host1, ctxs[i], strings[i])
+                if i + ahead < nb:
+                    f0[i + ahead] = pool.submit(self._decode_host0, strings[i + ahead], dims)
+            j = i - lag
+            if j >= 0:
+                f2.pop(j).result()
+                chunk, ctx = chunks[j], ctxs.pop(j)
+                idx = np.asarray([int(c[1]) for c in chunk], np.int64)
+                if graphs:
+                    dbg = {'bits': self._graph_dev2(ctx, len(chunk), dims, threshold_f32(self.thresholds, idx))}
+                else:
+                    x_hat, dbg = self._decode_dev2(ctx, self._h2d(threshold_f32(self.thresholds, idx)), debug)
+                pend = self._d2h(dbg['bits'])
+                f4.append(pool.submit(self._points_task, pend, dims))
+                dbgs.append([dbg if debug else None] * len(chunk))
         pts = [f.result() for f in f4]
         return [p for r in pts for p in r], [d for r in dbgs for d in r]
 
@@ -610,13 +617,17 @@ class CompressionModelV1(CompressionModel):
         return {'y_sym': y_sym, 'y_hat': y_hat}
 
     def _static_latents(self, n, dims):
-        return {'sym0': torch.zeros((n, self.num_filters) + tuple(d // 8 for d in dims), device='cuda', dtype=torch.int32)}
+        return {'sym1': torch.zeros((n, self.num_filters) + tuple(d // 8 for d in dims), device='cuda', dtype=torch.int32)}
 
-    def _dec1_compute(self, sym0):
-        return {'y_hat': ops.eb_dequantize(sym0, self.entropy_bottleneck.device_params())}
+    # one latent: nothing on the GPU between the two host stages, so the decode graph is a single stage (dequantise +
+    # synthesis + threshold + pack) fed from the static symbol buffer right before its replay -- a 'dec1' graph would
+    # leave its output in a static tensor that the next batch's replay overwrites before this batch's synthesis runs
+    def _graph_dev1(self, sym0_host, n, dims):
+        return {'ysym': sym0_host}
 
     def _dec2_compute(self, ctx, st):
-        return self._synthesize(ctx['y_hat'], st['thr'], False)[1]  # ctx['y_hat']: static output of the 'dec1' graph
+        y_hat = ops.eb_dequantize(st['sym1'], self.entropy_bottleneck.device_params())
+        return self._synthesize(y_hat, st['thr'], False)[1]
 
     def _encode_device(self, x, after_latents=None, thresholds=None, want_x_hat=True):
         dev = self._latents(x)

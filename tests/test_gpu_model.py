@@ -22,9 +22,9 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-def _model(config, seed):
+def _model(config, seed, **kw):
     m = ModelConfigType[config].build()
-    m.set_weights(synthetic.trained_like_weights(m, seed=seed))
+    m.set_weights(synthetic.trained_like_weights(m, seed=seed, **kw))
     return m
 
 
@@ -158,11 +158,13 @@ def test_encode_decode_self_consistency(config, size):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize('config,size', [('c3p', 64), ('c1', 64)])
-def test_graph_pipeline_equals_eager_pipeline(config, size):
+@pytest.mark.parametrize('config,size,bias', [('c3p', 64, -0.7), ('c1', 64, 0.4), ('c2', 64, 0.47)])
+def test_graph_pipeline_equals_eager_pipeline(config, size, bias):
     """The CUDA-graph stage replays of the block loops produce the same bytes and points as the eager launches, over
-    several ragged batches in flight, and survive a parameter change (graphs are re-captured)."""
-    m = _model(config, 7)
+    several ragged batches in flight (static buffers are shared between batches: a stage must never read a tensor that a
+    later batch's replay has already overwritten), and survive a parameter change (graphs are re-captured).  The output
+    bias is chosen per config so that the decoded point sets are non-empty and differ from block to block."""
+    m = _model(config, 7, output_bias=bias)
     m.batch_size = 3
     blocks = synthetic.surface_blocks(8, size=size, seed=21)
     m.compress((1, 1, size, size, size))
@@ -173,6 +175,7 @@ def test_graph_pipeline_equals_eager_pipeline(config, size):
         dec, _ = m.decompress_blocks(None, dl[0], (size, size, size))
         cur = ([s for s, _ in dl[0]], [p.tobytes() for p in meta[0]['x_hat_list']], [p.tobytes() for p in dec])
         assert out.setdefault('ref', cur) == cur
+        assert min(len(p) for p in dec) > 0 and len({len(p) for p in dec}) > 4, [len(p) for p in dec]
     assert m._graphs, 'the graph path did not run'
     # new parameters -> stale graphs must not be replayed
     m.use_graphs = True
