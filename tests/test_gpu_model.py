@@ -140,11 +140,11 @@ def test_golden_fixture(fixture, precision):
         assert pts.tolist() == sorted(pts.tolist())      # argwhere (C) order
 
 
-@pytest.mark.parametrize('config,size', [('c3p', 64), ('c1', 64), ('c2', 32), ('c3', 64)])
-def test_encode_decode_self_consistency(config, size):
+@pytest.mark.parametrize('config,size,bias', [('c3p', 64, -0.7), ('c1', 64, 0.4), ('c2', 32, 0.47), ('c3', 64, -0.7)])
+def test_encode_decode_self_consistency(config, size, bias):
     """decompress_octree.py --debug contract (decompress_octree.py:94-119): the decoder's point set equals the
     encoder's exactly, block by block, here over a ragged batch (incl. a 1-point block)."""
-    m = _model(config, 7)
+    m = _model(config, 7, output_bias=bias)   # per-config output bias: the decoded point sets must not be empty
     m.batch_size = 4
     blocks = synthetic.surface_blocks(6, size=size, seed=9) + [np.array([[0, 0, 0]], np.float32)]
     m.compress((1, 1, size, size, size))
@@ -156,6 +156,7 @@ def test_encode_decode_self_consistency(config, size):
     enc_pts = metadata[0]['x_hat_list']
     for a, b in zip(enc_pts, dec):
         assert np.array_equal(a, b)
+    assert sum(len(p) for p in dec) > 100, [len(p) for p in dec]
 
 
 @pytest.mark.parametrize('config,size,bias', [('c3p', 64, -0.7), ('c1', 64, 0.4), ('c2', 64, 0.47)])
