@@ -81,21 +81,24 @@ __global__ void eb_dequantize_kernel(const int32_t* __restrict__ sym, const floa
 }
 
 __global__ void eb_likelihood_kernel(const float* __restrict__ v, const float* __restrict__ params,
-                                     float* __restrict__ lik, double* __restrict__ partials, int C, int S) {
+                                     float* __restrict__ lik, double* __restrict__ partials, int N, int C, int S) {
   __shared__ double sm[32];
-  const int c = blockIdx.y, n = blockIdx.z;
+  const int c = blockIdx.y;
   const EbP p = load_eb(params + c * PCCGEO_EB_PARAM_STRIDE);
-  const long long base = ((long long)n * C + c) * S;
   double acc = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
-    const float val = v[base + i];
-    const float lo = eb_logits(p, val - 0.5f), up = eb_logits(p, val + 0.5f);
-    const float t = lo + up;
-    const float s = t > 0.f ? -1.f : (t < 0.f ? 1.f : 0.f);  // -sign(lower + upper)
-    float l = fabsf(sigmoidf_(s * up) - sigmoidf_(s * lo));
-    l = fmaxf(l, 1e-9f);
-    if (lik) lik[base + i] = l;
-    acc += (double)logf(l);
+  // grid.z may be smaller than the batch (the partial-sum workspace is fixed): a block then walks several samples, in order
+  for (int n = blockIdx.z; n < N; n += gridDim.z) {
+    const long long base = ((long long)n * C + c) * S;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+      const float val = v[base + i];
+      const float lo = eb_logits(p, val - 0.5f), up = eb_logits(p, val + 0.5f);
+      const float t = lo + up;
+      const float s = t > 0.f ? -1.f : (t < 0.f ? 1.f : 0.f);  // -sign(lower + upper)
+      float l = fabsf(sigmoidf_(s * up) - sigmoidf_(s * lo));
+      l = fmaxf(l, 1e-9f);
+      if (lik) lik[base + i] = l;
+      acc += (double)logf(l);
+    }
   }
   if (partials) {
     acc = block_sum(acc, sm);
@@ -190,15 +193,16 @@ extern "C" int pccgeo_eb_likelihood(const float* values, const float* eb_params,
   PCCGEO_REQUIRE(values && eb_params && n > 0 && c > 0 && spatial > 0, "eb_likelihood: bad argument");
   PCCGEO_REQUIRE(n <= 65535 && c <= 65535, "eb_likelihood: n or c too large");
   PCCGEO_REQUIRE(!sum_log || partials, "eb_likelihood: sum_log needs a partials workspace");
-  int gx = grid_for(spatial, 128, 16);
-  while ((long long)gx * c * n > kReduceBlocks && gx > 1) --gx;
-  PCCGEO_REQUIRE(!sum_log || (long long)gx * c * n <= kReduceBlocks, "eb_likelihood: n*c=%d exceeds the reduction workspace", n * c);
-  dim3 grid(gx, c, n);
+  PCCGEO_REQUIRE(c <= kReduceBlocks, "eb_likelihood: %d channels exceed the reduction workspace", c);
+  int gx = grid_for(spatial, 128, 16), gz = n;
+  while ((long long)gx * c * gz > kReduceBlocks && gx > 1) --gx;
+  while ((long long)gx * c * gz > kReduceBlocks && gz > 1) --gz;   // fewer z-blocks than samples: blocks loop over the batch
+  dim3 grid(gx, c, gz);
   cudaStream_t st = (cudaStream_t)stream;
-  eb_likelihood_kernel<<<grid, 128, 0, st>>>(values, eb_params, likelihood, sum_log ? partials : nullptr, c, spatial);
+  eb_likelihood_kernel<<<grid, 128, 0, st>>>(values, eb_params, likelihood, sum_log ? partials : nullptr, n, c, spatial);
   int rc = check_launch("eb_likelihood_kernel");
   if (rc || !sum_log) return rc;
-  finish_sum_kernel<<<1, 256, 0, st>>>(partials, gx * c * n, sum_log);
+  finish_sum_kernel<<<1, 256, 0, st>>>(partials, gx * c * gz, sum_log);
   return check_launch("finish_sum_kernel");
 }
 

@@ -265,6 +265,104 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradParams p) 
   }
 }
 
+// Register-tiled variant (channel counts are padded up to multiples of 4 with zero rows): a thread owns a
+// 4 x 4 (ci, co) tile of one voxel slice, so each staged value feeds 4 FMAs from registers (the kernel above reads two
+// shared-memory operands per FMA); voxel-major staging [v][(Cin+Cout)/4 + 1] float4 keeps the float4 reads of a warp on
+// few distinct addresses (broadcast) and the staging stores 4-way at worst.  Same reduction contract: fp32 inside a chunk
+// slice, double running sums, slices and splits added in a fixed order (deterministic).
+constexpr int WT_VC = 128;   // voxels per staged chunk
+
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tiled_kernel(const WgradParams p) {
+  extern __shared__ float4 smem4[];
+  const int C4i = (p.Cin + 3) / 4, C4o = (p.Cout + 3) / 4, C4 = C4i + C4o, ROW = C4 + 1;
+  const int TP = C4i * C4o, VS = WG_THREADS / TP;          // tiles, voxel slices (TP divides 256)
+  const int t = blockIdx.x, split = blockIdx.y;
+  const int kz = t / (p.K * p.K), ky = (t / p.K) % p.K, kx = t % p.K;
+  const int oxz = p.transposed ? 0 : kz - p.pb, oxy = p.transposed ? 0 : ky - p.pb, oxx = p.transposed ? 0 : kx - p.pb;
+  const int ogz = p.transposed ? kz - p.pb : 0, ogy = p.transposed ? ky - p.pb : 0, ogx = p.transposed ? kx - p.pb : 0;
+  const long long nb = (long long)p.Bd * p.Bh * p.Bw, total = nb * p.N;
+  const long long per = (total + p.splits - 1) / p.splits;
+  const long long lo = per * split, hi = lo + per < total ? lo + per : total;
+  const long long XHW = (long long)p.Xh * p.Xw, XDHW = XHW * p.Xd, GHW = (long long)p.Gh * p.Gw, GDHW = GHW * p.Gd;
+  const int tp = threadIdx.x % TP, vs = threadIdx.x / TP;
+  const int cit = tp / C4o, cot = tp % C4o;
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (long long base = lo; base < hi; base += WT_VC) {
+    __syncthreads();
+    {
+      const int vv = threadIdx.x & (WT_VC - 1);
+      const long long L = base + vv;
+      long long xoff = -1, goff = -1;
+      if (L < hi) {
+        const int n = (int)(L / nb);
+        const long long r = L % nb;
+        const int bz = (int)(r / ((long long)p.Bh * p.Bw)), by = (int)((r / p.Bw) % p.Bh), bx = (int)(r % p.Bw);
+        int z = bz * p.sx + oxz, y = by * p.sx + oxy, x = bx * p.sx + oxx;
+        if (z >= 0 && z < p.Xd && y >= 0 && y < p.Xh && x >= 0 && x < p.Xw)
+          xoff = (long long)n * p.Cin * XDHW + z * XHW + (long long)y * p.Xw + x;
+        z = bz * p.sy + ogz; y = by * p.sy + ogy; x = bx * p.sy + ogx;
+        if (z >= 0 && z < p.Gd && y >= 0 && y < p.Gh && x >= 0 && x < p.Gw)
+          goff = (long long)n * p.Cout * GDHW + z * GHW + (long long)y * p.Gw + x;
+      }
+      for (int c4 = threadIdx.x / WT_VC; c4 < C4; c4 += WG_THREADS / WT_VC) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < C4i) {
+          if (xoff >= 0) {
+            const int c0 = 4 * c4;
+            const float* q = p.x + xoff + (long long)c0 * XDHW;
+            v.x = __ldg(q);
+            if (c0 + 1 < p.Cin) v.y = __ldg(q + XDHW);
+            if (c0 + 2 < p.Cin) v.z = __ldg(q + 2 * XDHW);
+            if (c0 + 3 < p.Cin) v.w = __ldg(q + 3 * XDHW);
+          }
+        } else if (goff >= 0) {
+          const int c0 = 4 * (c4 - C4i);
+          const float* q = p.g + goff + (long long)c0 * GDHW;
+          v.x = __ldg(q);
+          if (c0 + 1 < p.Cout) v.y = __ldg(q + GDHW);
+          if (c0 + 2 < p.Cout) v.z = __ldg(q + 2 * GDHW);
+          if (c0 + 3 < p.Cout) v.w = __ldg(q + 3 * GDHW);
+        }
+        smem4[vv * ROW + c4] = v;
+      }
+    }
+    __syncthreads();
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 0.f;
+    for (int v = vs; v < WT_VC; v += VS) {
+      const float4 xv = smem4[v * ROW + cit], gv = smem4[v * ROW + C4i + cot];
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i * 4 + j] = fmaf(xa[i], ga[j], a[i * 4 + j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] += (double)a[i];
+  }
+  // add the voxel slices in order: slice sums go through shared memory as doubles
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(smem4);
+  const int pairs = p.Cin * p.Cout;
+  for (int s0 = 0; s0 < VS; ++s0) {
+    if (vs == s0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (cit * 4 + i >= p.Cin || cot * 4 + j >= p.Cout) continue;   // padding rows of the tile
+          const int pr = (cit * 4 + i) * p.Cout + cot * 4 + j;
+          red[pr] = (s0 == 0 ? 0.0 : red[pr]) + acc[i * 4 + j];
+        }
+    }
+    __syncthreads();
+  }
+  for (int pr = threadIdx.x; pr < pairs; pr += WG_THREADS) p.partial[((long long)t * p.splits + split) * pairs + pr] = (float)red[pr];
+}
+
 __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int splits, int pairs, float* __restrict__ dw, long long total) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long t = i / pairs, pr = i % pairs;
@@ -391,9 +489,24 @@ extern "C" int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw
   const int taps = k * k * k;
   p.splits = (592 + taps - 1) / taps;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)(cin + cout) * WG_VC * sizeof(float);
-  wgrad_kernel<<<dim3(taps, p.splits), WG_THREADS, smem, st>>>(p);
-  int rc = check_launch("wgrad_kernel");
+  int rc;
+  const int tp = ((cin + 3) / 4) * ((cout + 3) / 4);
+  if (tp <= WG_THREADS && WG_THREADS % tp == 0) {
+    size_t smem = (size_t)WT_VC * ((cin + 3) / 4 + (cout + 3) / 4 + 1) * sizeof(float4);
+    const size_t red = (size_t)cin * cout * sizeof(double);
+    if (red > smem) smem = red;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+      PCCGEO_CUDA(cudaFuncSetAttribute(wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = smem;
+    }
+    wgrad_tiled_kernel<<<dim3(taps, p.splits), WG_THREADS, smem, st>>>(p);
+    rc = check_launch("wgrad_tiled_kernel");
+  } else {
+    const size_t smem = (size_t)(cin + cout) * WG_VC * sizeof(float);
+    wgrad_kernel<<<dim3(taps, p.splits), WG_THREADS, smem, st>>>(p);
+    rc = check_launch("wgrad_kernel");
+  }
   if (rc) return rc;
   const long long total = (long long)taps * cin * cout;
   wgrad_finish_kernel<<<grid1d(total, 256, 148 * 8), 256, 0, st>>>(ws, p.splits, cin * cout, dw, total);

@@ -42,6 +42,17 @@ def test_eb_quantize_bit_exact_and_likelihood():
         assert abs(float(s[0]) - float(torch.log(ol).sum())) < 1e-5 * abs(float(torch.log(ol).sum()))
 
 
+def test_eb_likelihood_sum_at_training_batch_size():
+    """tr_train.py's batch 32 x 64 channels (model_types.py:333-353) exceeds one partial-sum slot per (sample, channel): the
+    kernel then walks several samples per block.  Sum of ln p against the oracle in float64."""
+    eb, w = _eb(64, 3)
+    x = torch.randn(40, 64, 4, 4, 4) * 4
+    s = eb.log_likelihood_sum(x.cuda())
+    _, ol = E.eb_forward(w, x, True, torch.zeros_like(x), torch.float64)
+    want = float(torch.log(ol).sum())
+    assert abs(float(s[0]) - want) < 1e-5 * abs(want), (float(s[0]), want)
+
+
 def test_gc_quantize_bit_exact_and_likelihood():
     st = EM.make_scale_table()
     rng = np.random.default_rng(1)
