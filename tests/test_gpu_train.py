@@ -58,17 +58,18 @@ def _rel(got, want):
     return float(np.abs(np.asarray(got, np.float64) - want).max() / (np.abs(want).max() + 1e-30))
 
 
-@pytest.mark.parametrize('config,size,lmbda', [('c3p', 32, 3e-3), ('c1', 32, 1e-3)])
-def test_gradients_match_oracle_autograd(config, size, lmbda):
+@pytest.mark.parametrize('config,size,lmbda,batch', [('c3p', 32, 3e-3, 2), ('c1', 32, 1e-3, 2), ('c3p', 16, 3e-3, 32)])
+def test_gradients_match_oracle_autograd(config, size, lmbda, batch):
+    """The third case runs the reference's training batch size (tr_train.py --batch_size 32): 32 x 64 latent channels."""
     m = ModelConfigType[config].build()
     w = synthetic.trained_like_weights(m, seed=11, output_bias=-0.3)
     m.set_weights(w)
-    blocks = synthetic.surface_blocks(2, size=size, seed=5)
+    blocks = synthetic.surface_blocks(batch, size=size, seed=5)
     x = np.concatenate([sparse_to_dense(b, (1, 1, size, size, size)) for b in blocks])
     g = torch.Generator().manual_seed(1)
     f = m.num_filters
-    ny = torch.rand((2, f) + (size // 8,) * 3, generator=g) - 0.5
-    nz = torch.rand((2, f) + (size // 16,) * 3, generator=g) - 0.5
+    ny = torch.rand((batch, f) + (size // 8,) * 3, generator=g) - 0.5
+    nz = torch.rand((batch, f) + (size // 16,) * 3, generator=g) - 0.5
     ref, leaves, eb = _oracle_loss_and_grads(config, w, x, ny, nz, 2, 0.75, lmbda)
 
     tr = Trainer(m, gamma=2, alpha=0.75, lmbda=lmbda)
