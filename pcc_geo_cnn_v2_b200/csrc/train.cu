@@ -270,8 +270,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradParams p) 
 // shared-memory operands per FMA); voxel-major staging [v][(Cin+Cout)/4 + 1] float4 keeps the float4 reads of a warp on
 // few distinct addresses (broadcast) and the staging stores 4-way at worst.  Same reduction contract: fp32 inside a chunk
 // slice, double running sums, slices and splits added in a fixed order (deterministic).
-constexpr int WT_VC = 128;   // voxels per staged chunk
-
+template <int WT_VC>   // voxels per staged chunk (256 for narrow layers: fewer barriers / index decodes per FMA)
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tiled_kernel(const WgradParams p) {
   extern __shared__ float4 smem4[];
   const int C4i = (p.Cin + 3) / 4, C4o = (p.Cout + 3) / 4, C4 = C4i + C4o, ROW = C4 + 1;
@@ -296,9 +295,13 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tiled_kernel(const WgradPara
       const long long L = base + vv;
       long long xoff = -1, goff = -1;
       if (L < hi) {
-        const int n = (int)(L / nb);
-        const long long r = L % nb;
-        const int bz = (int)(r / ((long long)p.Bh * p.Bw)), by = (int)((r / p.Bw) % p.Bh), bx = (int)(r % p.Bw);
+        // total < 2^31 (host-checked): 32-bit index decode
+        const uint32_t Lu = (uint32_t)L, nbu = (uint32_t)nb, hw = (uint32_t)(p.Bh * p.Bw);
+        const int n = (int)(Lu / nbu);
+        const uint32_t r = Lu - (uint32_t)n * nbu;
+        const int bz = (int)(r / hw);
+        const uint32_t r2 = r - (uint32_t)bz * hw;
+        const int by = (int)(r2 / (uint32_t)p.Bw), bx = (int)(r2 - (uint32_t)by * (uint32_t)p.Bw);
         int z = bz * p.sx + oxz, y = by * p.sx + oxy, x = bx * p.sx + oxx;
         if (z >= 0 && z < p.Xd && y >= 0 && y < p.Xh && x >= 0 && x < p.Xw)
           xoff = (long long)n * p.Cin * XDHW + z * XHW + (long long)y * p.Xw + x;
@@ -492,15 +495,21 @@ extern "C" int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw
   int rc;
   const int tp = ((cin + 3) / 4) * ((cout + 3) / 4);
   if (tp <= WG_THREADS && WG_THREADS % tp == 0) {
-    size_t smem = (size_t)WT_VC * ((cin + 3) / 4 + (cout + 3) / 4 + 1) * sizeof(float4);
+    const int c4 = (cin + 3) / 4 + (cout + 3) / 4;
+    const bool wide = c4 > 16;   // 32- and 64-channel layers: 128-voxel chunks; narrower ones: 256
+    const int vc = wide ? 128 : 256;
+    PCCGEO_REQUIRE((long long)p.N * p.Bd * p.Bh * p.Bw < (1LL << 31), "conv3d_wgrad: too many positions for the 32-bit index decode");
+    size_t smem = (size_t)vc * (c4 + 1) * sizeof(float4);
     const size_t red = (size_t)cin * cout * sizeof(double);
     if (red > smem) smem = red;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-      PCCGEO_CUDA(cudaFuncSetAttribute(wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = smem;
+    static bool attr = false;
+    if (!attr) {
+      PCCGEO_CUDA(cudaFuncSetAttribute(wgrad_tiled_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      PCCGEO_CUDA(cudaFuncSetAttribute(wgrad_tiled_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
     }
-    wgrad_tiled_kernel<<<dim3(taps, p.splits), WG_THREADS, smem, st>>>(p);
+    if (wide) wgrad_tiled_kernel<128><<<dim3(taps, p.splits), WG_THREADS, smem, st>>>(p);
+    else wgrad_tiled_kernel<256><<<dim3(taps, p.splits), WG_THREADS, smem, st>>>(p);
     rc = check_launch("wgrad_tiled_kernel");
   } else {
     const size_t smem = (size_t)(cin + cout) * WG_VC * sizeof(float);
