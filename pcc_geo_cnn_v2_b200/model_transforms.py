@@ -444,12 +444,16 @@ class _Val:
         return self.blk
 
 
-def run_steps(steps, out_id, x, pack=None):
+def run_steps(steps, out_id, x, pack=None, keep=None, extra=None):
     """Execute traced steps on a channels_first fp32 CUDA tensor.  pack = {'thresholds', 'want_f32'}: also return the
-    packed thresholded occupancy of the (single-channel) output -> (y or None, bits, counts)."""
+    packed thresholded occupancy of the (single-channel) output -> (y or None, bits, counts).  keep: dict that receives every
+    value (id -> fp32 tensor; the training path saves activations this way); extra: {id: fp32 tensor} of additional inputs
+    (e.g. a residual operand)."""
     mode = _precision['mode']
     terms = {'bf16x3': 2, 'bf16': 1, 'fp32': 0}[mode]
     vals = {0: _Val(f32=x, shape=tuple(x.shape))}
+    for vid, t in (extra or {}).items():
+        vals[vid] = _Val(f32=t, shape=tuple(t.shape))
     last_use = {}
     for i, s in enumerate(steps):
         for vid in ((s[2], s[4]) if s[0] == 'conv' else (s[1], s[2])):
@@ -490,11 +494,14 @@ def run_steps(steps, out_id, x, pack=None):
                                    layer.transposed, layer.relu, rf)
                 vals[dst] = _Val(f32=y, shape=tuple(y.shape))
         elif s[0] == 'add':
-            y = vals[s[1]].as_f32() + vals[s[2]].as_f32()  # only reachable for non-conv tails; never in the reference configs
+            y = ops.axpby(vals[s[1]].as_f32(), vals[s[2]].as_f32(), 1.0, 1.0)  # un-fused residual add (training traces)
             vals[s[3]] = _Val(f32=y, shape=tuple(y.shape))
         else:
             y = torch.cat((vals[s[1]].as_f32(), vals[s[2]].as_f32()), 1)
             vals[s[3]] = _Val(f32=y, shape=tuple(y.shape))
+        if keep is not None:
+            keep[s[3]] = vals[s[3]].as_f32()
+            continue
         for vid in [k for k, li in last_use.items() if li == i and k != out_id]:
             vals.pop(vid, None)
     y = vals[out_id].as_f32()
@@ -502,6 +509,12 @@ def run_steps(steps, out_id, x, pack=None):
         bits, counts = ops.threshold_pack(y, pack['thresholds'])
         return y, bits, counts
     return y
+
+
+def run_layer(layer, x, residual=None):
+    """One conv layer (fp32 in / fp32 out) through the same kernel dispatch as a transform; residual is added in the epilogue."""
+    steps = [('conv', layer, 0, 1, 2 if residual is not None else None)]
+    return run_steps(steps, 1, x, extra={2: residual} if residual is not None else None)
 
 
 def _run_transform(layer, tensor, data_format, pack=None):

@@ -578,7 +578,7 @@ class CompressionModel:
         # sess.run(m.train_op) of the reference == m.train_op(x): forward + backward + both Adam steps + table refresh
         from .training import Trainer
         if getattr(self, 'trainer', None) is None:
-            self.trainer = Trainer(self, gamma, alpha, lmbda)
+            self.trainer = Trainer(self, gamma, alpha, lmbda, tensor_cores=getattr(self, 'train_tensor_cores', False))
         self.train_op = self.trainer.step
         return mb
 

@@ -58,9 +58,12 @@ def _rel(got, want):
     return float(np.abs(np.asarray(got, np.float64) - want).max() / (np.abs(want).max() + 1e-30))
 
 
-@pytest.mark.parametrize('config,size,lmbda,batch', [('c3p', 32, 3e-3, 2), ('c1', 32, 1e-3, 2), ('c3p', 16, 3e-3, 32)])
-def test_gradients_match_oracle_autograd(config, size, lmbda, batch):
-    """The third case runs the reference's training batch size (tr_train.py --batch_size 32): 32 x 64 latent channels."""
+@pytest.mark.parametrize('config,size,lmbda,batch,tc', [('c3p', 32, 3e-3, 2, False), ('c1', 32, 1e-3, 2, False),
+                                                         ('c3p', 16, 3e-3, 32, False), ('c3p', 32, 3e-3, 2, True)])
+def test_gradients_match_oracle_autograd(config, size, lmbda, batch, tc):
+    """The third case runs the reference's training batch size (tr_train.py --batch_size 32): 32 x 64 latent channels; the
+    fourth the tensor-core (bf16x3) forward / data-gradient convs, whose 1e-5 forward differences the focal loss amplifies
+    to ~1e-2 in the gradients."""
     m = ModelConfigType[config].build()
     w = synthetic.trained_like_weights(m, seed=11, output_bias=-0.3)
     m.set_weights(w)
@@ -72,7 +75,7 @@ def test_gradients_match_oracle_autograd(config, size, lmbda, batch):
     nz = torch.rand((batch, f) + (size // 16,) * 3, generator=g) - 0.5
     ref, leaves, eb = _oracle_loss_and_grads(config, w, x, ny, nz, 2, 0.75, lmbda)
 
-    tr = Trainer(m, gamma=2, alpha=0.75, lmbda=lmbda)
+    tr = Trainer(m, gamma=2, alpha=0.75, lmbda=lmbda, tensor_cores=tc)
     vals, grads = tr.forward_backward(torch.from_numpy(x).cuda(), ny.cuda(), nz.cuda())
     for k in ('loss', 'fl', 'mbpov'):
         assert abs(vals[k] - ref[k]) < 1e-4 * abs(ref[k]), (k, vals[k], ref[k])
@@ -87,13 +90,13 @@ def test_gradients_match_oracle_autograd(config, size, lmbda, batch):
             worst = max(worst, r, rb)
             report.append(f'{name}[{li}] k{layer.k} s{layer.stride} {layer.in_channels}->{layer.filters}: w {r:.2e} b {rb:.2e}')
     print('\n'.join(report))
-    assert worst < 2e-3, report
+    assert worst < (2e-2 if tc else 2e-3), report
     ge = grads['entropy_bottleneck']
     want = [t.grad.numpy() for t in eb['matrices'] + eb['biases'] + eb['factors']]
     assert len(ge) == len(want) == 11
     for i, (a, b) in enumerate(zip(ge, want)):
         assert a.shape == b.shape
-        assert _rel(a, b) < 1e-3, ('entropy bottleneck variable', i, _rel(a, b))
+        assert _rel(a, b) < (1e-2 if tc else 1e-3), ('entropy bottleneck variable', i, _rel(a, b))
     print('worst conv-kernel gradient error', worst)
 
 

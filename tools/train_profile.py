@@ -16,6 +16,7 @@ from pcc_geo_cnn_v2_b200.model_types import blocks_to_coords  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 m = P.ModelConfigType['c3p'].build(batch_size=B)
 m.set_weights(synthetic.trained_like_weights(m, seed=42))
+m.train_tensor_cores = len(sys.argv) > 2 and sys.argv[2] == 'tc'
 blocks = synthetic.surface_blocks(min(B, 8), size=64, seed=5)
 blocks = [blocks[i % len(blocks)] for i in range(B)]
 x = ops.densify(torch.from_numpy(blocks_to_coords(blocks)).cuda(), B, 64, 64, 64)
