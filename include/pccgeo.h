@@ -217,6 +217,19 @@ int pccgeo_bits_to_points_host(const uint32_t* bits, int n_blocks, int d, int h,
  * input of pccgeo_densify.  Values are truncated like numpy's float -> int16 cast. */
 int pccgeo_blocks_to_coords_host(const void* const* blocks, const long long* counts, const long long* row_bytes,
                                  int n_blocks, int is_f64, int16_t* out, int threads);
+
+/* ---- per-block threshold optimisation ("next" #1) -----------------------------------------------
+ * Replaces the kd-tree loop of src/model_opt.py:9-44 (one compute_metrics, src/utils/pc_metric.py:76-108, per threshold and
+ * block): exact integer D1 sums between a block's points A and B_i = { x_hat > thresholds[i] } for every threshold at once.
+ * Stage 1 fills the workspace (rank volume + per-slice EDT of A) and the (N, T+1) histograms over rank of EDT2_A and of the
+ * voxel counts (exclusive suffix sums over rank give sum_BA[i] and |B_i|); stage 2 computes sum_AB[n][i] (-1: B_i empty,
+ * -2: B_i == B_{i-1}).  x_hat fp32 (N,1,D,H,W), H,W <= 128; points int16 (P,4) rows (block,z,y,x) sorted by block;
+ * offsets int64 (N+1); all device pointers. */
+size_t pccgeo_threshold_opt_ws_bytes(int n, int d, int h, int wd);
+int pccgeo_threshold_hist(const float* x_hat, const float* thresholds, int t, const int16_t* points, const long long* offsets,
+                          void* ws, unsigned long long* hist, unsigned long long* cnt, int n, int d, int h, int wd, void* stream);
+int pccgeo_threshold_sum_ab(const void* ws, const int16_t* points, const long long* offsets, const long long* counts_b,
+                            long long* sum_ab, int n, int t, int d, int h, int wd, int max_points, void* stream);
 /* tfc pmf_to_quantized_cdf (precision 16): pmf (len) doubles -> cdf (len+1) int32, HOST */
 int pccgeo_pmf_to_quantized_cdf_host(const double* pmf, int len, int precision, int32_t* cdf);
 

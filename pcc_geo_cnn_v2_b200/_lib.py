@@ -53,6 +53,9 @@ SIGNATURES = {
     'pccgeo_range_encode_host': (i32, [vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, vp, i64, vp, i32]),
     'pccgeo_range_decode_host': (i32, [vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, vp, i32]),
     'pccgeo_pmf_to_quantized_cdf_host': (i32, [vp, i32, i32, vp]),
+    'pccgeo_threshold_opt_ws_bytes': (C.c_size_t, [i32, i32, i32, i32]),
+    'pccgeo_threshold_hist': (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    'pccgeo_threshold_sum_ab': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_blocks_to_coords_host': (i32, [vp, vp, vp, i32, i32, vp, i32]),
     'pccgeo_bits_to_points_host': (i32, [vp, i32, i32, i32, i32, vp, vp, i64, i32]),
 }

@@ -469,13 +469,27 @@ class CompressionModel:
         return data_list, metadata, debug_t_list
 
     def _optimal_thresholds(self, blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas):
-        """Per-block threshold search (reference src/model_opt.py:21-77) is host-side kd-tree work outside the hot
-        path ("next" #1): reuse the reference's own module when it is importable."""
+        """Per-block threshold search (reference src/model_opt.py:21-77).  D1 metrics: every threshold's nearest-neighbour
+        sums come from the GPU (csrc/threshold_opt.cu, exact integer distance transforms) and the reference's selection
+        rules are applied to them.  D2 metrics (normals) fall back to the reference's own kd-tree module when it is
+        importable."""
+        from . import model_opt as MO
+        if not any(str(m).startswith('d2') for m in opt_metrics):
+            t32 = threshold_f32(self.thresholds, np.arange(len(self.thresholds)))
+            idx, ret = [], None
+            for a in range(0, len(blocks), self.batch_size):
+                chunk = blocks[a:a + self.batch_size]
+                coords = blocks_to_coords(chunk, self.coder_threads)
+                offsets = np.concatenate([[0], np.cumsum([len(b) for b in chunk])]).astype(np.int64)
+                ret, best = MO.compute_optimal_thresholds_batch(chunk, x_hat[a:a + len(chunk)], t32, self._h2d(coords), offsets,
+                                                                opt_metrics=opt_metrics, max_deltas=max_deltas)
+                idx.append(best)
+            return np.concatenate(idx), list(ret)
         try:
             from model_opt import compute_optimal_thresholds  # the reference's src/ on sys.path
         except ImportError as e:
-            raise NotImplementedError('adaptive thresholds need the reference host module model_opt.py on sys.path '
-                                      '(out of the hot path); pass fixed_threshold=True otherwise') from e
+            raise NotImplementedError('the D2 (point-to-plane) threshold metrics need the reference host module model_opt.py '
+                                      'on sys.path; the D1 metrics run on the GPU') from e
         xh = torch.clamp(x_hat[:, 0], 0.0, 1.0).cpu().numpy()
         idx, ret = [], None
         for j, block in enumerate(blocks):
