@@ -35,35 +35,46 @@ __global__ void rank_kernel(const float* __restrict__ xhat, const float* __restr
   }
 }
 
-// One z-slice of a binary volume -> its 2-D squared EDT g[y][x] (TO_INF where the slice is empty) in shared memory.
-// occ: H*W bytes; f1, g: H*W int32.  Called by all threads of the CTA.
-__device__ __forceinline__ void slice_edt(const uint8_t* occ, int* f1, int* g, int H, int W) {
+// One z-slice of a binary volume -> its 2-D squared EDT g[y][x] in shared memory; returns false (g untouched) when the
+// slice is empty.  occ: H*W bytes; f1, g: H*W int32; rows: H+1 ints (list of the non-empty rows; the y pass only visits
+// those -- decoded sets are surfaces, most rows of a slice are empty).  Called by all threads of the CTA.
+__device__ __forceinline__ bool slice_edt(const uint8_t* occ, int* f1, int* g, int* rows, int H, int W) {
+  if (threadIdx.x == 0) rows[H] = 0;
+  __syncthreads();
   // x direction: two running-distance sweeps per row
   for (int y = threadIdx.x; y < H; y += blockDim.x) {
     int d = TO_INF;
+    bool any = false;
     for (int x = 0; x < W; ++x) {
-      d = occ[y * W + x] ? 0 : (d >= TO_INF ? TO_INF : d + 1);
+      const bool o = occ[y * W + x] != 0;
+      any |= o;
+      d = o ? 0 : (d >= TO_INF ? TO_INF : d + 1);
       f1[y * W + x] = d;
     }
+    if (!any) continue;
+    rows[atomicAdd(&rows[H], 1)] = y;   // order is irrelevant: the y pass takes a minimum
     d = TO_INF;
     for (int x = W - 1; x >= 0; --x) {
       d = occ[y * W + x] ? 0 : (d >= TO_INF ? TO_INF : d + 1);
       const int m = min(f1[y * W + x], d);
-      f1[y * W + x] = m >= TO_INF ? TO_INF : m * m;
+      f1[y * W + x] = m * m;
     }
   }
   __syncthreads();
-  // y direction: min-plus with the parabola (y - y')^2
+  const int nr = rows[H];
+  if (nr == 0) return false;
+  // y direction: min-plus with the parabola (y - y')^2 over the non-empty rows
   for (int e = threadIdx.x; e < H * W; e += blockDim.x) {
     const int y = e / W, x = e - y * W;
     int best = TO_INF;
-    for (int yy = 0; yy < H; ++yy) {
-      const int dy = y - yy;
+    for (int r = 0; r < nr; ++r) {
+      const int yy = rows[r], dy = y - yy;
       best = min(best, f1[yy * W + x] + dy * dy);
     }
     g[e] = best;
   }
   __syncthreads();
+  return true;
 }
 
 // sum_AB for one (threshold, block): grid (T, N).  points: int16 (npts_total, 4) rows (block, z, y, x) sorted by block,
@@ -81,7 +92,8 @@ __global__ void __launch_bounds__(TO_THREADS) sum_ab_kernel(const uint16_t* __re
   }
   int* f1 = reinterpret_cast<int*>(sm);
   int* g = f1 + H * W;
-  int* mp = g + H * W;                       // per-point running minimum (pchunk entries)
+  int* rows = g + H * W;                     // H + 1 ints
+  int* mp = rows + H + 1;                    // per-point running minimum (pchunk entries)
   uint8_t* occ = reinterpret_cast<uint8_t*>(mp + pchunk);
   __shared__ long long red[TO_THREADS / 32];
   const long long p0 = offsets[n], p1 = offsets[n + 1];
@@ -94,7 +106,7 @@ __global__ void __launch_bounds__(TO_THREADS) sum_ab_kernel(const uint16_t* __re
       __syncthreads();
       for (int e = threadIdx.x; e < H * W; e += blockDim.x) occ[e] = rk[(long long)z * H * W + e] > (uint16_t)i;
       __syncthreads();
-      slice_edt(occ, f1, g, H, W);
+      if (!slice_edt(occ, f1, g, rows, H, W)) continue;   // empty slice: no candidate for any point
       for (int q = threadIdx.x; q < np; q += blockDim.x) {
         const short4 pt = reinterpret_cast<const short4*>(points)[c0 + q];   // (block, z, y, x)
         const int dz = pt.y - z;
@@ -124,7 +136,8 @@ __global__ void __launch_bounds__(TO_THREADS) slice_edt_points_kernel(const int1
   extern __shared__ __align__(16) uint8_t sm[];
   int* f1 = reinterpret_cast<int*>(sm);
   int* g = f1 + H * W;
-  uint8_t* occ = reinterpret_cast<uint8_t*>(g + H * W);
+  int* rows = g + H * W;
+  uint8_t* occ = reinterpret_cast<uint8_t*>(rows + H + 1);
   const int z = blockIdx.x, n = blockIdx.y;
   for (int e = threadIdx.x; e < H * W; e += blockDim.x) occ[e] = 0;
   __syncthreads();
@@ -133,9 +146,9 @@ __global__ void __launch_bounds__(TO_THREADS) slice_edt_points_kernel(const int1
     if (pt.y == z) occ[pt.z * W + pt.w] = 1;
   }
   __syncthreads();
-  slice_edt(occ, f1, g, H, W);
+  const bool any = slice_edt(occ, f1, g, rows, H, W);
   int* dst = gA + (((long long)n * D + z) * H) * W;
-  for (int e = threadIdx.x; e < H * W; e += blockDim.x) dst[e] = g[e];
+  for (int e = threadIdx.x; e < H * W; e += blockDim.x) dst[e] = any ? g[e] : TO_INF;
 }
 
 // z fold of gA + histograms over rank: hist[n][k] += EDT2_A[v], cnt[n][k] += 1 (k = rank[v], 0..T); grid (chunks, N)
@@ -193,7 +206,7 @@ extern "C" int pccgeo_threshold_hist(const float* x_hat, const float* thresholds
   rank_kernel<<<(int)b, 256, t * sizeof(float), st>>>(x_hat, thresholds, t, rank, n * V);
   int rc = check_launch("rank_kernel");
   if (rc) return rc;
-  const size_t sm2 = (size_t)h * wd * (2 * sizeof(int) + 1);
+  const size_t sm2 = (size_t)h * wd * (2 * sizeof(int) + 1) + (h + 1) * sizeof(int);
   static bool attr = false;
   if (!attr) {
     PCCGEO_CUDA(cudaFuncSetAttribute(slice_edt_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -215,7 +228,7 @@ extern "C" int pccgeo_threshold_sum_ab(const void* ws, const int16_t* points, co
                                        long long* sum_ab, int n, int t, int d, int h, int wd, int max_points, void* stream) {
   PCCGEO_REQUIRE(ws && points && offsets && counts_b && sum_ab, "threshold_sum_ab: null pointer");
   PCCGEO_REQUIRE(n > 0 && t > 0 && d > 0 && h > 0 && wd > 0 && h <= 128 && wd <= 128, "threshold_sum_ab: bad shape");
-  const size_t fixed = (size_t)h * wd * (2 * sizeof(int) + 1) + 16;
+  const size_t fixed = (size_t)h * wd * (2 * sizeof(int) + 1) + (h + 1) * sizeof(int) + 16;
   long long pchunk = max_points > 0 ? max_points : 1;
   const long long room = (long long)(200 * 1024 - fixed) / (long long)sizeof(int);
   if (pchunk > room) pchunk = room;
