@@ -218,6 +218,11 @@ int pccgeo_bits_to_points_host(const uint32_t* bits, int n_blocks, int d, int h,
 int pccgeo_blocks_to_coords_host(const void* const* blocks, const long long* counts, const long long* row_bytes,
                                  int n_blocks, int is_f64, int16_t* out, int threads);
 
+/* Host half of partition_octree (src/utils/octree_coding.py:103-111): stable counting sort of float64 point rows (n, cols)
+ * by block index, block origins (n_blocks, 3) subtracted from the first three columns; offsets = (n_blocks + 1) prefix sums. */
+int pccgeo_group_points_host(const double* rows, const int32_t* block_idx, long long n, int cols, int n_blocks,
+                             const double* origins, double* out, long long* offsets);
+
 /* ---- per-block threshold optimisation ("next" #1) -----------------------------------------------
  * Replaces the kd-tree loop of src/model_opt.py:9-44 (one compute_metrics, src/utils/pc_metric.py:76-108, per threshold and
  * block): exact integer D1 sums between a block's points A and B_i = { x_hat > thresholds[i] } for every threshold at once.

@@ -57,6 +57,7 @@ SIGNATURES = {
     'pccgeo_threshold_hist': (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'pccgeo_threshold_sum_ab': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_blocks_to_coords_host': (i32, [vp, vp, vp, i32, i32, vp, i32]),
+    'pccgeo_group_points_host': (i32, [vp, vp, i64, i32, i32, vp, vp, vp]),
     'pccgeo_bits_to_points_host': (i32, [vp, i32, i32, i32, i32, vp, vp, i64, i32]),
 }
 

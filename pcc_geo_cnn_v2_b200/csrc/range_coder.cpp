@@ -477,3 +477,33 @@ extern "C" int pccgeo_blocks_to_coords_host(const void* const* blocks, const lon
   });
   return PCCGEO_OK;
 }
+
+// Host half of partition_octree (reference src/utils/octree_coding.py:103-111, the per-point Python loop that takes 7.6 s
+// on longdress): stable counting sort of point rows by block index.  rows: (n, cols) float64; block_idx[i] in [0, n_blocks);
+// origins: (n_blocks, 3) block origins subtracted from the first three columns; out: (n, cols) grouped rows, points of a
+// block keep their input order; offsets: (n_blocks + 1) prefix sums.
+extern "C" int pccgeo_group_points_host(const double* rows, const int32_t* block_idx, long long n, int cols, int n_blocks,
+                                        const double* origins, double* out, long long* offsets) {
+  if (n < 0 || cols < 3 || n_blocks < 0 || (n > 0 && (!rows || !block_idx || !origins || !out)) || !offsets) {
+    pccgeo::set_error("group_points: bad argument");
+    return PCCGEO_EINVAL;
+  }
+  for (int b = 0; b <= n_blocks; ++b) offsets[b] = 0;
+  for (long long i = 0; i < n; ++i) {
+    if (block_idx[i] < 0 || block_idx[i] >= n_blocks) {
+      pccgeo::set_error("group_points: block index out of range");
+      return PCCGEO_EINVAL;
+    }
+    ++offsets[block_idx[i] + 1];
+  }
+  for (int b = 0; b < n_blocks; ++b) offsets[b + 1] += offsets[b];
+  std::vector<long long> cur(offsets, offsets + n_blocks);
+  for (long long i = 0; i < n; ++i) {
+    const int b = block_idx[i];
+    double* o = out + cur[b]++ * cols;
+    const double* r = rows + i * cols;
+    o[0] = r[0] - origins[b * 3]; o[1] = r[1] - origins[b * 3 + 1]; o[2] = r[2] - origins[b * 3 + 2];
+    for (int c = 3; c < cols; ++c) o[c] = r[c];
+  }
+  return PCCGEO_OK;
+}

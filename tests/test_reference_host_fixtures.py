@@ -1,0 +1,61 @@
+"""Container and octree partitioning against golden vectors produced by the REFERENCE's own modules
+(tests/golden/make_reference_host_fixtures.py imports /root/reference/src/model_syntax.py and utils/octree_coding.py): the
+two rows of this repo whose parity is pinned by the reference itself.  CPU only."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from pcc_geo_cnn_v2_b200 import model_syntax as MS
+from pcc_geo_cnn_v2_b200 import octree_coding as OC
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_host_fixtures.npz'))
+
+
+@pytest.mark.parametrize('ci', range(int(G['syntax_cases'])))
+def test_container_bytes_equal_the_reference(ci):
+    res, lvl, n_blocks, n_strings = (int(v) for v in G[f'syntax{ci}_meta'])
+    lens, blob = G[f'syntax{ci}_lens'], G[f'syntax{ci}_strings'].tobytes()
+    strings, pos = [], 0
+    for ln in lens:
+        strings.append(blob[pos:pos + int(ln)])
+        pos += int(ln)
+    data = [(tuple(strings[b * n_strings:(b + 1) * n_strings]), int(G[f'syntax{ci}_thr'][b])) for b in range(n_blocks)]
+    got = MS.save_compressed_file(list(G[f'syntax{ci}_binstr']), data, res, lvl)
+    assert got == G[f'syntax{ci}_blob'].tobytes()
+    r2, l2, binstr2, blocks2 = MS.load_compressed_file(io.BytesIO(got))
+    assert (int(r2), int(l2)) == (res, lvl) and np.array_equal(binstr2, G[f'syntax{ci}_binstr'])
+    assert [(tuple(s), int(t)) for s, t in blocks2] == data
+
+
+def test_container_limits_raise_like_the_reference():
+    with pytest.raises(AssertionError):
+        MS.save_compressed_file([1], [((b'x' * 70000,), 0)], 64, 1)
+    with pytest.raises(AssertionError):
+        MS.load_compressed_file(io.BytesIO(MS.save_compressed_file([1], [((b'ab',), 3)], 64, 1) + b'!'))
+
+
+@pytest.mark.parametrize('ci', range(int(G['oct_cases'])))
+def test_octree_partition_equals_the_reference(ci):
+    res, level, cols = (int(v) for v in G[f'oct{ci}_meta'])
+    pts = G[f'oct{ci}_points']
+    blocks, binstr = OC.partition_octree(pts, [0, 0, 0], [res] * 3, level)
+    assert [len(b) for b in blocks] == list(G[f'oct{ci}_block_len'])
+    assert np.array_equal(np.vstack(blocks), G[f'oct{ci}_blocks']) and blocks[0].dtype == np.float64
+    assert list(binstr) == list(G[f'oct{ci}_binstr'])
+    dep = OC.departition_octree(blocks, binstr, [0, 0, 0], [res] * 3, level)
+    if len(G[f'oct{ci}_departitioned']):       # (the reference's departition raises on one-level trees)
+        assert np.array_equal(np.vstack(dep), G[f'oct{ci}_departitioned'])
+    assert sorted(map(tuple, np.vstack(dep))) == sorted(map(tuple, pts))
+
+
+def test_octree_deep_levels_round_trip():
+    """geo_level < 2*level: the reference's truncated sort key breaks its own departition; Morton order round-trips."""
+    rng = np.random.default_rng(0)
+    pts = np.unique(rng.integers(0, 256, size=(3000, 3)), axis=0).astype(np.float64)
+    for level in (5, 8):
+        blocks, binstr = OC.partition_octree(pts, [0, 0, 0], [256] * 3, level)
+        dep = OC.departition_octree(blocks, binstr, [0, 0, 0], [256] * 3, level)
+        assert sorted(map(tuple, np.vstack(dep))) == sorted(map(tuple, pts))
+        assert all((b[:, :3] >= 0).all() and (b[:, :3] < 256 // 2 ** level).all() for b in blocks)
