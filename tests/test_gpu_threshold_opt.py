@@ -71,3 +71,27 @@ def test_optimal_thresholds_match_the_oracle_kdtree_search():
     dec, _ = m.decompress_blocks(None, dl[0], (size, size, size))
     for a, b in zip(meta[0]['x_hat_list'], dec):
         assert np.array_equal(a, b)
+
+
+def test_gpu_threshold_search_equals_the_reference_model_opt():
+    """The GPU path against choices made by the REFERENCE's own model_opt.py / pc_metric.py on the same blocks and x_hat
+    fields (tests/golden/ref_model_opt.npz): this row's parity is pinned by the reference itself."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_model_opt.npz'))
+    size, thr = int(g['size']), g['thresholds']
+    opt_metrics, max_deltas = [str(m) for m in g['opt_metrics']], [float(d) for d in g['max_deltas']]
+    n = int(g['n_blocks'])
+    blocks = [g[f'block{j}'].astype(np.float32) for j in range(n)]
+    x_hat = torch.from_numpy(np.stack([g[f'x_hat{j}'] for j in range(n)])[:, None]).cuda()
+    coords = torch.from_numpy(blocks_to_coords(blocks)).cuda()
+    offsets = np.concatenate([[0], np.cumsum([len(b) for b in blocks])]).astype(np.int64)
+    t32 = threshold_f32(thr, np.arange(len(thr)))
+    names, best = MO.compute_optimal_thresholds_batch(blocks, x_hat, t32, coords, offsets, opt_metrics=opt_metrics, max_deltas=max_deltas)
+    assert names == [str(v) for v in g['names']]
+    for j in range(n):
+        assert list(best[j]) == list(g[f'best{j}']), (j, list(best[j]), list(g[f'best{j}']))
+    # and the sums behind the first choice equal the reference's compute_metrics
+    sab, sba, cb = MO.threshold_sums(x_hat, t32, coords, offsets)
+    for j in range(n):
+        i = int(g[f'best{j}'][0])
+        assert [float(sab[j, i]), float(sba[j, i])] == list(g[f'metrics{j}'][:2])

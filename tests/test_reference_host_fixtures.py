@@ -59,3 +59,19 @@ def test_octree_deep_levels_round_trip():
         dep = OC.departition_octree(blocks, binstr, [0, 0, 0], [256] * 3, level)
         assert sorted(map(tuple, np.vstack(dep))) == sorted(map(tuple, pts))
         assert all((b[:, :3] >= 0).all() and (b[:, :3] < 256 // 2 ** level).all() for b in blocks)
+
+
+def test_oracle_threshold_search_equals_the_reference_model_opt():
+    """oracle/model_opt.py (kd-tree restatement) against choices made by the reference's own model_opt.py / pc_metric.py
+    (tests/golden/make_reference_model_opt_fixture.py): pins the oracle that the GPU path is tested against."""
+    from oracle import model_opt as OMO
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_model_opt.npz'))
+    size, thr = int(g['size']), g['thresholds']
+    opt_metrics, max_deltas = [str(m) for m in g['opt_metrics']], [float(d) for d in g['max_deltas']]
+    for j in range(int(g['n_blocks'])):
+        names, best = OMO.compute_optimal_thresholds(g[f'block{j}'].astype(np.float32), g[f'x_hat{j}'], thr, size,
+                                                     opt_metrics=opt_metrics, max_deltas=max_deltas)
+        assert names == [str(n) for n in g['names']]
+        assert list(best) == list(g[f'best{j}']), j
+        m = OMO.compute_metrics(g[f'block{j}'].astype(np.float64), np.argwhere(g[f'x_hat{j}'] > thr[best[0]]), size - 1)
+        assert np.allclose([m['d1_sum_AB'], m['d1_sum_BA'], m['d1_mse'], m['d1_psnr']], g[f'metrics{j}'], rtol=1e-6)
