@@ -127,6 +127,37 @@ def v2_summaries(log_z_likelihoods, sigma_tilde, train_mbpov_z, z, z_likelihoods
             'z_likelihoods': z_likelihoods, 'log_z_likelihoods': log_z_likelihoods}
 
 
+def select_best_per_opt_metric(binstr, x_hat_list, level, opt_metrics, points, resolution, with_normals, opt_groups=('d1', 'd2')):
+    """src/model_types.py:128-176: per metric group, re-assemble every candidate reconstruction of the whole cloud
+    (departition_octree), score it against the original points and keep the best by `<group>_psnr`.  Host code (kd-trees)
+    like the reference; the d2 group needs normals and is only available through the reference's own modules."""
+    from scipy.spatial import cKDTree
+    from .octree_coding import departition_octree
+    from .pc_metric import compute_metrics
+    assert len(opt_metrics) == len(x_hat_list), (f'lengths of opt_metrics {len(opt_metrics)} and x_hat_list'
+                                                 f' {len(x_hat_list)} should be equal')
+    om_groups = [[(x, y, i) for i, (x, y) in enumerate(zip(opt_metrics, x_hat_list)) if x.startswith(group)] for group in opt_groups]
+    points = np.asarray(points)
+    bbox_min, bbox_max = [0, 0, 0], [resolution] * 3
+    t1 = cKDTree(points[:, :3])
+    metadata = []
+    for group, om_group in zip(opt_groups, om_groups):
+        if len(om_group) == 0:
+            continue
+        if group != 'd1':
+            raise NotImplementedError(f'{group} metrics need normals: use the reference host modules')
+        metric_key = f'{group}_psnr'
+        om_names, cur_x_hat_list, indexes = zip(*om_group)
+        cur_blocks_depart = [departition_octree(x, list(binstr), bbox_min, bbox_max, level) for x in cur_x_hat_list]
+        cur_blocks_full = [np.vstack(x) for x in cur_blocks_depart]
+        cur_metrics_full = [compute_metrics(points[:, :3], x, resolution - 1, t1=t1) for x in cur_blocks_full]
+        local_best_idx = int(np.argmax([x[metric_key] for x in cur_metrics_full]))
+        metadata.append({'idx': indexes[local_best_idx], 'metrics': cur_metrics_full[local_best_idx],
+                         'x_hat_list': cur_x_hat_list[local_best_idx], 'blocks_depart': cur_blocks_depart[local_best_idx],
+                         'blocks_full': cur_blocks_full[local_best_idx]})
+    return metadata
+
+
 def sparse_to_dense(block, x_shape, data_format='channels_first'):
     """src/model_types.py:108-114 on the GPU: (n,3) integer coords -> fp32 occupancy of shape x_shape."""
     assert data_format == 'channels_first'
@@ -500,13 +531,11 @@ class CompressionModel:
         return np.asarray(idx, np.int64), list(ret)
 
     def _select_best(self, binstr, x_hat_list, level, opt_metrics, points, resolution, with_normals):
-        """select_best_per_opt_metric (model_types.py:128-176) needs the reference's octree + metric host modules;
-        without them the first opt_metric is selected and no metrics are reported."""
-        try:
-            from model_types import select_best_per_opt_metric  # noqa: the reference's own host code
-            return select_best_per_opt_metric(binstr, x_hat_list, level, opt_metrics, points, resolution, with_normals)
-        except Exception:
+        """select_best_per_opt_metric (model_types.py:128-176) when the caller passes the whole cloud and its octree;
+        without them (block-level callers, benchmarks) the first opt_metric is selected and no metrics are reported."""
+        if points is None or binstr is None:
             return [{'idx': 0, 'metrics': {}, 'x_hat_list': x_hat_list[0], 'blocks_depart': None, 'blocks_full': None}]
+        return select_best_per_opt_metric(binstr, x_hat_list, level, opt_metrics, points, resolution, with_normals)
 
     def decompress_blocks(self, sess, blocks, x_shape, debug=False):
         """src/model_types.py:220-238: blocks = [(strings, threshold_idx)] -> ([float32 (m,3)], debug list)."""

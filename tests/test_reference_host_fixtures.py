@@ -75,3 +75,12 @@ def test_oracle_threshold_search_equals_the_reference_model_opt():
         assert list(best) == list(g[f'best{j}']), j
         m = OMO.compute_metrics(g[f'block{j}'].astype(np.float64), np.argwhere(g[f'x_hat{j}'] > thr[best[0]]), size - 1)
         assert np.allclose([m['d1_sum_AB'], m['d1_sum_BA'], m['d1_mse'], m['d1_psnr']], g[f'metrics{j}'], rtol=1e-6)
+
+
+def test_scale_table_and_thresholds_equal_the_reference_constructors():
+    """CompressionModel.thresholds / CompressionModelV2.scale_table (model_types.py:181,324) as the reference builds them."""
+    from pcc_geo_cnn_v2_b200 import ModelConfigType
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_block_loops.npz'))
+    m = ModelConfigType['c3p'].build()
+    assert np.array_equal(np.asarray(m.thresholds), g['thresholds'])
+    assert np.array_equal(np.asarray(m.scale_table, np.float64), g['scale_table'])
