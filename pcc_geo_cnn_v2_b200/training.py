@@ -14,7 +14,10 @@ autograd (the focal loss amplifies the 1e-5 forward differences).  The default k
 kernel (gradients within 2e-3).  Both optimisers follow TF1's AdamOptimizer
 (lr_t = lr*sqrt(1-b2^t)/(1-b1^t), theta -= lr_t*m/(sqrt(v)+eps)): Adam(1e-4) on every trainable of the main loss, Adam(1e-3)
 on the entropy bottleneck's quantiles (auxiliary loss).  Whole-batch sums everywhere (FL is sum-reduced and mbpov divides
-by the batch's occupied-voxel count), so multi-GPU training must all-reduce sums, not average per-rank losses.
+by the batch's occupied-voxel count), so data-parallel training all-reduces SUMS, not averages: with torch.distributed
+initialised (one process per GPU, NCCL) every rank runs its slice of the global batch, the occupied-voxel count is
+all-reduced BEFORE the backward pass (it scales every likelihood gradient), and all gradients travel in ONE flat
+all-reduce; every rank then applies the same Adam step, so the replicas stay bit-identical without a broadcast.
 """
 import math
 
@@ -60,6 +63,7 @@ class Trainer:
         self.model, self.gamma, self.alpha, self.lmbda, self.lr = model, gamma, alpha, lmbda, lr
         self.tensor_cores = tensor_cores
         self.twins = {}    # layer -> adjoint layer (data gradient), sharing the kernel array
+        self.distributed = None   # None: use torch.distributed when it is initialised with more than one rank
         self.v2 = hasattr(model, 'hyper_analysis_transform')
         self.transforms = model.transforms()
         self.traces = {k: trace(t, fuse_residual=False) for k, t in self.transforms.items()}
@@ -196,6 +200,18 @@ class Trainer:
         gf = [d[:, 34 + 3 * i:37 + 3 * i].reshape(C, 3, 1) * (1.0 - np.tanh(eb.factors[i].astype(np.float64)) ** 2) for i in range(3)]
         return gm + gb + gf
 
+    # -- data parallelism ------------------------------------------------------------------------------
+    def _world(self):
+        import torch.distributed as dist
+        on = self.distributed if self.distributed is not None else (dist.is_available() and dist.is_initialized())
+        return dist if (on and dist.get_world_size() > 1) else None
+
+    @staticmethod
+    def _allreduce_scalars(dist, *vals):
+        t = torch.tensor(vals, dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     # -- one step ----------------------------------------------------------------------------------------
     def forward_backward(self, x, noise_y=None, noise_z=None):
         """Returns (values dict, grads dict): loss / fl / mbpov as python floats; grads[layer] = {'w','b'} (tap-major),
@@ -212,7 +228,10 @@ class Trainer:
                             self._p(s[1], s[1].in_channels)
             self._refresh_layers()
         y, tape_a = self._forward('analysis', x)
+        dist = self._world()
         n_occ = float(x.sum(dtype=torch.float64))
+        if dist is not None:
+            (n_occ,) = self._allreduce_scalars(dist, n_occ)   # the GLOBAL batch's occupied voxels (model_types.py:347)
         c = 1.0 / (-math.log(2.0) * n_occ)                 # d mbpov / d (sum ln p)
         if noise_y is None:
             noise_y = torch.rand_like(y) - 0.5
@@ -231,8 +250,11 @@ class Trainer:
             _, sum_y = ops.eb_likelihood(y_tilde, ebp, want_likelihood=False)
         x_tilde, tape_s = self._forward('synthesis', y_tilde)
         fl = float(ops.focal_loss_sum(x, x_tilde, self.gamma, self.alpha)[0])
-        mb_y = float(sum_y[0]) * c
-        mb_z = float(sum_z[0]) * c if self.v2 else 0.0
+        ly, lz = float(sum_y[0]), float(sum_z[0]) if self.v2 else 0.0
+        if dist is not None:
+            fl, ly, lz = self._allreduce_scalars(dist, fl, ly, lz)   # reported values are those of the global batch
+        mb_y = ly * c
+        mb_z = lz * c if self.v2 else 0.0
         values = {'fl': fl, 'mbpov_y': mb_y, 'mbpov_z': mb_z, 'mbpov': mb_y + mb_z, 'loss': self.lmbda * fl + mb_y + mb_z,
                   'num_occupied_voxels': n_occ, 'x_tilde': x_tilde, 'y': y}
         # ---- backward
@@ -249,6 +271,19 @@ class Trainer:
             dv, dpar = ops.eb_likelihood_bwd(y_tilde, ebp, c)
             g_y = ops.axpby(g_y, dv, 1.0, 1.0)
         self._backward(tape_a, g_y, grads, need_input_grad=False)
+        if dist is not None:
+            # one flat all-reduce (sum) of every gradient: conv kernels, biases and the entropy bottleneck's (C,44) block
+            parts = [dpar.reshape(-1)]
+            for layer in self.params:
+                parts.append(grads[layer]['w'].reshape(-1))
+                if grads[layer]['b'] is not None:
+                    parts.append(grads[layer]['b'].reshape(-1))
+            flat = torch.cat(parts)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            pos = 0
+            for t in parts:
+                t.copy_(flat[pos:pos + t.numel()])
+                pos += t.numel()
         grads['entropy_bottleneck'] = self._eb_raw_grads(dpar)
         return values, grads
 
