@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_kernel(const WgradParams p) 
 // few distinct addresses (broadcast) and the staging stores 4-way at worst.  Same reduction contract: fp32 inside a chunk
 // slice, double running sums, slices and splits added in a fixed order (deterministic).
 template <int WT_VC>   // voxels per staged chunk (256 for narrow layers: fewer barriers / index decodes per FMA)
-__global__ void __launch_bounds__(WG_THREADS) wgrad_tiled_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(WG_THREADS, WT_VC == 256 ? 3 : 2) wgrad_tiled_kernel(const WgradParams p) {
   extern __shared__ float4 smem4[];
   const int C4i = (p.Cin + 3) / 4, C4o = (p.Cout + 3) / 4, C4 = C4i + C4o, ROW = C4 + 1;
   const int TP = C4i * C4o, VS = WG_THREADS / TP;          // tiles, voxel slices (TP divides 256)

@@ -9,7 +9,7 @@ and the data gradients (the adjoint layer: conv <-> transposed conv with the sam
 kernel dispatch as the codec -- the tcgen05 kernels in the active precision mode (bf16x3 by default, fp32-class) -- with
 the packed weight images rebuilt from the fp32 master weights every step; weight / bias gradients, ReLU masks, focal-loss
 and likelihood backward are the fp32 kernels of csrc/train.cu.  That is `Trainer(..., tensor_cores=True)`
-(`model.train_tensor_cores = True`): 181 -> 124 ms per batch-32 c3p step, conv-kernel gradients within 1e-2 of float64
+(`model.train_tensor_cores = True`): 155 -> 99 ms per batch-32 c3p step, conv-kernel gradients within 1e-2 of float64
 autograd (the focal loss amplifies the 1e-5 forward differences).  The default keeps every conv on the fp32 CUDA-core
 kernel (gradients within 2e-3).  Both optimisers follow TF1's AdamOptimizer
 (lr_t = lr*sqrt(1-b2^t)/(1-b1^t), theta -= lr_t*m/(sqrt(v)+eps)): Adam(1e-4) on every trainable of the main loss, Adam(1e-3)
