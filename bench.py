@@ -105,6 +105,17 @@ def ncu_traffic(kernel, blocks):
     return None
 
 
+def ncu_summary_field(kernel, blocks, field):
+    p = os.path.join(ROOT, 'profiles', 'ncu_dominant_kernel.json')
+    try:
+        d = json.load(open(p))
+        if d.get('kernel') == kernel and d.get('blocks') == blocks:
+            return d.get(field)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -286,7 +297,12 @@ def main():
     roofline = {'kernel': kname, 'bound': 'tensor', 'achieved': ach_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': ach_tf / peak_tf, 'traffic': ncu_traffic(kname, B), 'peak_source': peak_src, 'ms_per_launch': kms,
                 'algorithmic_flop_per_launch': 2 * LAYER_MMAC * 1e6 * B,
-                'hbm_gbs_algorithmic': io_bytes / (kms / 1e3) / 1e9, 'hbm_peak_gbs': peak_gbs}
+                'hbm_gbs_algorithmic': io_bytes / (kms / 1e3) / 1e9, 'hbm_peak_gbs': peak_gbs,
+                # context from the committed ncu capture of this launch and the issue-rate microbenchmark:
+                # an N=48 tcgen05.mma stream from two CTAs per SM cannot keep the tensor pipe busier than 24/57 = 42 %
+                'tensor_pipe_active_pct_ncu': ncu_summary_field(kname, B, 'tensor_pipe_active_pct'),
+                'tensor_pipe_ceiling_pct_small_n': 42.1 if terms else None,
+                'executed_bf16_products_per_algorithmic_flop': 3 if terms == 2 else (1 if terms else None)}
     del xin
 
     # ---- e2e through the public API: host blocks in, strings out, strings in, host points out ----
