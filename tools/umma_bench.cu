@@ -20,15 +20,16 @@ struct Cfg {
   int m64;      // 1: M = 64
   int smem_kb;
   int dual;     // 1: two warps of the same CTA issue concurrently (different accumulators)
+  int commit_every;  // > 0: tcgen05.commit (to a scratch mbarrier, nobody waits) after this many groups of 9 MMAs
 };
 
 __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar, bar2;
+  __shared__ uint64_t bar, bar2, scratch[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x * 16; i < c.smem_kb * 1024; i += blockDim.x * 16) *reinterpret_cast<int4*>(smem + i) = make_int4(0, 0, 0, 0);
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); mbar_init(smem_u32(&scratch[0]), 1); mbar_init(smem_u32(&scratch[1]), 1); fence_barrier_init(); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(c.smem_kb >= 200 ? 512 : 256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* out) {
               umma_bf16_lh(tmem_base + dwarp + doff[k], a_lo0 + offs[k], a_hi, b_lo, b_hi, idesc, 1u);
             }
           }
+          if (c.commit_every > 0 && (it % c.commit_every) == c.commit_every - 1) umma_commit(smem_u32(&scratch[warp & 1]));
         }
         __syncwarp();
       }
@@ -98,17 +100,21 @@ int main() {
   cudaMalloc(&d, 8);
   cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int ns[] = {16, 32, 48, 64, 96, 128, 144, 192, 256};
-  struct P { const char* name; int ts, rot, m64, ctas_per_sm, dual; } pats[] = {
-      {"SS 2 warps of one CTA (per warp)", 0, 1, 0, 1, 1},
-      {"SS 1 acc", 0, 1, 0, 1, 0},
-      {"SS 2 acc rotate", 0, 2, 0, 1, 0},
-      {"SS 3 acc rotate", 0, 3, 0, 1, 0},
-      {"SS M=64", 0, 1, 1, 1, 0},
-      {"SS 2 CTAs/SM (per CTA)", 0, 1, 0, 2, 0},
-      {"SS 2 CTAs/SM, 2 acc", 0, 2, 0, 2, 0},
-      {"TS 1 acc", 1, 1, 0, 1, 0},
-      {"TS 2 acc rotate", 1, 2, 0, 1, 0},
-      {"TS 2 CTAs/SM (per CTA)", 1, 1, 0, 2, 0},
+  struct P { const char* name; int ts, rot, m64, ctas_per_sm, dual, ce; } pats[] = {
+      {"SS 2 warps of one CTA (per warp)", 0, 1, 0, 1, 1, 0},
+      {"SS 2 warps, commit every 27 MMAs", 0, 1, 0, 1, 1, 3},
+      {"SS 2 warps, commit every 9 MMAs", 0, 1, 0, 1, 1, 1},
+      {"SS 1 warp, commit every 9 MMAs", 0, 1, 0, 1, 0, 1},
+      {"SS 2 CTAs/SM, commit every 9 MMAs", 0, 1, 0, 2, 0, 1},
+      {"SS 1 acc", 0, 1, 0, 1, 0, 0},
+      {"SS 2 acc rotate", 0, 2, 0, 1, 0, 0},
+      {"SS 3 acc rotate", 0, 3, 0, 1, 0, 0},
+      {"SS M=64", 0, 1, 1, 1, 0, 0},
+      {"SS 2 CTAs/SM (per CTA)", 0, 1, 0, 2, 0, 0},
+      {"SS 2 CTAs/SM, 2 acc", 0, 2, 0, 2, 0, 0},
+      {"TS 1 acc", 1, 1, 0, 1, 0, 0},
+      {"TS 2 acc rotate", 1, 2, 0, 1, 0, 0},
+      {"TS 2 CTAs/SM (per CTA)", 1, 1, 0, 2, 0, 0},
   };
   printf("%-32s", "cycles/MMA  N=");
   for (int n : ns) printf("%7d", n);
@@ -119,7 +125,7 @@ int main() {
       if (pt.rot == 3 && n > 128) { printf("      -"); continue; }
       if (pt.ctas_per_sm == 2 && pt.rot * (n <= 128 ? 128 : 256) > 256 && pt.rot > 1) { printf("      -"); continue; }
       const int smem_kb = pt.ctas_per_sm == 2 ? 100 : 200;
-      Cfg c{n, 160, 2880, 1, 400, pt.ts, pt.rot, pt.m64, smem_kb, pt.dual};
+      Cfg c{n, 160, 2880, 1, 400, pt.ts, pt.rot, pt.m64, smem_kb, pt.dual, pt.ce};
       bench_kernel<<<148 * pt.ctas_per_sm, 128, smem_kb * 1024>>>(c, d);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("  ERR %s\n", cudaGetErrorString(e)); return 1; }
