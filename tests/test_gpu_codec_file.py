@@ -46,3 +46,24 @@ def test_point_cloud_file_round_trip(fixed_threshold):
     cloud = np.vstack(OC.departition_octree(dec_blocks, list(binstr2), [0, 0, 0], [res] * 3, level)) if nonempty else np.zeros((0, 3))
     assert cloud.shape[1] == 3 and (cloud >= 0).all() and (cloud < res).all()
     assert len(blob) < 40 * len(pts)   # a plausible size for untrained weights; the exact rate is checked elsewhere
+
+
+def test_codec_functions_and_ply_files(tmp_path):
+    """compress_point_cloud / decompress_point_cloud (the script bodies as functions) from and to PLY files, adaptive thresholds."""
+    from pcc_geo_cnn_v2_b200 import codec, pc_io
+    res, level = 128, 1
+    rng = np.random.default_rng(9)
+    u = rng.random((20000, 2))
+    pts = np.stack([u[:, 0] * (res - 1), (0.5 + 0.3 * np.cos(u[:, 1] * 4)) * (res - 1), u[:, 1] * (res - 1)], 1)
+    pts = np.unique(pts.astype(np.int64), axis=0).astype(np.float32)
+    src = tmp_path / 'in.ply'
+    pc_io.write_pc(str(src), pts)
+    m = ModelConfigType['c3p'].build(batch_size=4)
+    m.set_weights(synthetic.trained_like_weights(m, seed=3, output_bias=-0.45))
+    blobs, data = codec.compress_point_cloud(m, pc_io.load_pc(str(src)), res, level, opt_metrics=('d1_mse',), max_deltas=(np.inf,))
+    assert len(blobs) == 1 and data[0]['metrics']['d1_psnr'] > 0
+    out = codec.decompress_point_cloud(m, blobs[0])
+    assert out.dtype == np.float32 and np.array_equal(out, np.asarray(data[0]['blocks_full'], np.float32))
+    dst = tmp_path / 'out.ply'
+    pc_io.write_pc(str(dst), out)
+    assert np.array_equal(pc_io.load_pc(str(dst)), out)

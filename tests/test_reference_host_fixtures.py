@@ -84,3 +84,31 @@ def test_scale_table_and_thresholds_equal_the_reference_constructors():
     m = ModelConfigType['c3p'].build()
     assert np.array_equal(np.asarray(m.thresholds), g['thresholds'])
     assert np.array_equal(np.asarray(m.scale_table, np.float64), g['scale_table'])
+
+
+def test_ply_reader_and_writer(tmp_path):
+    """pc_io: binary / ASCII PLY vertex elements (the reference's dataset layout: binary float x y z) and the writer's layout
+    (float32 x y z + uint8 colours, pc_io.py:16-26,49-51)."""
+    from pcc_geo_cnn_v2_b200 import pc_io
+    rng = np.random.default_rng(0)
+    pts = rng.integers(0, 64, size=(100, 3)).astype(np.float32)
+    p = tmp_path / 'a.ply'
+    pc_io.write_pc(str(p), pts)
+    assert np.array_equal(pc_io.load_pc(str(p)), pts)
+    cols = np.concatenate([pts, rng.integers(0, 256, size=(100, 3))], axis=1)
+    pc_io.write_pc(str(p), cols)
+    c = pc_io.read_ply(str(p))
+    assert list(c) == ['x', 'y', 'z', 'red', 'green', 'blue'] and c['red'].dtype == np.uint8 and np.array_equal(c['blue'], cols[:, 5])
+    ascii_ply = ('ply\nformat ascii 1.0\ncomment made by hand\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n'
+                 'property float nx\nproperty float ny\nproperty float nz\nelement face 0\nproperty list uchar int vertex_indices\n'
+                 'end_header\n1 2 3 0 0 1\n4 5 6 0 1 0\n7 8 9 1 0 0\n').encode()
+    q = tmp_path / 'b.ply'
+    q.write_bytes(ascii_ply)
+    assert np.array_equal(pc_io.load_pc(str(q)), [[1, 2, 3], [4, 5, 6], [7, 8, 9]])
+    assert np.array_equal(pc_io.load_normals(str(q)), [[0, 0, 1], [0, 1, 0], [1, 0, 0]])
+    blocks = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'modelnet_blocks.npz'))
+    header = b'ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nend_header\n'
+    b0 = blocks['block0'].astype('<f4')
+    assert np.array_equal(pc_io.load_pc(header % len(b0) + b0.tobytes()) if False else pc_io.read_ply(header % len(b0) + b0.tobytes())['x'], b0[:, 0])
+    p_min, p_max, shape = pc_io.get_shape_data(64, 'channels_first')
+    assert list(shape) == [1, 64, 64, 64] and list(pc_io.get_shape_data(64, 'channels_last')[2]) == [64, 64, 64, 1]
