@@ -10,11 +10,57 @@ from . import _lib as L
 D1_METRICS = ('d1_sum_AB', 'd1_sum_BA', 'd1_sum_max', 'd1_sum_mean', 'd1_mse_AB', 'd1_mse_BA', 'd1_mse')
 
 
-def validate_opt_metrics(opt_metrics, with_normals=False):  # pc_metric.py:59-63
+def validate_opt_metrics(opt_metrics, with_normals=False):  # the GPU path: D1 only
     for m in opt_metrics:
         if m.startswith('d2'):
-            raise NotImplementedError(f'{m}: the D2 (point-to-plane) metrics are not implemented on the GPU path')
+            raise NotImplementedError(f'{m}: the D2 (point-to-plane) metrics run on the host path (compute_optimal_thresholds)')
         assert m in D1_METRICS, f'{m} not found in {D1_METRICS}'
+
+
+def build_points_threshold(x_hat, thresholds, len_block, max_delta=np.inf):  # model_opt.py:9-18
+    pa_list = []
+    for i, t in enumerate(thresholds):
+        pa = np.argwhere(x_hat > t).astype('float32')
+        if len(pa) == 0:
+            break
+        len_ratio = len(pa) / len_block
+        if (1 / max_delta) < len_ratio < max_delta:
+            pa_list.append((i, pa))
+    return pa_list
+
+
+def compute_optimal_thresholds(block, x_hat, thresholds, resolution, normals=None, opt_metrics=('d1_mse',), max_deltas=(np.inf,),
+                               fixed_threshold=False):
+    """model_opt.py:21-77 on the host with kd-trees, any metric incl. D2 (the GPU path, compute_optimal_thresholds_batch,
+    covers the D1 metrics and is what compress_blocks uses when no normals are involved)."""
+    from scipy.spatial import cKDTree
+    from .pc_metric import compute_metrics, validate_opt_metrics as validate
+    validate(opt_metrics, with_normals=normals is not None)
+    assert len(max_deltas) > 0
+    best_thresholds = []
+    ret_opt_metrics = [f'{opt_metric}_{max_delta}' for max_delta in max_deltas for opt_metric in opt_metrics]
+    if fixed_threshold:
+        return ret_opt_metrics, [len(thresholds) // 2] * len(max_deltas) * len(opt_metrics)
+    block = np.asarray(block)
+    pa_list = build_points_threshold(x_hat, thresholds, len(block))
+    max_threshold_idx = len(thresholds) - 1
+    if len(pa_list) == 0:
+        return ret_opt_metrics, [max_threshold_idx] * len(opt_metrics)
+    t1 = cKDTree(block[:, :3], balanced_tree=False)
+    pa_metrics = [compute_metrics(block[:, :3], pa, resolution - 1, p1_n=normals, t1=t1) for _, pa in pa_list]
+    for max_delta in max_deltas:
+        cur_pa_list, cur_pa_metrics = pa_list, pa_metrics
+        if max_delta is not None:
+            cand = build_points_threshold(x_hat, thresholds, len(block), max_delta)
+            if len(cand) > 0:
+                cur_pa_list, cur_pa_metrics = cand, [pa_metrics[i] for i in [x[0] for x in cand]]
+        for opt_metric in opt_metrics:
+            best = int(np.argmin([x[opt_metric] for x in cur_pa_metrics]))
+            mean_point = np.round(np.mean(block[:, :3], axis=0))[np.newaxis, :]
+            mean_point_metric = compute_metrics(block[:, :3], mean_point, resolution - 1, p1_n=normals, t1=t1)[opt_metric]
+            best_thresholds.append(max_threshold_idx if cur_pa_metrics[best][opt_metric] > mean_point_metric else cur_pa_list[best][0])
+    assert len(ret_opt_metrics) == len(best_thresholds)
+    return ret_opt_metrics, best_thresholds
 
 
 def threshold_sums(x_hat, thresholds_f32, coords, offsets):

@@ -130,7 +130,7 @@ def v2_summaries(log_z_likelihoods, sigma_tilde, train_mbpov_z, z, z_likelihoods
 def select_best_per_opt_metric(binstr, x_hat_list, level, opt_metrics, points, resolution, with_normals, opt_groups=('d1', 'd2')):
     """src/model_types.py:128-176: per metric group, re-assemble every candidate reconstruction of the whole cloud
     (departition_octree), score it against the original points and keep the best by `<group>_psnr`.  Host code (kd-trees)
-    like the reference; the d2 group needs normals and is only available through the reference's own modules."""
+    like the reference)."""
     from scipy.spatial import cKDTree
     from .octree_coding import departition_octree
     from .pc_metric import compute_metrics
@@ -144,13 +144,12 @@ def select_best_per_opt_metric(binstr, x_hat_list, level, opt_metrics, points, r
     for group, om_group in zip(opt_groups, om_groups):
         if len(om_group) == 0:
             continue
-        if group != 'd1':
-            raise NotImplementedError(f'{group} metrics need normals: use the reference host modules')
         metric_key = f'{group}_psnr'
         om_names, cur_x_hat_list, indexes = zip(*om_group)
         cur_blocks_depart = [departition_octree(x, list(binstr), bbox_min, bbox_max, level) for x in cur_x_hat_list]
         cur_blocks_full = [np.vstack(x) for x in cur_blocks_depart]
-        cur_metrics_full = [compute_metrics(points[:, :3], x, resolution - 1, t1=t1) for x in cur_blocks_full]
+        normals = points[:, points.shape[1] - 3:] if with_normals else None   # get_normals_if, model_types.py:117-118
+        cur_metrics_full = [compute_metrics(points[:, :3], x, resolution - 1, p1_n=normals, t1=t1) for x in cur_blocks_full]
         local_best_idx = int(np.argmax([x[metric_key] for x in cur_metrics_full]))
         metadata.append({'idx': indexes[local_best_idx], 'metrics': cur_metrics_full[local_best_idx],
                          'x_hat_list': cur_x_hat_list[local_best_idx], 'blocks_depart': cur_blocks_depart[local_best_idx],
@@ -502,8 +501,7 @@ class CompressionModel:
     def _optimal_thresholds(self, blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas):
         """Per-block threshold search (reference src/model_opt.py:21-77).  D1 metrics: every threshold's nearest-neighbour
         sums come from the GPU (csrc/threshold_opt.cu, exact integer distance transforms) and the reference's selection
-        rules are applied to them.  D2 metrics (normals) fall back to the reference's own kd-tree module when it is
-        importable."""
+        rules are applied to them.  D2 metrics (point-to-plane, normals) run the same search on the host with kd-trees."""
         from . import model_opt as MO
         if not any(str(m).startswith('d2') for m in opt_metrics):
             t32 = threshold_f32(self.thresholds, np.arange(len(self.thresholds)))
@@ -516,17 +514,14 @@ class CompressionModel:
                                                                 opt_metrics=opt_metrics, max_deltas=max_deltas)
                 idx.append(best)
             return np.concatenate(idx), list(ret)
-        try:
-            from model_opt import compute_optimal_thresholds  # the reference's src/ on sys.path
-        except ImportError as e:
-            raise NotImplementedError('the D2 (point-to-plane) threshold metrics need the reference host module model_opt.py '
-                                      'on sys.path; the D1 metrics run on the GPU') from e
+        # D2 (point-to-plane) metrics: host kd-tree search with the reference's normal transfer, block by block
         xh = torch.clamp(x_hat[:, 0], 0.0, 1.0).cpu().numpy()
         idx, ret = [], None
         for j, block in enumerate(blocks):
+            block = np.asarray(block)
             normals = block[:, block.shape[1] - 3:] if with_normals else None
-            ret, best = compute_optimal_thresholds(block, xh[j], self.thresholds, resolution, normals=normals,
-                                                   opt_metrics=opt_metrics, max_deltas=max_deltas, fixed_threshold=False)
+            ret, best = MO.compute_optimal_thresholds(block, xh[j], self.thresholds, resolution, normals=normals,
+                                                      opt_metrics=opt_metrics, max_deltas=max_deltas, fixed_threshold=False)
             idx.append(best)
         return np.asarray(idx, np.int64), list(ret)
 

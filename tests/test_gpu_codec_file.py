@@ -67,3 +67,27 @@ def test_codec_functions_and_ply_files(tmp_path):
     dst = tmp_path / 'out.ply'
     pc_io.write_pc(str(dst), out)
     assert np.array_equal(pc_io.load_pc(str(dst)), out)
+
+
+def test_compress_blocks_with_normals_and_d2_metrics():
+    """with_normals=True, one D1 and one D2 opt_metric (compress_octree.py --input_normals ... --opt_metrics d1_mse d2_mse): two
+    metric groups -> two data lists, each decodable to the encoder's own reconstruction."""
+    res, level, bs = 64, 1, 32
+    rng = np.random.default_rng(6)
+    u = rng.random((6000, 2))
+    pts = np.unique(np.stack([u[:, 0] * (res - 1), (0.5 + 0.3 * np.sin(u[:, 0] * 5)) * (res - 1), u[:, 1] * (res - 1)], 1).astype(np.int64), axis=0)
+    nrm = rng.normal(size=(len(pts), 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    cloud = np.concatenate([pts.astype(np.float64), nrm], axis=1)
+    blocks, binstr = OC.partition_octree(cloud, [0, 0, 0], [res] * 3, level)
+    m = ModelConfigType['c3p'].build(batch_size=4)
+    m.set_weights(synthetic.trained_like_weights(m, seed=3, output_bias=-0.45))
+    m.compress((1, 1, bs, bs, bs))
+    data_list, metadata, _ = m.compress_blocks(None, blocks, binstr, cloud, res, level, with_normals=True,
+                                               opt_metrics=('d1_mse', 'd2_mse'), max_deltas=(np.inf,), fixed_threshold=False)
+    assert len(data_list) == 2 and [md['idx'] for md in metadata] == [0, 1]
+    assert 'd2_psnr' in metadata[1]['metrics'] and np.isfinite(metadata[1]['metrics']['d2_psnr'])
+    m.decompress()
+    for dl, md in zip(data_list, metadata):
+        dec, _ = m.decompress_blocks(None, dl, (bs, bs, bs))
+        assert all(np.array_equal(a, b) for a, b in zip(md['x_hat_list'], dec))

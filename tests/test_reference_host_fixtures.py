@@ -112,3 +112,21 @@ def test_ply_reader_and_writer(tmp_path):
     assert np.array_equal(pc_io.load_pc(header % len(b0) + b0.tobytes()) if False else pc_io.read_ply(header % len(b0) + b0.tobytes())['x'], b0[:, 0])
     p_min, p_max, shape = pc_io.get_shape_data(64, 'channels_first')
     assert list(shape) == [1, 64, 64, 64] and list(pc_io.get_shape_data(64, 'channels_last')[2]) == [64, 64, 64, 1]
+
+
+def test_d2_metrics_and_threshold_search_equal_the_reference():
+    """pc_metric.compute_metrics incl. the D2 branch / assign_attr, and model_opt.compute_optimal_thresholds with normals,
+    against the reference's own pc_metric.py (numba assign_attr) and model_opt.py (tests/golden/make_reference_d2_fixture.py)."""
+    from pcc_geo_cnn_v2_b200 import model_opt as MO
+    from pcc_geo_cnn_v2_b200 import pc_metric as PM
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_d2.npz'))
+    size, thr = int(g['size']), g['thresholds']
+    opt_metrics, max_deltas = [str(m) for m in g['opt_metrics']], [float(d) for d in g['max_deltas']]
+    for j in range(int(g['n_blocks'])):
+        block, x_hat = g[f'block{j}'], g[f'x_hat{j}']
+        names, best = MO.compute_optimal_thresholds(block, x_hat, thr, size, normals=block[:, 3:], opt_metrics=opt_metrics,
+                                                    max_deltas=max_deltas)
+        assert names == [str(n) for n in g['names']] and list(best) == list(g[f'best{j}'])
+        m = PM.compute_metrics(block[:, :3], np.argwhere(x_hat > thr[20]).astype('float32'), size - 1, p1_n=block[:, 3:])
+        got = np.array([m[str(k)] for k in g['metric_keys']], np.float64)
+        assert np.allclose(got, g[f'metrics{j}'], rtol=1e-9, atol=0), (got, g[f'metrics{j}'])
