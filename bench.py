@@ -332,9 +332,13 @@ def main():
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_value = world * B * EB * esteps / float(et[0])
     nsym = B * EB * 64 * (8 ** 3 + 4 ** 3)
-    h2d = coords_host.nbytes * EB + nsym * 4 + B * EB * 4 * 2         # coords (enc) + symbols (dec) + thresholds
-    d2h = nsym * 4 + B * EB * 64 * 8 ** 3 * 4 * 2 + 2 * B * EB * SIZE ** 3 // 8   # symbols + indexes (enc+dec) + packed occupancy (enc+dec)
     str_bytes = sum(len(s) for blk, _ in data_list[0] for s in blk) / EB
+    if m.device_coder:   # strings instead of symbols cross PCIe (+ per-stream lengths / offsets)
+        h2d = coords_host.nbytes * EB + int(str_bytes * EB) + B * EB * (2 * 8 + 4 * 2)   # coords + strings, offsets, thresholds
+        d2h = int(str_bytes * EB) + B * EB * 2 * 12 + 2 * B * EB * SIZE ** 3 // 8           # strings, lengths/offsets + packed occupancy
+    else:
+        h2d = coords_host.nbytes * EB + nsym * 4 + B * EB * 4 * 2         # coords (enc) + symbols (dec) + thresholds
+        d2h = nsym * 4 + B * EB * 64 * 8 ** 3 * 4 * 2 + 2 * B * EB * SIZE ** 3 // 8   # symbols + indexes (enc+dec) + packed occupancy (enc+dec)
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -348,7 +352,8 @@ def main():
             'tensor_frac_whole_step': value / world * (GFLOP_ENCODE + GFLOP_DECODE) / 1e3 / peak_tf,
             'roofline': roofline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': esteps, 'blocks_per_step_per_gpu': B * EB, 'bitstream_bytes_per_block': str_bytes / B},
+                    'steps': esteps, 'blocks_per_step_per_gpu': B * EB, 'bitstream_bytes_per_block': str_bytes / B,
+                    'entropy_coder': 'device (rc_device.cu)' if m.device_coder else f'host ({m.coder_threads} threads x {m.pipeline_depth} workers)'},
             'gpu_launches': int(launches), 'clocks': cs.summary(), 'clocks_e2e': cs_e2e.summary()}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, cores = cpu_encode_decode(args.cpu_blocks)

@@ -206,6 +206,33 @@ int pccgeo_range_decode_host(const uint8_t* bytes, const long long* byte_offsets
                              const long long* sym_offsets, int nstreams, const int32_t* cdf, int cdf_stride,
                              const int32_t* cdf_length, const int32_t* offset, int rows, int index_mode,
                              long long channel_stride, int32_t* symbols_out, int threads);
+/* ---- range coder (DEVICE) -------------------------------------------------------------------------
+ * The same coder as above, byte for byte, run on the GPU with one warp per stream so that the block loops of
+ * compress_blocks / decompress_blocks (src/model_types.py:184-238) need no host entropy coding.  All pointers are DEVICE
+ * memory; every stream has per_stream symbols (the codec's streams are the latents of equal-sized blocks).  Tables as
+ * above, uploaded by the caller; `err` (device int, caller-zeroed) is set to 1 on an out-of-range table index or a
+ * corrupt escape code.
+ *   encode: ws of pccgeo_rc_encode_ws_bytes(); streams are packed back to back into `packed` (bytes beyond
+ *           packed_capacity are dropped: compare offsets[nstreams] with the capacity), lengths (nstreams) and offsets
+ *           (nstreams+1) receive the byte ranges; lengths[i] == -1 if stream i outgrew 4 bytes per symbol.
+ *   decode: byte_offsets (nstreams+1) into `bytes`; lut from pccgeo_range_lut_host (rows x 256 uint16), uploaded. */
+size_t pccgeo_rc_encode_ws_bytes(int nstreams, long long per_stream);
+int pccgeo_range_encode_device(const int32_t* symbols, const int32_t* indexes, int nstreams, long long per_stream,
+                               const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, const int32_t* offset,
+                               int rows, int index_mode, long long channel_stride, void* ws, uint8_t* packed,
+                               long long packed_capacity, int32_t* lengths, long long* offsets, int* err, void* stream);
+int pccgeo_range_decode_device(const uint8_t* bytes, const long long* byte_offsets, const int32_t* indexes, int nstreams,
+                               long long per_stream, const int32_t* cdf, int cdf_stride, const int32_t* cdf_length,
+                               const int32_t* offset, const uint16_t* lut, int rows, int index_mode,
+                               long long channel_stride, int32_t* symbols_out, int* err, void* stream);
+/* HOST: the decoder's per-row search accelerators: lut[r][b] = largest s < cdf_length[r]-1 with cdf[r][s] <= b << 8. */
+int pccgeo_range_lut_host(const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, int rows, uint16_t* lut);
+/* HOST test hook: the device encoder's arithmetic (the same inline functions the kernels call) run sequentially over
+ * HOST arrays, so that the CPU test-suite can pin it against pccgeo_range_encode_host without a GPU. */
+int pccgeo_range_encode_emulate_host(const int32_t* symbols, const int32_t* indexes, int nstreams, long long per_stream,
+                                     const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, const int32_t* offset,
+                                     int rows, int index_mode, long long channel_stride, uint8_t* packed,
+                                     long long packed_capacity, int32_t* lengths, long long* offsets);
 /* HOST: packed occupancy words from pccgeo_threshold_pack (copied to the host) -> float32 (z,y,x) rows in np.argwhere
  * order, the host half of the reference's `np.argwhere(x_hat > t).astype(float32)` (src/model_types.py:209,234).
  * offsets (n_blocks+1) receives the prefix sum of per-block point counts; pass points == NULL to query sizes only. */

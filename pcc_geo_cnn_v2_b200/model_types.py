@@ -18,7 +18,8 @@ import numpy as np
 import torch
 
 from . import ops
-from .entropy_models import EntropyBottleneck, GaussianConditional, make_scale_table
+from .entropy_models import EntropyBottleneck, GaussianConditional, make_scale_table, gaussian_tables
+from ._lib import PccGeoError
 from .focal_loss import focal_loss
 from . import model_transforms as _mt
 from .model_transforms import TransformType
@@ -288,6 +289,16 @@ class CompressionModel:
         self.x = self.x_hat = self.strings = self.debug_tensors = None
         self.x_shape = None
         self.use_graphs = True   # capture the per-batch kernel sequences of the block loops into CUDA graphs
+        # entropy-code on the GPU (csrc/rc_device.cu: one warp per stream, all streams of up to `coder_group_blocks` blocks in
+        # one launch) instead of in the host workers; byte-identical strings.  Used by the CUDA-graph block loops.
+        # Default: on when this rank has few host cores (several GPUs per host: measured cross-over on the 16-core B200 host,
+        # DESIGN.md section 8), PCCGEO_DEVICE_CODER=0/1 overrides.  A group's coding costs a fixed few milliseconds (the length
+        # of one stream's serial chain), so groups are large; `coder_overlap` moves it to a side stream under the next
+        # group's transforms (off: its one-warp CTAs displace the persistent conv CTAs and cost more than they hide).
+        env = os.environ.get('PCCGEO_DEVICE_CODER', '')
+        self.device_coder = env == '1' if env in ('0', '1') else cores <= 8
+        self.coder_group_blocks = 1024
+        self.coder_overlap = False
         self._graphs, self._statics, self._graph_epoch = {}, {}, -1
 
     # -- weights -------------------------------------------------------------------------------------
@@ -446,6 +457,8 @@ class CompressionModel:
 
         post_f, xs = [], []
         graphs = self.use_graphs and thr_idx is not None and not keep_x_hat
+        if graphs and self.device_coder:
+            return self._encode_blocks_device_coder(spans, coords_f, dims, thr_idx)
         for (a, b), cf in zip(spans, coords_f):
             if len(post_f) >= self.pipeline_depth + 4:  # bound the driver's run-ahead (staging memory in flight)
                 post_f[len(post_f) - self.pipeline_depth - 4].result()
@@ -545,6 +558,8 @@ class CompressionModel:
         # i-lag, and the first-latent decodes are submitted only two batches ahead, so that the host work the GPU is waiting
         # for (batch 0's second latent) is at the front of the workers' queue instead of behind every batch's stage 0.
         graphs = self.use_graphs and not debug
+        if graphs and self.device_coder:
+            return self._decompress_blocks_device_coder(chunks, dims)
         nb, lag, ahead = len(chunks), 2, 2
         f0 = {i: pool.submit(self._decode_host0, strings[i], dims) for i in range(min(ahead, nb))}
         ctxs, f2, f4, dbgs = {}, {}, [], []
@@ -568,6 +583,191 @@ class CompressionModel:
                 dbgs.append([dbg if debug else None] * len(chunk))
         pts = [f.result() for f in f4]
         return [p for r in pts for p in r], [d for r in dbgs for d in r]
+
+    # -- block loops with the entropy coder on the GPU ----------------------------------------------------
+    # A stream is serial, so the device coder's parallelism is the number of streams: the loops below collect the symbols
+    # of a whole group of batches (<= coder_group_blocks blocks) in HBM and code all of the group's streams with one launch
+    # per latent -- a few milliseconds per group, however many blocks it holds -- instead of handing every batch's symbols
+    # to the host workers.  _coder_latents() (V1/V2) describes the latents in the order of the strings tuple.
+    def _coder_latents(self, dims):
+        """[{'sym': latent-dict key, 'idx': key or None, 'shape': per-block shape, 'tables': host tables, 'st': static key}]"""
+        raise NotImplementedError
+
+    def _groups(self, spans):
+        per = max(1, self.coder_group_blocks // self.batch_size)
+        return [spans[i:i + per] for i in range(0, len(spans), per)]
+
+    def _coder_stream(self):
+        """The stream of the device coder: the current one, or with coder_overlap a side stream (one per model and device)."""
+        if not self.coder_overlap:
+            return torch.cuda.current_stream()
+        key = ('coder_stream', torch.cuda.current_device())
+        if key not in self.__dict__:
+            self.__dict__[key] = torch.cuda.Stream()
+        return self.__dict__[key]
+
+    def _encode_blocks_device_coder(self, spans, coords_f, dims, thr_idx):
+        pool = self._pool()
+        lats = self._coder_latents(dims)
+        cf_of = dict(zip(spans, coords_f))
+        main, side = torch.cuda.current_stream(), self._coder_stream()
+        str_f, pts_f = [], []
+        for group in self._groups(spans):
+            g0, g1 = group[0][0], group[-1][1]
+            big = {}
+            for l in lats:
+                for k in (l['sym'], l['idx']):
+                    if k is not None and k not in big:
+                        big[k] = torch.empty((g1 - g0,) + tuple(l['shape']), dtype=torch.int32, device='cuda')
+                        big[k].record_stream(side)
+            for a, b in group:
+                lat, st = self.device_encode(self._h2d(cf_of[(a, b)].result()), b - a, dims, None)
+                for k, t in big.items():
+                    t[a - g0:b - g0].copy_(lat[k].view(t[a - g0:b - g0].shape))
+                pend = self._d2h(self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b])))
+                pts_f.append(pool.submit(self._points_task, pend, dims))
+            # the group's streams are coded on the side stream, under the next group's transforms
+            side.wait_stream(main)
+            coded = []
+            with torch.cuda.stream(side):
+                for l in lats:
+                    per = int(np.prod(l['shape']))
+                    idx = big[l['idx']] if l['idx'] is not None else None
+                    packed, lengths, offsets, err = ops.range_encode_device(big[l['sym']], ops.device_tables(l['tables']), indexes=idx,
+                                                                            channel_stride=per // l['shape'][0])
+                    coded.append((packed, self._d2h(lengths, offsets, err)))
+            str_f.append(pool.submit(self._strings_task, coded, big, lats, g1 - g0))
+        strings = [t for f in str_f for t in f.result()]
+        pts = [q for f in pts_f for q in f.result()]
+        return strings, None, pts
+
+    def _strings_task(self, coded, big, lats, n):
+        """Host worker: byte ranges of a coded group -> per-block tuples of bytes.  The (rare) stream that outgrew the device
+        buffer sends its latent through the host coder (same bytes)."""
+        per_latent = []
+        side = self._worker_stream()
+        for (packed, pend), l in zip(coded, lats):
+            lengths, offsets, err = self._wait(pend)
+            lengths, offsets, bad = lengths.copy(), offsets.copy(), bool(err[0])
+            self._release(pend)
+            if bad:
+                raise PccGeoError('range_encode_device: table index out of range')
+            total = int(offsets[-1])
+            if (lengths < 0).any() or total > packed.numel():
+                sym = big[l['sym']].cpu().numpy()
+                offs = np.arange(n + 1, dtype=np.int64) * int(np.prod(l['shape']))
+                if l['idx'] is not None:
+                    per_latent.append(ops.range_encode(sym.reshape(-1), offs, l['tables'], indexes=big[l['idx']].cpu().numpy().reshape(-1),
+                                                       threads=self.coder_threads))
+                else:
+                    per_latent.append(ops.range_encode(sym.reshape(-1), offs, l['tables'],
+                                                       channel_stride=int(np.prod(l['shape'][1:])), threads=self.coder_threads))
+                continue
+            buf = _pinned.get(max(total, 1))
+            with torch.cuda.stream(side):   # the exact byte count is only known now: second, tight copy from this worker
+                buf[:total].copy_(packed[:total], non_blocking=True)
+            side.synchronize()
+            blob = buf[:total].numpy().tobytes()
+            _pinned.put(buf)
+            per_latent.append([blob[offsets[i]:offsets[i + 1]] for i in range(n)])
+        return list(zip(*per_latent))
+
+    def _worker_stream(self):
+        import threading
+        tl = self.__dict__.setdefault('_tls', threading.local())
+        if getattr(tl, 'stream', None) is None:
+            tl.stream = torch.cuda.Stream()
+        return tl.stream
+
+    def _upload_strings(self, strings):
+        """[bytes] -> (uint8 CUDA blob, int64 CUDA offsets (n+1)); the strings are gathered straight into pinned memory."""
+        offs = np.zeros(len(strings) + 1, np.int64)
+        offs[1:] = np.cumsum([len(t) for t in strings])
+        total = int(offs[-1])
+        buf = _pinned.get(total + 1)   # + one pad byte: never an empty device buffer
+        view = buf[:total + 1].numpy()
+        for t, o in zip(strings, offs):
+            if t:
+                view[o:o + len(t)] = np.frombuffer(t, np.uint8)
+        view[total] = 0
+        blob = torch.empty(total + 1, dtype=torch.uint8, device='cuda')
+        blob.copy_(buf[:total + 1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _pinned.put_after(buf, ev)
+        return blob, self._h2d(offs)
+
+    def _decompress_blocks_device_coder(self, chunks, dims):
+        pool = self._pool()
+        lats = self._coder_latents(dims)
+        main, side = torch.cuda.current_stream(), self._coder_stream()
+        spans, a = [], 0
+        for c in chunks:
+            spans.append((a, a + len(c)))
+            a += len(c)
+        flat = [c for chunk in chunks for c in chunk]
+        f4, errs = [], []
+
+        def decode_group(group):
+            """Side stream: strings -> symbols of every latent, in decoding order (the last latent of the strings tuple -- the
+            hyperprior, whose tables are fixed -- first, then what its values parameterise); main stream, in between: the
+            group's hyper-synthesis batches.  -> (symbols of the first latent, event after which they are complete)"""
+            g0, g1 = group[0][0], group[-1][1]
+            n = g1 - g0
+            sym, idx_big = {}, None
+            for li in reversed(range(len(lats))):
+                l = lats[li]
+                per = int(np.prod(l['shape']))
+                with torch.cuda.stream(side):
+                    blob, offs = self._upload_strings([flat[g0 + i][0][li] for i in range(n)])
+                if l['idx'] is not None:   # decoded hyper-latent -> scale indexes of the whole group, batch by batch
+                    main.wait_stream(side)
+                    idx_big = torch.empty((n,) + tuple(l['shape']), dtype=torch.int32, device='cuda')
+                    idx_big.record_stream(side)
+                    for a, b in group:
+                        st = self._static(b - a, dims)
+                        st['sym0'].copy_(sym[lats[li + 1]['sym']][a - g0:b - g0].view(st['sym0'].shape))
+                        ctx = self._stage('dec1', b - a, dims, lambda: self._dec1_compute(st['sym0']))
+                        idx_big[a - g0:b - g0].copy_(ctx['indexes'].view(idx_big[a - g0:b - g0].shape))
+                    side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+                    errs.append(err)
+                    out, _ = ops.range_decode_device(blob, offs, n, per, ops.device_tables(l['tables']),
+                                                     indexes=idx_big if l['idx'] is not None else None,
+                                                     channel_stride=per // l['shape'][0], err=err)
+                    out.record_stream(main)
+                    sym[l['sym']] = out
+            ev = torch.cuda.Event()
+            ev.record(side)
+            return sym[lats[0]['sym']], ev
+
+        def synthesize_group(group, ysym, ev):
+            g0 = group[0][0]
+            main.wait_event(ev)
+            for a, b in group:
+                st = self._static(b - a, dims)
+                st['sym1'].copy_(ysym[a - g0:b - g0].view(st['sym1'].shape))
+                thr = threshold_f32(self.thresholds, np.asarray([int(c[1]) for c in flat[a:b]], np.int64))
+                self._copy_in(st['thr'], thr)
+                bits = self._stage('dec2', b - a, dims, lambda: self._dec2_compute(None, st))
+                f4.append(pool.submit(self._points_task, self._d2h(bits), dims))
+
+        # software pipeline with a lag of one group: the side stream decodes group g+1 under the synthesis of group g
+        prev = None
+        for group in self._groups(spans):
+            cur = (group,) + decode_group(group)
+            if prev is not None:
+                synthesize_group(*prev)
+            prev = cur
+        if prev is not None:
+            synthesize_group(*prev)
+        main.wait_stream(side)
+        bad = torch.stack(errs).sum().item() if errs else 0   # one sync, after everything is enqueued
+        pts = [f.result() for f in f4]
+        if bad:
+            raise PccGeoError('range_decode_device: corrupt stream')
+        return [p for r in pts for p in r], [None] * len(flat)
 
     def _points_task(self, pend, dims):
         pts = ops.bits_to_points(self._wait(pend)[0], dims, self.coder_threads)
@@ -682,6 +882,10 @@ class CompressionModelV1(CompressionModel):
     def _latent_tensors(dev):
         return (dev['y_sym'],)
 
+    def _coder_latents(self, dims):
+        return [{'sym': 'y_sym', 'idx': None, 'shape': (self.num_filters,) + tuple(d // 8 for d in dims),
+                 'tables': self.entropy_bottleneck.tables}]
+
     def _encode_host(self, dev, host=None):
         y_sym = host[0] if host is not None else dev['y_sym'].cpu().numpy()
         ys = self.entropy_bottleneck.encode_symbols(y_sym, self.coder_threads)
@@ -786,6 +990,12 @@ class CompressionModelV2(CompressionModel):
     @staticmethod
     def _latent_tensors(dev):
         return (dev['z_sym'], dev['y_sym'], dev['indexes'])
+
+    def _coder_latents(self, dims):
+        f = self.num_filters
+        return [{'sym': 'y_sym', 'idx': 'indexes', 'shape': (f,) + tuple(d // 8 for d in dims),
+                 'tables': gaussian_tables(self.scale_table)},
+                {'sym': 'z_sym', 'idx': None, 'shape': (f,) + tuple(d // 16 for d in dims), 'tables': self.entropy_bottleneck.tables}]
 
     def _encode_host(self, dev, host=None):
         z_sym, y_sym, idx = host if host is not None else [t.cpu().numpy() for t in self._latent_tensors(dev)]

@@ -392,6 +392,92 @@ def range_decode(strings, sym_offsets, tables, indexes=None, channel_stride=0, t
     return out
 
 
+# ---- device range coder ----------------------------------------------------------------------------------
+_dev_tables = {}
+
+
+def device_tables(tables):
+    """{'cdf','cdf_length','offset'} host tables -> the same + 'lut' as CUDA tensors, uploaded once per table set and device
+    (keyed by the identity of the host cdf array: entropy models build a new dict when their tables change)."""
+    key = (id(tables['cdf']), torch.cuda.current_device())
+    hit = _dev_tables.get(key)
+    if hit is not None and hit[0] is tables['cdf']:
+        return hit[1]
+    cdf = np.ascontiguousarray(tables['cdf'], np.int32)
+    cl = np.ascontiguousarray(tables['cdf_length'], np.int32)
+    of = np.ascontiguousarray(tables['offset'], np.int32)
+    lut = np.zeros((cdf.shape[0], 256), np.uint16)
+    L.check(L.lib().pccgeo_range_lut_host(L.ptr(cdf), cdf.shape[1], L.ptr(cl), cdf.shape[0], L.ptr(lut)), 'range_lut')
+    dev = {'cdf': torch.from_numpy(cdf).cuda(), 'cdf_length': torch.from_numpy(cl).cuda(), 'offset': torch.from_numpy(of).cuda(),
+           'lut': torch.from_numpy(lut.view(np.int16)).cuda(), 'rows': cdf.shape[0], 'stride': cdf.shape[1]}
+    if len(_dev_tables) > 64:
+        _dev_tables.clear()
+    _dev_tables[key] = (tables['cdf'], dev)
+    return dev
+
+
+def range_encode_device(symbols, dtab, indexes=None, channel_stride=0, packed_capacity=None):
+    """symbols int32 CUDA (nstreams, ...) -> (packed uint8, lengths int32 (nstreams), offsets int64 (nstreams+1), err int32 (1))
+    on the device, the bytes of pccgeo_range_encode_host.  Async on the current stream."""
+    L.require_cuda()
+    assert symbols.is_cuda and symbols.dtype == torch.int32 and symbols.is_contiguous()
+    ns = symbols.shape[0]
+    per = symbols.numel() // ns
+    mode = 0 if indexes is not None else 1
+    if indexes is not None:
+        assert indexes.is_cuda and indexes.dtype == torch.int32 and indexes.is_contiguous() and indexes.numel() == symbols.numel()
+    cap = int(packed_capacity) if packed_capacity else ns * (per * 4 + 64)
+    ws = torch.empty(int(L.lib().pccgeo_rc_encode_ws_bytes(ns, per)), dtype=torch.uint8, device='cuda')
+    packed = torch.empty(cap, dtype=torch.uint8, device='cuda')
+    lengths = torch.empty(ns, dtype=torch.int32, device='cuda')
+    offsets = torch.empty(ns + 1, dtype=torch.int64, device='cuda')
+    err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    L.check(L.lib().pccgeo_range_encode_device(L.ptr(symbols), L.ptr(indexes), ns, per, L.ptr(dtab['cdf']), dtab['stride'],
+                                               L.ptr(dtab['cdf_length']), L.ptr(dtab['offset']), dtab['rows'], mode,
+                                               int(channel_stride), L.ptr(ws), L.ptr(packed), cap, L.ptr(lengths), L.ptr(offsets),
+                                               L.ptr(err), L.stream_ptr()), 'range_encode_device')
+    return packed, lengths, offsets, err
+
+
+def range_decode_device(bytes_dev, byte_offsets, nstreams, per_stream, dtab, indexes=None, channel_stride=0, out=None, err=None):
+    """bytes_dev uint8 CUDA, byte_offsets int64 CUDA (nstreams+1) -> (symbols int32 CUDA (nstreams, per_stream), err)."""
+    L.require_cuda()
+    assert bytes_dev.is_cuda and bytes_dev.dtype == torch.uint8 and byte_offsets.is_cuda and byte_offsets.dtype == torch.int64
+    mode = 0 if indexes is not None else 1
+    if indexes is not None:
+        assert indexes.is_cuda and indexes.dtype == torch.int32 and indexes.is_contiguous() and indexes.numel() == nstreams * per_stream
+    if out is None:
+        out = torch.empty((nstreams, per_stream), dtype=torch.int32, device='cuda')
+    if err is None:
+        err = torch.zeros(1, dtype=torch.int32, device='cuda')
+    L.check(L.lib().pccgeo_range_decode_device(L.ptr(bytes_dev), L.ptr(byte_offsets), L.ptr(indexes), nstreams, per_stream,
+                                               L.ptr(dtab['cdf']), dtab['stride'], L.ptr(dtab['cdf_length']), L.ptr(dtab['offset']),
+                                               L.ptr(dtab['lut']), dtab['rows'], mode, int(channel_stride), L.ptr(out), L.ptr(err),
+                                               L.stream_ptr()), 'range_decode_device')
+    return out, err
+
+
+def range_encode_emulate(symbols, nstreams, tables, indexes=None, channel_stride=0):
+    """Test hook: the device encoder's arithmetic run on the host (see include/pccgeo.h) -> list of bytes."""
+    symbols = np.ascontiguousarray(symbols, np.int32)
+    per = symbols.size // nstreams
+    cdf = np.ascontiguousarray(tables['cdf'], np.int32)
+    cl = np.ascontiguousarray(tables['cdf_length'], np.int32)
+    of = np.ascontiguousarray(tables['offset'], np.int32)
+    mode = 0 if indexes is not None else 1
+    if indexes is not None:
+        indexes = np.ascontiguousarray(indexes, np.int32)
+    cap = symbols.size * 4 + 64 * nstreams
+    packed = np.zeros(cap, np.uint8)
+    lengths = np.zeros(nstreams, np.int32)
+    offs = np.zeros(nstreams + 1, np.int64)
+    L.check(L.lib().pccgeo_range_encode_emulate_host(L.ptr(symbols), L.ptr(indexes), nstreams, per, L.ptr(cdf), cdf.shape[1], L.ptr(cl),
+                                                     L.ptr(of), cdf.shape[0], mode, int(channel_stride), L.ptr(packed), cap,
+                                                     L.ptr(lengths), L.ptr(offs)), 'range_encode_emulate')
+    buf = packed.tobytes()
+    return [buf[offs[i]:offs[i] + max(int(lengths[i]), 0)] for i in range(nstreams)]
+
+
 def bits_to_points(bits_host, dims, threads=0):
     """bits_host: numpy int32/uint32 (n, d*h*w/32) packed occupancy -> list of float32 (m_i, 3) arrays, argwhere order."""
     import os

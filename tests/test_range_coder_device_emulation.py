@@ -1,0 +1,36 @@
+"""The device range ENCODER's arithmetic (csrc/rc_device.cu: rc_map_symbol / rc_enc_symbol / rc_enc_finish, the inline functions
+the kernels call) run on the host through pccgeo_range_encode_emulate_host, pinned against the production host coder
+(range_coder.cpp) byte for byte.  No GPU needed; the kernels themselves are covered by tests/test_gpu_range_coder_device.py."""
+import numpy as np
+import pytest
+
+from pcc_geo_cnn_v2_b200 import ops
+from pcc_geo_cnn_v2_b200.entropy_models import gaussian_tables, make_scale_table
+
+
+@pytest.mark.parametrize('ns,per,spread', [(4, 1000, 1.0), (3, 4097, 30.0), (2, 31, 3.0), (5, 1, 1.0), (2, 5000, 2000.0)])
+def test_emulated_device_encoder_matches_host_coder(ns, per, spread):
+    t = gaussian_tables(make_scale_table())
+    rng = np.random.default_rng(ns * 1000 + per)
+    idx = rng.integers(0, 64, (ns, per)).astype(np.int32)
+    sym = np.round(rng.standard_normal((ns, per)) * make_scale_table()[idx] * spread).astype(np.int32)  # spread > 1: escapes
+    offs = np.arange(ns + 1, dtype=np.int64) * per
+    assert ops.range_encode_emulate(sym, ns, t, indexes=idx) == ops.range_encode(sym.reshape(-1), offs, t, indexes=idx.reshape(-1), threads=2)
+
+
+def test_emulated_device_encoder_per_channel_tables_and_zero_streams():
+    t = gaussian_tables(make_scale_table())
+    rows = 8
+    tt = {k: v[:rows] for k, v in t.items()}
+    rng = np.random.default_rng(5)
+    sym = rng.integers(-6, 7, (3, rows * 16)).astype(np.int32)
+    offs = np.arange(4, dtype=np.int64) * rows * 16
+    assert ops.range_encode_emulate(sym, 3, tt, channel_stride=16) == ops.range_encode(sym.reshape(-1), offs, tt, channel_stride=16, threads=1)
+    z = np.zeros((2, 100), np.int32)
+    assert ops.range_encode_emulate(z, 2, t, indexes=z) == ops.range_encode(z.reshape(-1), np.array([0, 100, 200]), t, indexes=z.reshape(-1))
+
+
+def test_emulated_device_encoder_rejects_bad_table_index():
+    t = gaussian_tables(make_scale_table())
+    with pytest.raises(Exception):
+        ops.range_encode_emulate(np.zeros((1, 4), np.int32), 1, t, indexes=np.full((1, 4), 64, np.int32))
