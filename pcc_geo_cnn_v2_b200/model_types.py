@@ -667,9 +667,10 @@ class CompressionModel:
             with torch.cuda.stream(side):   # the exact byte count is only known now: second, tight copy from this worker
                 buf[:total].copy_(packed[:total], non_blocking=True)
             side.synchronize()
-            blob = buf[:total].numpy().tobytes()
+            view = memoryview(buf.numpy())
+            offs = offsets.tolist()
+            per_latent.append([bytes(view[offs[i]:offs[i + 1]]) for i in range(n)])
             _pinned.put(buf)
-            per_latent.append([blob[offsets[i]:offsets[i + 1]] for i in range(n)])
         return list(zip(*per_latent))
 
     def _worker_stream(self):

@@ -38,6 +38,9 @@ from pcc_geo_cnn_v2_b200 import ops  # noqa: E402
 for n in ('range_encode_device', 'range_decode_device', 'bits_to_points'):
     wrap(ops, n)
 wrap(model_types, 'blocks_to_coords')
+wrap(model_types._pinned, 'get')
+wrap(m, '_worker_stream')
+wrap(model_types._pinned, 'put')
 print('device_coder', m.device_coder)
 uniq = synthetic.surface_blocks(8, size=64, seed=100)
 blocks = [uniq[i % 8] for i in range(B * NB)]
