@@ -291,12 +291,12 @@ class CompressionModel:
         self.use_graphs = True   # capture the per-batch kernel sequences of the block loops into CUDA graphs
         # entropy-code on the GPU (csrc/rc_device.cu: one warp per stream, all streams of up to `coder_group_blocks` blocks in
         # one launch) instead of in the host workers; byte-identical strings.  Used by the CUDA-graph block loops.
-        # Default: on when this rank has few host cores (several GPUs per host: measured cross-over on the 16-core B200 host,
-        # DESIGN.md section 8), PCCGEO_DEVICE_CODER=0/1 overrides.  A group's coding costs a fixed few milliseconds (the length
+        # Default: on when this rank has fewer than 16 host cores (several GPUs per host; measured cross-over, DESIGN.md
+        # section 8), PCCGEO_DEVICE_CODER=0/1 overrides.  A group's coding costs a fixed few milliseconds (the length
         # of one stream's serial chain), so groups are large; `coder_overlap` moves it to a side stream under the next
         # group's transforms (off: its one-warp CTAs displace the persistent conv CTAs and cost more than they hide).
         env = os.environ.get('PCCGEO_DEVICE_CODER', '')
-        self.device_coder = env == '1' if env in ('0', '1') else cores <= 8
+        self.device_coder = env == '1' if env in ('0', '1') else cores < 16
         self.coder_group_blocks = 1024
         self.coder_overlap = False
         self._graphs, self._statics, self._graph_epoch = {}, {}, -1
