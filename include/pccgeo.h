@@ -215,24 +215,29 @@ int pccgeo_range_decode_host(const uint8_t* bytes, const long long* byte_offsets
  *   encode: ws of pccgeo_rc_encode_ws_bytes(); streams are packed back to back into `packed` (bytes beyond
  *           packed_capacity are dropped: compare offsets[nstreams] with the capacity), lengths (nstreams) and offsets
  *           (nstreams+1) receive the byte ranges; lengths[i] == -1 if stream i outgrew 4 bytes per symbol.
- *   decode: byte_offsets (nstreams+1) into `bytes`; lut from pccgeo_range_lut_host (rows x 256 uint16), uploaded. */
+ *   decode: byte_offsets (nstreams+1) into `bytes`; cdf16 / row_start from pccgeo_range_compact_tables_host, uploaded. */
 size_t pccgeo_rc_encode_ws_bytes(int nstreams, long long per_stream);
 int pccgeo_range_encode_device(const int32_t* symbols, const int32_t* indexes, int nstreams, long long per_stream,
                                const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, const int32_t* offset,
                                int rows, int index_mode, long long channel_stride, void* ws, uint8_t* packed,
                                long long packed_capacity, int32_t* lengths, long long* offsets, int* err, void* stream);
 int pccgeo_range_decode_device(const uint8_t* bytes, const long long* byte_offsets, const int32_t* indexes, int nstreams,
-                               long long per_stream, const int32_t* cdf, int cdf_stride, const int32_t* cdf_length,
-                               const int32_t* offset, const uint16_t* lut, int rows, int index_mode,
-                               long long channel_stride, int32_t* symbols_out, int* err, void* stream);
-/* HOST: the decoder's per-row search accelerators: lut[r][b] = largest s < cdf_length[r]-1 with cdf[r][s] <= b << 8. */
-int pccgeo_range_lut_host(const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, int rows, uint16_t* lut);
+                               long long per_stream, const uint16_t* cdf16, const int32_t* row_start, const int32_t* cdf_length,
+                               const int32_t* offset, int rows, int total_entries, int index_mode, long long channel_stride,
+                               int32_t* symbols_out, int* err, void* stream);
+/* HOST: the decoder's compact tables (it keeps them in shared memory): the rows' first cdf_length[r]-1 entries as 16 bits, back
+ * to back (a row's last entry, 2^16, is implied), row_start (rows) = the rows' positions.  Returns the number of entries, -1 if
+ * a row is not a 16-bit CDF; cdf16 == NULL queries the size. */
+long long pccgeo_range_compact_tables_host(const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, int rows,
+                                           uint16_t* cdf16, int32_t* row_start);
 /* HOST test hook: the device encoder's arithmetic (the same inline functions the kernels call) run sequentially over
  * HOST arrays, so that the CPU test-suite can pin it against pccgeo_range_encode_host without a GPU. */
 int pccgeo_range_encode_emulate_host(const int32_t* symbols, const int32_t* indexes, int nstreams, long long per_stream,
                                      const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, const int32_t* offset,
                                      int rows, int index_mode, long long channel_stride, uint8_t* packed,
                                      long long packed_capacity, int32_t* lengths, long long* offsets);
+/* HOST test hook: the device encoder's carry out of its 4-byte register into the n bytes already stored in buf. */
+unsigned pccgeo_rc_carry_probe_host(uint8_t* buf, int n);
 /* HOST: packed occupancy words from pccgeo_threshold_pack (copied to the host) -> float32 (z,y,x) rows in np.argwhere
  * order, the host half of the reference's `np.argwhere(x_hat > t).astype(float32)` (src/model_types.py:209,234).
  * offsets (n_blocks+1) receives the prefix sum of per-block point counts; pass points == NULL to query sizes only. */

@@ -55,8 +55,9 @@ SIGNATURES = {
     'pccgeo_pmf_to_quantized_cdf_host': (i32, [vp, i32, i32, vp]),
     'pccgeo_rc_encode_ws_bytes': (C.c_size_t, [i32, i64]),
     'pccgeo_range_encode_device': (i32, [vp, vp, i32, i64, vp, i32, vp, vp, i32, i32, i64, vp, vp, i64, vp, vp, vp, vp]),
-    'pccgeo_range_decode_device': (i32, [vp, vp, vp, i32, i64, vp, i32, vp, vp, vp, i32, i32, i64, vp, vp, vp]),
-    'pccgeo_range_lut_host': (i32, [vp, i32, vp, i32, vp]),
+    'pccgeo_range_decode_device': (i32, [vp, vp, vp, i32, i64, vp, vp, vp, vp, i32, i32, i32, i64, vp, vp, vp]),
+    'pccgeo_rc_carry_probe_host': (C.c_uint, [vp, i32]),
+    'pccgeo_range_compact_tables_host': (i64, [vp, i32, vp, i32, vp, vp]),
     'pccgeo_range_encode_emulate_host': (i32, [vp, vp, i32, i64, vp, i32, vp, vp, i32, i32, i64, vp, i64, vp, vp]),
     'pccgeo_threshold_opt_ws_bytes': (C.c_size_t, [i32, i32, i32, i32]),
     'pccgeo_threshold_hist': (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),

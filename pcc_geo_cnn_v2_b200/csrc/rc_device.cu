@@ -11,10 +11,9 @@
 //           touches a table; rc_encode_kernel's lanes fetch 32 mapped symbols at a time (coalesced) and broadcast them one
 //           by one; lane 0 emits the bytes.
 //   decode: the lanes prefetch the stream bytes (128 at a time, double buffered) and the next 32 table indexes, and the
-//           CDF search is lane-parallel: a 256-entry LUT gives the start, 32 lanes compare 32 consecutive CDF entries,
-//           ballot/popc gives the symbol -- one dependent table load instead of a binary search.
-// A warp needs < 64 registers and no shared memory, so these kernels co-reside with the persistent conv CTAs of the
-// transforms that run meanwhile on the other streams of the block loops.
+//           CDF search is lane-parallel and division-free (see rc_decode_kernel), on compact tables in shared memory.
+// The time of a launch is the length of ONE stream's chain (16 384 symbols: 1.4 ms encode, 3.9 ms decode) for any number of
+// streams up to the machine's warp slots, so the callers batch as many streams as they can into one launch.
 #include "common.cuh"
 
 namespace pccgeo {
@@ -25,44 +24,46 @@ constexpr uint32_t kRcMaxOverflow = (1u << kRcOverflowWidth) - 1;
 constexpr uint32_t kRcTop = 1u << 24;
 
 // ---------------------------------------------------------------- encoder core (host + device: the CPU tests run it too)
+// Same arithmetic as the host coder's low/cache/cache_size machine, arranged for a GPU thread: `low` is 32 bits, a carry out of
+// it is applied at once to the bytes already emitted -- the last four of them are still in a register (`tail`), so a carry
+// is one increment; only when all four are 0xFF does it walk back through memory -- and every renormalisation step is one
+// (delayed) byte store and two shifts, without the data-dependent flush loop of the cache/cache_size form.
 struct RcEnc {
-  unsigned long long low;
-  uint32_t range, cache, cache_size;
+  uint32_t low, range;
+  uint32_t tail;     // emitted bytes cnt-4 .. cnt-1, oldest in the top byte; not yet in memory
+  uint32_t cnt;      // bytes emitted so far, counting the always-zero first byte (emitted "before" the stream starts)
   uint8_t* out;      // stream buffer, null on the lanes that only follow the arithmetic
-  uint32_t pos;      // bytes emitted so far (including the always-zero first byte)
-  uint32_t last_nz;  // index after the last non-zero byte
   uint32_t cap;
 };
 
 __host__ __device__ __forceinline__ void rc_enc_init(RcEnc& s, uint8_t* out, uint32_t cap) {
-  s.low = 0; s.range = 0xFFFFFFFFu; s.cache = 0; s.cache_size = 1;
-  s.out = out; s.pos = 0; s.last_nz = 0; s.cap = cap;
+  s.low = 0; s.range = 0xFFFFFFFFu; s.tail = 0; s.cnt = 1;
+  s.out = out; s.cap = cap;
 }
-__host__ __device__ __forceinline__ void rc_enc_put(RcEnc& s, uint32_t byte) {
-  byte &= 0xffu;
-  if (s.out && s.pos < s.cap) s.out[s.pos] = (uint8_t)byte;
-  ++s.pos;
-  if (byte) s.last_nz = s.pos;
+__host__ __device__ __forceinline__ void rc_enc_emit(RcEnc& s, uint32_t byte) {
+  if (s.cnt >= 4 && s.out && s.cnt - 4 < s.cap) s.out[s.cnt - 4] = (uint8_t)(s.tail >> 24);
+  s.tail = (s.tail << 8) | (byte & 0xffu);
+  ++s.cnt;
 }
-__host__ __device__ __forceinline__ void rc_enc_shift_low(RcEnc& s) {
-  if ((uint32_t)s.low < 0xFF000000u || (s.low >> 32) != 0) {
-    const uint32_t carry = (uint32_t)(s.low >> 32);
-    uint32_t temp = s.cache;
-    do {
-      rc_enc_put(s, temp + carry);
-      temp = 0xFF;
-    } while (--s.cache_size != 0);
-    s.cache = (uint32_t)(s.low >> 24) & 0xffu;
+__host__ __device__ __forceinline__ void rc_enc_carry(RcEnc& s) {
+  if (++s.tail == 0 && s.out) {   // 0xFFFFFFFF + 1: the carry leaves the register (the zero first byte stops it at the latest)
+    long long p = (long long)s.cnt - 5;
+    while (p > 0 && (p >= s.cap || s.out[p] == 0xFF)) {
+      if (p < s.cap) s.out[p] = 0;
+      --p;
+    }
+    if (p >= 0 && p < s.cap) ++s.out[p];
   }
-  ++s.cache_size;
-  s.low = (s.low & 0x00FFFFFFull) << 8;
 }
 __host__ __device__ __forceinline__ void rc_enc_interval(RcEnc& s, uint32_t lower, uint32_t freq, int precision) {
   const uint32_t r = s.range >> precision;
-  s.low += (unsigned long long)r * lower;
+  const uint32_t add = r * lower;   // r < 2^(32 - precision), lower < 2^precision
+  s.low += add;
+  if (s.low < add) rc_enc_carry(s);
   s.range = r * freq;
   while (s.range < kRcTop) {
-    rc_enc_shift_low(s);
+    rc_enc_emit(s, s.low >> 24);
+    s.low <<= 8;
     s.range <<= 8;
   }
 }
@@ -83,16 +84,30 @@ __host__ __device__ __forceinline__ void rc_enc_symbol(RcEnc& s, uint32_t lf, ui
   }
 }
 // terminator: the value in [low, low + range) with the most trailing zero bits; -> stream length (first byte and trailing
-// zeros dropped), or -1 when the buffer was too small
+// zeros dropped; valid on the writing lane), or -1 when the buffer was too small
 __host__ __device__ __forceinline__ int32_t rc_enc_finish(RcEnc& s) {
-  const unsigned long long hi = s.low + s.range - 1;
+  const unsigned long long lo = s.low, hi = lo + s.range - 1;
+  unsigned long long v = lo;
   for (int nbits = 32; nbits >= 0; --nbits) {
     const unsigned long long mask = (1ull << nbits) - 1;
-    const unsigned long long v = (s.low + mask) & ~mask;
-    if (v <= hi) { s.low = v; break; }
+    v = (lo + mask) & ~mask;
+    if (v <= hi) break;
   }
-  for (int k = 0; k < 5; ++k) rc_enc_shift_low(s);
-  return s.pos > s.cap ? -1 : (s.last_nz > 1 ? (int32_t)(s.last_nz - 1) : 0);
+  if (v >> 32) rc_enc_carry(s);
+  s.low = (uint32_t)v;
+  for (int k = 0; k < 4; ++k) {
+    rc_enc_emit(s, s.low >> 24);
+    s.low <<= 8;
+  }
+  if (s.cnt > s.cap) return -1;
+  if (!s.out) return 0;
+  for (int k = 0; k < 4; ++k) {   // the bytes still in the register
+    const long long p = (long long)s.cnt - 4 + k;
+    if (p >= 0) s.out[p] = (uint8_t)(s.tail >> (24 - 8 * k));
+  }
+  long long p = (long long)s.cnt - 1;
+  while (p >= 1 && s.out[p] == 0) --p;
+  return (int32_t)p;
 }
 // symbol -> (lf, ov); false when the table index is out of range
 __host__ __device__ __forceinline__ bool rc_map_symbol(int32_t sym, int row, const int32_t* cdf, int cdf_stride, const int32_t* cdf_length,
@@ -174,12 +189,14 @@ __global__ void rc_pack_kernel(const uint8_t* __restrict__ streams, uint32_t cap
 }
 
 // ---------------------------------------------------------------- decoder
-// stream bytes through the lanes' registers: 128 bytes per refill, the next 128 already in flight
+// stream bytes through the lanes' registers: 128 bytes per refill (the next 128 already in flight); the current 4 bytes sit
+// in a warp-uniform register, so a byte costs a shift and every fourth byte one shuffle
 struct RcBytes {
   const uint8_t* p;
   long long len;
   long long chunk;     // index of the 128-byte chunk in `cur`
   uint32_t cur, nxt;   // this lane's 4 bytes of chunk / chunk + 1
+  uint32_t word;       // bytes [pos & ~3, +4) of the chunk (warp-uniform)
   uint32_t pos;        // next byte within the chunk (warp-uniform)
 };
 __device__ __forceinline__ uint32_t rc_load4(const uint8_t* p, long long len, long long at) {
@@ -193,15 +210,19 @@ __device__ __forceinline__ void rc_bytes_init(RcBytes& b, const uint8_t* p, long
   b.p = p; b.len = len; b.chunk = 0; b.pos = 0;
   b.cur = rc_load4(p, len, 4 * lane);
   b.nxt = rc_load4(p, len, 128 + 4 * lane);
+  b.word = __shfl_sync(0xffffffffu, b.cur, 0);
 }
 __device__ __forceinline__ uint32_t rc_bytes_next(RcBytes& b, int lane) {
-  const uint32_t w = __shfl_sync(0xffffffffu, b.cur, b.pos >> 2);
-  const uint32_t v = (w >> ((b.pos & 3u) * 8u)) & 0xffu;
-  if (++b.pos == 128u) {
-    b.pos = 0;
-    ++b.chunk;
-    b.cur = b.nxt;
-    b.nxt = rc_load4(b.p, b.len, (b.chunk + 1) * 128 + 4 * lane);
+  const uint32_t v = (b.word >> ((b.pos & 3u) * 8u)) & 0xffu;
+  ++b.pos;
+  if ((b.pos & 3u) == 0) {
+    if (b.pos == 128u) {
+      b.pos = 0;
+      ++b.chunk;
+      b.cur = b.nxt;
+      b.nxt = rc_load4(b.p, b.len, (b.chunk + 1) * 128 + 4 * lane);
+    }
+    b.word = __shfl_sync(0xffffffffu, b.cur, b.pos >> 2);
   }
   return v;
 }
@@ -215,24 +236,47 @@ __device__ __forceinline__ void rc_dec_normalize(RcDec& d, RcBytes& b, int lane)
     d.range <<= 8;
   }
 }
+// min(code / r, 15) without the division: the number of k in 1..15 with k * r <= code, one k per lane
 __device__ __forceinline__ uint32_t rc_dec_uniform(RcDec& d, RcBytes& b, int lane) {
-  const uint32_t r = d.range >> kRcOverflowWidth;
-  uint32_t s = d.code / r;
-  if (s > kRcMaxOverflow) s = kRcMaxOverflow;
+  const uint32_t r = d.range >> kRcOverflowWidth;   // < 2^28: lane * r fits
+  const uint32_t s = __popc(__ballot_sync(0xffffffffu, lane >= 1 && lane <= (int)kRcMaxOverflow && (uint32_t)lane * r <= d.code));
   d.code -= r * s;
   d.range = r;
   rc_dec_normalize(d, b, lane);
   return s;
 }
 
-// grid = streams, block = 32.  lut (rows, 256): lut[r][v] = largest s in [0, n) with cdf[r][s] <= v << 8.
-__global__ void __launch_bounds__(32) rc_decode_kernel(const uint8_t* __restrict__ bytes, const long long* __restrict__ byte_offsets,
-                                                       const int32_t* __restrict__ indexes, long long per_stream,
-                                                       const int32_t* __restrict__ cdf, int cdf_stride,
-                                                       const int32_t* __restrict__ cdf_length, const int32_t* __restrict__ offset,
-                                                       const uint16_t* __restrict__ lut, int rows, int index_mode,
-                                                       long long channel_stride, int32_t* __restrict__ out, int* __restrict__ err) {
-  const int sidx = blockIdx.x, lane = threadIdx.x;
+// The symbol search is lane-parallel and division-free: with r = range >> 16, symbol s is the largest one with
+// cdf[s] * r <= code (== cdf[s] <= min(code / r, 65535), the host decoder's test, since cdf[s] < 65536 for s < n).
+// Level 1: lane L holds the pivot cdf[L * step], step = n / 32 + 1 -- fetched while the PREVIOUS symbol was decoded, the
+// table row of a symbol does not depend on the coder state -- and a ballot picks the segment; rows of up to 31 symbols
+// (scales < 5.4: most of a trained model's latents) are resolved right there.  Level 2: 32 lanes compare 32 consecutive
+// entries of the segment: one dependent table load per symbol -- from SHARED memory: every CTA first copies the compact
+// tables (16-bit entries, rows back to back: 27 KB for the 64 Gaussian scale rows), because an L2 round trip per symbol
+// (the tables do not fit L1) was most of the chain (4.1 ms per 16 384-symbol stream with the tables in global memory).
+// grid = ceil(streams / kRcDecWarps), block = kRcDecWarps warps, one stream per warp.
+constexpr int kRcDecWarps = 4;
+
+__global__ void __launch_bounds__(kRcDecWarps * 32) rc_decode_kernel(
+    const uint8_t* __restrict__ bytes, const long long* __restrict__ byte_offsets, const int32_t* __restrict__ indexes, int nstreams,
+    long long per_stream, const uint16_t* __restrict__ cdf16, const int32_t* __restrict__ row_start, const int32_t* __restrict__ cdf_length,
+    const int32_t* __restrict__ offset, int rows, int total_entries, int index_mode, long long channel_stride, int32_t* __restrict__ out,
+    int* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char rc_smem[];
+  int32_t* s_start = (int32_t*)rc_smem;
+  int32_t* s_len = s_start + rows;
+  int32_t* s_off = s_len + rows;
+  uint16_t* s_cdf = (uint16_t*)(s_off + rows);
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    s_start[i] = row_start[i];
+    s_len[i] = cdf_length[i];
+    s_off[i] = offset[i];
+  }
+  for (int i = threadIdx.x; i < total_entries; i += blockDim.x) s_cdf[i] = cdf16[i];
+  __syncthreads();   // the only block-wide step: the warps are independent from here on
+
+  const int sidx = blockIdx.x * kRcDecWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (sidx >= nstreams) return;
   const long long b0 = byte_offsets[sidx], b1 = byte_offsets[sidx + 1];
   RcBytes bs;
   rc_bytes_init(bs, bytes + b0, b1 - b0, lane);
@@ -250,34 +294,46 @@ __global__ void __launch_bounds__(32) rc_decode_kernel(const uint8_t* __restrict
     if (r < 0 || r >= rows) { bad = true; r = 0; }
     return r;
   };
+  // entry k of a row with n symbols: cdf[n] = 2^16 does not fit the 16-bit table and is implied; beyond the row: "infinite"
+  auto entry = [&](int start, int k, int n) -> uint32_t { return k < n ? (uint32_t)s_cdf[start + k] : (k == n ? 0x10000u : 0x7fffffffu); };
   int nrow = row_of(lane);
-  int nlen = cdf_length[nrow], noff = offset[nrow];
+  uint32_t piv_next = entry(s_start[__shfl_sync(0xffffffffu, nrow, 0)], lane * (((s_len[__shfl_sync(0xffffffffu, nrow, 0)] - 1) >> 5) + 1),
+                            s_len[__shfl_sync(0xffffffffu, nrow, 0)] - 1);
   for (long long base = 0; base < per_stream; base += 32) {
-    const int my_row = nrow, my_len = nlen, my_off = noff;
-    nrow = row_of(base + 32 + lane);   // next group's table parameters fly during this group's decoding
-    nlen = cdf_length[nrow];
-    noff = offset[nrow];
+    const int my_row = nrow;
+    nrow = row_of(base + 32 + lane);   // next group's table indexes fly during this group's decoding
     const int cnt_syms = (int)min(32LL, per_stream - base);
     int32_t my_out = 0;
     for (int j = 0; j < cnt_syms; ++j) {
       const int row = __shfl_sync(0xffffffffu, my_row, j);
-      const int n = __shfl_sync(0xffffffffu, my_len, j) - 1;   // symbols incl. the escape slot; cdf[0..n]
-      const int off = __shfl_sync(0xffffffffu, my_off, j);
-      const int32_t* rowp = cdf + (long long)row * cdf_stride;
-      const uint32_t r = d.range >> kRcPrecision;
-      uint32_t value = d.code / r;
-      if (value > 0xffffu) value = 0xffffu;
-      int lo = lut[row * 256 + (int)(value >> 8)];
-      int32_t c;
-      int cnt;
-      do {   // lane L looks at cdf[lo + L]; lanes >= 1 vote whether the symbol is at or beyond lo + L
-        const int k = lo + lane;
-        c = k <= n ? rowp[k] : 0x7fffffff;
-        const unsigned m = __ballot_sync(0xffffffffu, lane >= 1 && k < n && (uint32_t)c <= value);
-        cnt = __popc(m);
-        lo += cnt;
-      } while (cnt == 31);
-      const uint32_t c_lo = (uint32_t)__shfl_sync(0xffffffffu, c, cnt), c_hi = (uint32_t)__shfl_sync(0xffffffffu, c, cnt + 1);
+      const int start = s_start[row], n = s_len[row] - 1, off = s_off[row];   // n symbols incl. the escape slot; cdf[0..n]
+      const int step = (n >> 5) + 1;
+      const uint32_t piv = piv_next;
+      {   // the next symbol's pivots: issued now, consumed one symbol later
+        const int r_in = __shfl_sync(0xffffffffu, my_row, (j + 1) & 31), r_nx = __shfl_sync(0xffffffffu, nrow, 0);
+        const int rn = j + 1 < 32 ? r_in : r_nx;
+        const int nn = s_len[rn] - 1;
+        piv_next = entry(s_start[rn], lane * ((nn >> 5) + 1), nn);
+      }
+      const uint32_t r = d.range >> kRcPrecision;   // < 2^16, cdf <= 2^16: the products fit
+      const int seg = __popc(__ballot_sync(0xffffffffu, lane >= 1 && lane * step < n && piv * r <= d.code));
+      int lo = seg * step;
+      uint32_t c_lo, c_hi;
+      if (step == 1) {   // n <= 31: the pivots are the row
+        c_lo = __shfl_sync(0xffffffffu, piv, seg);
+        c_hi = __shfl_sync(0xffffffffu, piv, seg + 1);
+      } else {
+        uint32_t c;
+        int cnt;
+        do {   // lane L looks at cdf[lo + L]; lanes >= 1 vote whether the symbol is at or beyond lo + L
+          const int k = lo + lane;
+          c = entry(start, k, n);
+          cnt = __popc(__ballot_sync(0xffffffffu, lane >= 1 && k < n && c * r <= d.code));
+          lo += cnt;
+        } while (cnt == 31);
+        c_lo = __shfl_sync(0xffffffffu, c, cnt);
+        c_hi = __shfl_sync(0xffffffffu, c, cnt + 1);
+      }
       d.code -= r * c_lo;
       d.range = r * (c_hi - c_lo);
       rc_dec_normalize(d, bs, lane);
@@ -344,33 +400,51 @@ extern "C" int pccgeo_range_encode_device(const int32_t* symbols, const int32_t*
 }
 
 extern "C" int pccgeo_range_decode_device(const uint8_t* bytes, const long long* byte_offsets, const int32_t* indexes, int nstreams,
-                                          long long per_stream, const int32_t* cdf, int cdf_stride, const int32_t* cdf_length,
-                                          const int32_t* offset, const uint16_t* lut, int rows, int index_mode, long long channel_stride,
+                                          long long per_stream, const uint16_t* cdf16, const int32_t* row_start, const int32_t* cdf_length,
+                                          const int32_t* offset, int rows, int total_entries, int index_mode, long long channel_stride,
                                           int32_t* symbols_out, int* err, void* stream) {
-  PCCGEO_REQUIRE(bytes && byte_offsets && cdf && cdf_length && offset && lut && symbols_out && err, "range_decode_device: null pointer");
-  PCCGEO_REQUIRE(nstreams > 0 && per_stream > 0 && rows > 0 && (index_mode == 0 || index_mode == 1), "range_decode_device: bad argument");
+  PCCGEO_REQUIRE(bytes && byte_offsets && cdf16 && row_start && cdf_length && offset && symbols_out && err, "range_decode_device: null pointer");
+  PCCGEO_REQUIRE(nstreams > 0 && per_stream > 0 && rows > 0 && total_entries > 0 && (index_mode == 0 || index_mode == 1),
+                 "range_decode_device: bad argument");
   PCCGEO_REQUIRE(index_mode == 1 || indexes, "range_decode_device: index mode 0 needs indexes");
   PCCGEO_REQUIRE(index_mode == 0 || channel_stride > 0, "range_decode_device: index mode 1 needs channel_stride");
-  rc_decode_kernel<<<nstreams, 32, 0, (cudaStream_t)stream>>>(bytes, byte_offsets, indexes, per_stream, cdf, cdf_stride, cdf_length, offset,
-                                                              lut, rows, index_mode, channel_stride, symbols_out, err);
+  const size_t smem = (size_t)rows * 12 + (size_t)total_entries * 2;
+  PCCGEO_REQUIRE(smem <= 200 * 1024, "range_decode_device: tables of %zu bytes do not fit shared memory", smem);
+  PCCGEO_CUDA(cudaFuncSetAttribute(rc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rc_decode_kernel<<<(nstreams + kRcDecWarps - 1) / kRcDecWarps, kRcDecWarps * 32, smem, (cudaStream_t)stream>>>(
+      bytes, byte_offsets, indexes, nstreams, per_stream, cdf16, row_start, cdf_length, offset, rows, total_entries, index_mode, channel_stride,
+      symbols_out, err);
   return check_launch("rc_decode_kernel");
 }
 
-// The decoder's search accelerators, on the host (uploaded once per table set): lut[r][b] = largest s in [0, n) with
-// cdf[r][s] <= b << 8, n = cdf_length[r] - 1.
-extern "C" int pccgeo_range_lut_host(const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, int rows, uint16_t* lut) {
-  PCCGEO_REQUIRE(cdf && cdf_length && lut && rows > 0, "range_lut: bad argument");
+// The decoder's tables, on the host (uploaded once per table set): the rows' first cdf_length[r] - 1 entries as 16 bits, back to
+// back (the last entry of a row, 2^16, is implied); row_start (rows) receives the rows' positions.  -> number of entries, or
+// -1 if a row is not a valid 16-bit CDF.  Pass cdf16 == NULL to query the size.
+extern "C" long long pccgeo_range_compact_tables_host(const int32_t* cdf, int cdf_stride, const int32_t* cdf_length, int rows, uint16_t* cdf16,
+                                                      int32_t* row_start) {
+  if (!cdf || !cdf_length || rows <= 0) {
+    set_error("range_compact_tables: bad argument");
+    return -1;
+  }
+  long long pos = 0;
   for (int r = 0; r < rows; ++r) {
     const int32_t* row = cdf + (long long)r * cdf_stride;
     const int n = cdf_length[r] - 1;
-    int s = 0;
-    for (int b = 0; b < 256; ++b) {
-      const int32_t v = b << (kRcPrecision - 8);
-      while (s + 1 < n && row[s + 1] <= v) ++s;
-      lut[(size_t)r * 256 + b] = (uint16_t)s;
+    if (n < 1 || n + 1 > cdf_stride || row[0] != 0 || row[n] != (1 << kRcPrecision)) {
+      set_error("range_compact_tables: row %d is not a %d-bit CDF", r, kRcPrecision);
+      return -1;
     }
+    for (int k = 0; k < n; ++k) {
+      if (row[k] < 0 || row[k] >= (1 << kRcPrecision) || row[k + 1] < row[k]) {
+        set_error("range_compact_tables: row %d is not a %d-bit CDF", r, kRcPrecision);
+        return -1;
+      }
+      if (cdf16) cdf16[pos + k] = (uint16_t)row[k];
+    }
+    if (cdf16 && row_start) row_start[r] = (int32_t)pos;
+    pos += n;
   }
-  return PCCGEO_OK;
+  return pos;
 }
 
 // The device encoder's arithmetic (rc_map_symbol + rc_enc_symbol + rc_enc_finish, the same inline functions the kernels
@@ -407,4 +481,15 @@ extern "C" int pccgeo_range_encode_emulate_host(const int32_t* symbols, const in
   offsets[nstreams] = pos;
   free(buf);
   return PCCGEO_OK;
+}
+
+// Test hook for the one branch of the device encoder that random data practically never takes: a carry that leaves the
+// 4-byte register and walks back through memory.  buf holds n already-stored bytes; -> the register after the carry.
+extern "C" unsigned pccgeo_rc_carry_probe_host(uint8_t* buf, int n) {
+  RcEnc e;
+  rc_enc_init(e, buf, (uint32_t)n + 16);
+  e.tail = 0xFFFFFFFFu;
+  e.cnt = (uint32_t)n + 4;
+  rc_enc_carry(e);
+  return e.tail;
 }

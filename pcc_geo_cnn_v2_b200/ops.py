@@ -397,7 +397,7 @@ _dev_tables = {}
 
 
 def device_tables(tables):
-    """{'cdf','cdf_length','offset'} host tables -> the same + 'lut' as CUDA tensors, uploaded once per table set and device
+    """{'cdf','cdf_length','offset'} host tables -> the same + the decoder's compact 16-bit rows as CUDA tensors, uploaded once per table set and device
     (keyed by the identity of the host cdf array: entropy models build a new dict when their tables change)."""
     key = (id(tables['cdf']), torch.cuda.current_device())
     hit = _dev_tables.get(key)
@@ -406,10 +406,14 @@ def device_tables(tables):
     cdf = np.ascontiguousarray(tables['cdf'], np.int32)
     cl = np.ascontiguousarray(tables['cdf_length'], np.int32)
     of = np.ascontiguousarray(tables['offset'], np.int32)
-    lut = np.zeros((cdf.shape[0], 256), np.uint16)
-    L.check(L.lib().pccgeo_range_lut_host(L.ptr(cdf), cdf.shape[1], L.ptr(cl), cdf.shape[0], L.ptr(lut)), 'range_lut')
+    total = int(L.lib().pccgeo_range_compact_tables_host(L.ptr(cdf), cdf.shape[1], L.ptr(cl), cdf.shape[0], None, None))
+    if total < 0:
+        raise L.PccGeoError('range_compact_tables: ' + L.lib().pccgeo_last_error().decode('utf-8', 'replace'))
+    cdf16, starts = np.zeros(total, np.uint16), np.zeros(cdf.shape[0], np.int32)
+    L.lib().pccgeo_range_compact_tables_host(L.ptr(cdf), cdf.shape[1], L.ptr(cl), cdf.shape[0], L.ptr(cdf16), L.ptr(starts))
     dev = {'cdf': torch.from_numpy(cdf).cuda(), 'cdf_length': torch.from_numpy(cl).cuda(), 'offset': torch.from_numpy(of).cuda(),
-           'lut': torch.from_numpy(lut.view(np.int16)).cuda(), 'rows': cdf.shape[0], 'stride': cdf.shape[1]}
+           'cdf16': torch.from_numpy(cdf16.view(np.int16)).cuda(), 'row_start': torch.from_numpy(starts).cuda(), 'entries': total,
+           'rows': cdf.shape[0], 'stride': cdf.shape[1]}
     if len(_dev_tables) > 64:
         _dev_tables.clear()
     _dev_tables[key] = (tables['cdf'], dev)
@@ -451,9 +455,9 @@ def range_decode_device(bytes_dev, byte_offsets, nstreams, per_stream, dtab, ind
     if err is None:
         err = torch.zeros(1, dtype=torch.int32, device='cuda')
     L.check(L.lib().pccgeo_range_decode_device(L.ptr(bytes_dev), L.ptr(byte_offsets), L.ptr(indexes), nstreams, per_stream,
-                                               L.ptr(dtab['cdf']), dtab['stride'], L.ptr(dtab['cdf_length']), L.ptr(dtab['offset']),
-                                               L.ptr(dtab['lut']), dtab['rows'], mode, int(channel_stride), L.ptr(out), L.ptr(err),
-                                               L.stream_ptr()), 'range_decode_device')
+                                               L.ptr(dtab['cdf16']), L.ptr(dtab['row_start']), L.ptr(dtab['cdf_length']),
+                                               L.ptr(dtab['offset']), dtab['rows'], dtab['entries'], mode, int(channel_stride),
+                                               L.ptr(out), L.ptr(err), L.stream_ptr()), 'range_decode_device')
     return out, err
 
 

@@ -34,3 +34,25 @@ def test_emulated_device_encoder_rejects_bad_table_index():
     t = gaussian_tables(make_scale_table())
     with pytest.raises(Exception):
         ops.range_encode_emulate(np.zeros((1, 4), np.int32), 1, t, indexes=np.full((1, 4), 64, np.int32))
+
+
+def test_device_encoder_carry_walks_back_through_memory():
+    """0x12 FF FF | FF FF FF FF (register) + 1 -> 0x13 00 00 | 00 00 00 00"""
+    from pcc_geo_cnn_v2_b200 import _lib as L
+    buf = np.array([0x00, 0x12, 0xFF, 0xFF], np.uint8)
+    assert L.lib().pccgeo_rc_carry_probe_host(L.ptr(buf), 4) == 0
+    assert buf.tolist() == [0x00, 0x13, 0x00, 0x00]
+    buf = np.array([0x00, 0x12, 0xFF, 0x7F], np.uint8)
+    assert L.lib().pccgeo_rc_carry_probe_host(L.ptr(buf), 4) == 0
+    assert buf.tolist() == [0x00, 0x12, 0xFF, 0x80]
+
+
+def test_emulated_device_encoder_many_random_streams():
+    t = gaussian_tables(make_scale_table())
+    rng = np.random.default_rng(99)
+    for spread in (0.02, 0.3, 1.0, 8.0):
+        ns, per = 48, 3000
+        idx = rng.integers(0, 64, (ns, per)).astype(np.int32)
+        sym = np.round(rng.standard_normal((ns, per)) * make_scale_table()[idx] * spread).astype(np.int32)
+        offs = np.arange(ns + 1, dtype=np.int64) * per
+        assert ops.range_encode_emulate(sym, ns, t, indexes=idx) == ops.range_encode(sym.reshape(-1), offs, t, indexes=idx.reshape(-1))
