@@ -17,6 +17,13 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
+@pytest.fixture(params=['host', 'device'], autouse=True)
+def _entropy_coder(request, monkeypatch):
+    """every test of this file runs with the range coder in the host workers and on the GPU (models read the switch when built)"""
+    monkeypatch.setenv('PCCGEO_DEVICE_CODER', '1' if request.param == 'device' else '0')
+    yield request.param
+
+
 def _modelnet_blocks():
     g = np.load(os.path.join(GOLDEN, 'modelnet_blocks.npz'))
     return [g[f'block{i}'].astype(np.float32) for i in range(len(g['names']))]
@@ -51,6 +58,8 @@ def test_modelnet_blocks_round_trip_and_rate():
     blocks = _modelnet_blocks()
     assert len(blocks) == 24 and min(map(len, blocks)) == 3571 and max(map(len, blocks)) == 38933
     m = _model(batch_size=8)          # 3 pipelined batches
+    assert m.device_coder == (os.environ['PCCGEO_DEVICE_CODER'] == '1')
+    m.coder_group_blocks = 16         # 2 coder groups
     m.compress((1, 1, 64, 64, 64))
     data, meta, _ = m.compress_blocks(None, blocks, None, None, 512, 3, fixed_threshold=True)
     dec, _ = m.decompress_blocks(None, data[0], (64, 64, 64))
