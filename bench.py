@@ -313,8 +313,8 @@ def main():
         data_list, meta, _ = m.compress_blocks(None, e2e_blocks, None, None, SIZE, 0, fixed_threshold=True)
         if world > 1:  # the path's only exchange step: per-block byte strings gathered over NCCL (rank 0 writes the container)
             from pcc_geo_cnn_v2_b200.sharding import gather_block_data
-            gathered = gather_block_data(data_list[0])
-            assert len(gathered) == world * B * EB
+            gathered = gather_block_data(data_list[0], dst=0)
+            assert (gathered is None) == (rank != 0) and (rank != 0 or len(gathered) == world * B * EB)
         dec, _ = m.decompress_blocks(None, data_list[0], (SIZE, SIZE, SIZE))
         return data_list, dec
 

@@ -42,7 +42,8 @@ def _worker(rank, world, port, q):
             for _ in range(11)]
     b, e = sharding.shard_range(len(full), rank, world)
     got = sharding.gather_block_data(full[b:e])
-    q.put((rank, got == full))
+    only0 = sharding.gather_block_data(full[b:e], dst=0)   # the container writer alone unpacks
+    q.put((rank, got == full and (only0 == full if rank == 0 else only0 is None)))
     dist.barrier()
     dist.destroy_process_group()
 
