@@ -87,3 +87,30 @@ def test_block_loops_identical_with_device_coder(config, bias):
     m.device_coder = False
     dec, _ = m.decompress_blocks(None, res[True][0], (64, 64, 64))
     assert [p.tobytes() for p in dec] == res[False][2]
+
+
+def test_corrupt_streams_never_crash_the_decoder():
+    """Random bytes, truncated and empty strings: the device decoder must return (garbage symbols, possibly the error flag),
+    like the host decoder -- and agree with it symbol for symbol whenever neither flags an error."""
+    t = gaussian_tables(make_scale_table())
+    dt = ops.device_tables(t)
+    rng = np.random.default_rng(11)
+    ns, per = 12, 700
+    idx = rng.integers(0, 64, (ns, per)).astype(np.int32)
+    strings = [rng.bytes(int(n)) for n in rng.integers(0, 900, ns)]
+    strings[3] = b''
+    strings[5] = b'\xff' * 400            # long escape runs: unary width code beyond any valid value
+    offs = np.zeros(ns + 1, np.int64)
+    offs[1:] = np.cumsum([len(s) for s in strings])
+    blob = torch.from_numpy(np.frombuffer(b''.join(strings) + b'\0', np.uint8).copy()).cuda()
+    out, err = ops.range_decode_device(blob, torch.from_numpy(offs).cuda(), ns, per, dt, indexes=torch.from_numpy(idx).cuda())
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    soffs = np.arange(ns + 1, dtype=np.int64) * per
+    for i in range(ns):   # stream by stream: the host decoder raises on a corrupt escape code
+        try:
+            ref = ops.range_decode([strings[i]], soffs[:2], t, indexes=idx[i])
+        except Exception:
+            continue
+        assert np.array_equal(got[i], ref), i
+    assert int(err.item()) in (0, 1)
