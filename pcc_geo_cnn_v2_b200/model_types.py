@@ -166,10 +166,15 @@ def sparse_to_dense(block, x_shape, data_format='channels_first'):
     return ops.densify(torch.from_numpy(np.ascontiguousarray(coords)).cuda(), 1, *[int(s) for s in x_shape[2:]])
 
 
-def blocks_to_coords(blocks, threads=1):
-    """list of (n_i, >=3) arrays -> one int16 (sum n_i, 4) array of (block, z, y, x) rows (C++ host helper)."""
+def blocks_to_coords(blocks, threads=1, staged=False):
+    """list of (n_i, >=3) arrays -> one int16 (sum n_i, 4) array of (block, z, y, x) rows (C++ host helper).
+    staged=True writes the rows straight into a pinned staging buffer and returns (pinned int16 torch view, pool buffer):
+    the block loops' driver thread then only enqueues the H2D copy instead of copying megabytes itself."""
     n = len(blocks)
     if not n:
+        if staged:
+            buf = _pinned.get(1)
+            return buf[:0].view(torch.int16).view(0, 4), buf
         return np.zeros((0, 4), np.int16)
     arrs = [np.asarray(b) for b in blocks]
     f64 = any(a.dtype == np.float64 for a in arrs)
@@ -182,11 +187,17 @@ def blocks_to_coords(blocks, threads=1):
     counts = np.array([len(a) for a in arrs], np.int64)
     pitch = np.array([a.strides[0] if len(a) else 0 for a in arrs], np.int64)
     ptrs = np.array([a.__array_interface__['data'][0] if len(a) else 0 for a in arrs], np.uint64)
-    out = np.empty((int(counts.sum()), 4), np.int16)
+    rows = int(counts.sum())
+    if staged:
+        buf = _pinned.get(max(rows * 8, 1))
+        host = buf[:rows * 8].view(torch.int16).view(rows, 4)
+        out = host.numpy()
+    else:
+        out = np.empty((rows, 4), np.int16)
     from . import _lib as L
     L.check(L.lib().pccgeo_blocks_to_coords_host(L.ptr(ptrs), L.ptr(counts), L.ptr(pitch), n, int(f64), L.ptr(out), int(threads)),
             'blocks_to_coords')
-    return out
+    return (host, buf) if staged else out
 
 
 def bits_to_points(bits_host, shape):
@@ -429,6 +440,18 @@ class CompressionModel:
         _pinned.put_after(buf, ev)
         return dst
 
+    @staticmethod
+    def _h2d_staged(staged):
+        """(pinned host tensor, pool buffer) from a host worker -> new CUDA tensor (async on the current stream)."""
+        host, buf = staged
+        dst = torch.empty(host.shape, dtype=host.dtype, device='cuda')
+        if host.numel():
+            dst.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        _pinned.put_after(buf, ev)
+        return dst
+
     def _h2d(self, arr):
         """numpy -> new CUDA tensor through recycled pinned memory (async on the current stream)."""
         a = np.asarray(arr)
@@ -444,7 +467,7 @@ class CompressionModel:
         dims = [int(s) for s in (x_shape if x_shape is not None else self.x_shape)][-3:]
         spans = [(i, min(i + self.batch_size, len(blocks))) for i in range(0, len(blocks), self.batch_size)]
         pool = self._pool()
-        coords_f = [pool.submit(blocks_to_coords, blocks[a:b], self.coder_threads) for a, b in spans]
+        coords_f = [pool.submit(blocks_to_coords, blocks[a:b], self.coder_threads, True) for a, b in spans]
 
         def post(dev, pend):
             strings = self._encode_host(dev, self._wait(pend['sym']))
@@ -463,13 +486,13 @@ class CompressionModel:
             if len(post_f) >= self.pipeline_depth + 4:  # bound the driver's run-ahead (staging memory in flight)
                 post_f[len(post_f) - self.pipeline_depth - 4].result()
             if graphs:
-                lat, st = self.device_encode(self._h2d(cf.result()), b - a, dims, None)
+                lat, st = self.device_encode(self._h2d_staged(cf.result()), b - a, dims, None)
                 pend = {'sym': self._d2h(*self._latent_tensors(lat))}
                 pend['bits'] = self._d2h(self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b])))
                 xs.append(None)
                 post_f.append(pool.submit(post, lat, pend))
                 continue
-            x = ops.densify(self._h2d(cf.result()), b - a, *dims)
+            x = ops.densify(self._h2d_staged(cf.result()), b - a, *dims)
             pend = {}
             t = self._h2d(threshold_f32(self.thresholds, thr_idx[a:b])) if thr_idx is not None else None
             # the symbol D2H is enqueued BEFORE synthesis is launched: range coding overlaps the synthesis kernels
@@ -621,7 +644,7 @@ class CompressionModel:
                         big[k] = torch.empty((g1 - g0,) + tuple(l['shape']), dtype=torch.int32, device='cuda')
                         big[k].record_stream(side)
             for a, b in group:
-                lat, st = self.device_encode(self._h2d(cf_of[(a, b)].result()), b - a, dims, None)
+                lat, st = self.device_encode(self._h2d_staged(cf_of[(a, b)].result()), b - a, dims, None)
                 for k, t in big.items():
                     t[a - g0:b - g0].copy_(lat[k].view(t[a - g0:b - g0].shape))
                 pend = self._d2h(self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b])))

@@ -30,7 +30,7 @@ B, NB = 32, int(sys.argv[1]) if len(sys.argv) > 1 else 4
 m = P.ModelConfigType['c3p'].build(batch_size=B)
 m.set_weights(synthetic.trained_like_weights(m, seed=42))
 m.compress((1, 1, 64, 64, 64))
-for n in ('_h2d', '_d2h', 'device_encode', 'device_synthesis', '_graph_dev1', '_graph_dev2', '_encode_host', '_decode_host0',
+for n in ('_h2d', '_h2d_staged', '_d2h', 'device_encode', 'device_synthesis', '_graph_dev1', '_graph_dev2', '_encode_host', '_decode_host0',
           '_decode_host1', '_wait', '_copy_in', 'encode_blocks', '_strings_task', '_points_task', '_upload_strings', '_stage',
           '_decompress_blocks_device_coder', '_encode_blocks_device_coder'):
     wrap(m, n)
