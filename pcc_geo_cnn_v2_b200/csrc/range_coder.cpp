@@ -76,11 +76,23 @@ struct Decoder {
     for (int i = 0; i < 4; ++i) code = (code << 8) | next();
   }
   inline uint32_t next() { return p < end ? *p++ : (++p, 0u); }
+  // Renormalisation without a data-dependent loop: the number of bytes to shift in is the number of leading zero bytes of
+  // `range` (the loop `while (range < 2^24) { code = code << 8 | next(); range <<= 8; }` in closed form), and they are taken
+  // from one unaligned big-endian 4-byte load.  Whether a symbol needs 0, 1 or 2 bytes is close to a coin flip, so the loop's
+  // branch mispredicted on most symbols.  Past the end of the stream the bytes read as zero (next() semantics).
   inline void normalize() {
-    while (range < kTop) {
-      code = (code << 8) | next();
-      range <<= 8;
+    const int nb = __builtin_clz(range) >> 3;  // range != 0
+    uint32_t w;
+    if (end - p >= 4) {
+      std::memcpy(&w, p, 4);
+      w = __builtin_bswap32(w);
+    } else {
+      w = 0;
+      for (int k = 0; k < 4; ++k) w = (w << 8) | (p + k < end ? p[k] : 0u);
     }
+    code = (uint32_t)(((((uint64_t)code) << 32) | w) >> (32 - 8 * nb));
+    range <<= 8 * nb;
+    p += nb;
   }
   // lut (optional, 256 entries): lut[b] = largest symbol s with cdf[s] <= (b << (precision-8)); the search then scans
   // forward from there -- for the peaked tables of this codec that is 0-2 steps instead of an 11-step binary search.
