@@ -17,7 +17,13 @@ m.set_weights(synthetic.trained_like_weights(m, seed=42))
 m.compress((1, 1, 64, 64, 64))
 uniq = synthetic.surface_blocks(8, size=64, seed=100)
 blocks = [uniq[i % 8] for i in range(B * NB)]
+import gc  # noqa: E402
 for i in range(steps):
+    if os.environ.get('E2E_GC_OFF_HALFWAY') and i == steps // 2:
+        gc.collect()
+        gc.freeze()
+        gc.disable()
+        print('-- gc frozen + disabled --', flush=True)
     t0 = time.perf_counter()
     dl, _, _ = m.compress_blocks(None, blocks, None, None, 64, 0, fixed_threshold=True)
     t1 = time.perf_counter()
