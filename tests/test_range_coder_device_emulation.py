@@ -56,3 +56,25 @@ def test_emulated_device_encoder_many_random_streams():
         sym = np.round(rng.standard_normal((ns, per)) * make_scale_table()[idx] * spread).astype(np.int32)
         offs = np.arange(ns + 1, dtype=np.int64) * per
         assert ops.range_encode_emulate(sym, ns, t, indexes=idx) == ops.range_encode(sym.reshape(-1), offs, t, indexes=idx.reshape(-1))
+
+
+def test_compact_tables_for_the_device_decoder():
+    """pccgeo_range_compact_tables_host: rows back to back as 16-bit entries without their (implied) final 2^16; rejects
+    rows that are not 16-bit CDFs."""
+    from pcc_geo_cnn_v2_b200 import _lib as L
+    t = gaussian_tables(make_scale_table())
+    cdf, cl = np.ascontiguousarray(t['cdf'], np.int32), np.ascontiguousarray(t['cdf_length'], np.int32)
+    rows = cdf.shape[0]
+    total = L.lib().pccgeo_range_compact_tables_host(L.ptr(cdf), cdf.shape[1], L.ptr(cl), rows, None, None)
+    assert total == int((cl - 1).sum()) and total * 2 + rows * 12 < 48 * 1024      # fits the default shared-memory window
+    c16, start = np.zeros(total, np.uint16), np.zeros(rows, np.int32)
+    assert L.lib().pccgeo_range_compact_tables_host(L.ptr(cdf), cdf.shape[1], L.ptr(cl), rows, L.ptr(c16), L.ptr(start)) == total
+    for r in (0, 1, 17, rows - 1):
+        n = int(cl[r]) - 1
+        assert np.array_equal(c16[start[r]:start[r] + n], cdf[r, :n]) and cdf[r, n] == 65536
+    bad = cdf.copy()
+    bad[3, int(cl[3]) - 1] = 65535      # a row that does not end at 2^16
+    assert L.lib().pccgeo_range_compact_tables_host(L.ptr(bad), bad.shape[1], L.ptr(cl), rows, None, None) == -1
+    bad = cdf.copy()
+    bad[5, 1] = bad[5, 2] + 1           # not monotone
+    assert L.lib().pccgeo_range_compact_tables_host(L.ptr(bad), bad.shape[1], L.ptr(cl), rows, None, None) == -1
