@@ -7,10 +7,15 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <queue>
 #include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../include/pccgeo.h"
 
@@ -249,26 +254,104 @@ bool decode_stream_x2(const Tables& t, const uint8_t* b0, const uint8_t* e0, con
   return true;
 }
 
+// Fork-join helpers of ONE calling thread (thread_local): created on first use, parked on a condition variable between
+// calls.  Spawning std::threads per call cost 0.3-0.7 ms for 8-16 threads -- as much as the work itself for the small host
+// stages of a batch (first latent's decode, coordinate packing, point extraction), six of which run per batch.  Each caller
+// (the block loops' driver and each of its host workers) owns its team, so concurrent callers never queue behind each
+// other's jobs; the caller takes part in the loop itself and then waits for its helpers.
+class HelperTeam {
+ public:
+  ~HelperTeam() { shutdown(); }
+
+  void run(int n, int threads, const std::function<void(int)>& f) {
+    if (pid_ != getpid()) abandon();   // forked child: the parent's helper threads do not exist here
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      while ((int)helpers_.size() < threads - 1) {
+        const int id = (int)helpers_.size();
+        helpers_.emplace_back([this, id, seen = gen_] { loop(id, seen); });
+      }
+      f_ = &f;
+      n_ = n;
+      next_.store(0, std::memory_order_relaxed);
+      active_ = threads - 1;
+      done_ = 0;
+      ++gen_;
+    }
+    cv_start_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return done_ == active_; });
+    f_ = nullptr;
+  }
+
+ private:
+  void work() {
+    for (;;) {
+      const int i = next_.fetch_add(1, std::memory_order_relaxed);
+      if (i >= n_) break;
+      (*f_)(i);
+    }
+  }
+  void loop(int id, unsigned long long seen) {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_start_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        if (id >= active_) continue;   // this job wants fewer helpers
+      }
+      work();
+      std::unique_lock<std::mutex> lk(m_);
+      if (++done_ == active_) cv_done_.notify_one();
+    }
+  }
+  void shutdown() {
+    if (pid_ != getpid()) {
+      abandon();
+      return;
+    }
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      stop_ = true;
+    }
+    cv_start_.notify_all();
+    for (auto& t : helpers_) t.join();
+    helpers_.clear();
+  }
+  void abandon() {
+    // the std::thread objects name threads of the parent process: leak them (neither join nor detach may touch them)
+    new std::vector<std::thread>(std::move(helpers_));
+    helpers_.clear();
+    gen_ = 0;
+    stop_ = false;
+    pid_ = getpid();
+  }
+
+  std::mutex m_;
+  std::condition_variable cv_start_, cv_done_;
+  std::vector<std::thread> helpers_;
+  const std::function<void(int)>* f_ = nullptr;
+  int n_ = 0, active_ = 0, done_ = 0;
+  std::atomic<int> next_{0};
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+  pid_t pid_ = getpid();
+};
+
 template <class F>
 void parallel_for(int n, int threads, F&& f) {
   if (threads < 1) threads = 1;
   if (threads > n) threads = n;
+  if (threads > 256) threads = 256;
   if (threads <= 1) {
     for (int i = 0; i < n; ++i) f(i);
     return;
   }
-  std::atomic<int> next{0};
-  std::vector<std::thread> pool;
-  pool.reserve(threads);
-  for (int t = 0; t < threads; ++t)
-    pool.emplace_back([&] {
-      for (;;) {
-        const int i = next.fetch_add(1);
-        if (i >= n) break;
-        f(i);
-      }
-    });
-  for (auto& th : pool) th.join();
+  static thread_local HelperTeam team;
+  const std::function<void(int)> fn = [&f](int i) { f(i); };
+  team.run(n, threads, fn);
 }
 
 }  // namespace
