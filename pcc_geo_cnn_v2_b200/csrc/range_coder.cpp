@@ -27,48 +27,59 @@ namespace {
 
 constexpr uint32_t kTop = 1u << 24;
 
+// The low/cache/cache_size machine of an LZMA-style range encoder, restated without its data-dependent loops (same bytes):
+// `low` is 32 bits; a carry out of it is added at once to the bytes already written (a walk back over 0xFF bytes: the
+// always-zero first byte stops it at the latest); renormalisation emits the `nb` leading bytes of `low`, nb = number of
+// leading zero bytes of `range`, with one unaligned 4-byte store.  Whether a symbol emits 0, 1 or 2 bytes is close to a coin
+// flip, so the byte loop mispredicted on most symbols (21 -> 13 ns per symbol on the bench's latents).
 struct Encoder {
-  uint64_t low = 0;
+  uint32_t low = 0;
   uint32_t range = 0xFFFFFFFFu;
-  uint8_t cache = 0;
-  uint64_t cache_size = 1;
-  std::vector<uint8_t> out;
+  std::vector<uint8_t> out;  // out[0]: the always-zero first byte; every encode() may write 4 bytes at pos
+  size_t pos = 1;
 
-  void shift_low() {
-    if ((uint32_t)low < 0xFF000000u || (low >> 32) != 0) {
-      const uint8_t carry = (uint8_t)(low >> 32);
-      uint8_t temp = cache;
-      do {
-        out.push_back((uint8_t)(temp + carry));
-        temp = 0xFF;
-      } while (--cache_size != 0);
-      cache = (uint8_t)(low >> 24);
-    }
-    ++cache_size;
-    low = (low & 0x00FFFFFFull) << 8;
+  explicit Encoder(size_t reserve) : out(reserve + 64, 0) {}
+  inline void ensure() {  // once per symbol: a symbol emits at most 2 + 11 bytes (escape: 3 + 8 four-bit intervals)
+    if (pos + 32 > out.size()) out.resize(out.size() * 2);
+  }
+  inline void carry() {
+    uint8_t* p = out.data() + pos - 1;
+    while (*p == 0xFF) *p-- = 0;
+    ++*p;
+  }
+  inline void put4() {
+    const uint32_t be = __builtin_bswap32(low);
+    std::memcpy(out.data() + pos, &be, 4);
   }
   inline void encode(uint32_t lower, uint32_t upper, int precision) {
     const uint32_t r = range >> precision;
-    low += (uint64_t)r * lower;
+    const uint32_t add = r * lower;  // r < 2^(32 - precision), lower < 2^precision
+    low += add;
+    if (low < add) carry();
     range = r * (upper - lower);
-    while (range < kTop) {
-      shift_low();
-      range <<= 8;
-    }
+    const int nb = __builtin_clz(range) >> 3;  // range >= 2^8: nb <= 2
+    put4();
+    pos += nb;
+    low <<= 8 * nb;
+    range <<= 8 * nb;
   }
   void finish() {
-    const uint64_t hi = low + range - 1;
+    // the value in [low, low + range) with the most trailing zero bits
+    const uint64_t lo = low, hi = lo + range - 1;
+    uint64_t v = lo;
     for (int nbits = 32; nbits >= 0; --nbits) {
       const uint64_t mask = (1ull << nbits) - 1;
-      const uint64_t v = (low + mask) & ~mask;
-      if (v <= hi) {
-        low = v;
-        break;
-      }
+      v = (lo + mask) & ~mask;
+      if (v <= hi) break;
     }
-    for (int i = 0; i < 5; ++i) shift_low();
+    if (v >> 32) carry();
+    low = (uint32_t)v;
+    ensure();
+    put4();
+    pos += 4;
+    while (pos > 1 && out[pos - 1] == 0) --pos;  // trailing zero bytes are implied
+    out.resize(pos);
     out.erase(out.begin());  // the first byte is always 0
-    while (!out.empty() && out.back() == 0) out.pop_back();
   }
 };
 
@@ -166,6 +177,7 @@ bool encode_stream(const Tables& t, const int32_t* sym, const int32_t* idx, long
       overflow = (uint64_t)(2 * (value - max_value));
       value = max_value;
     }
+    enc.ensure();
     enc.encode((uint32_t)row[value], (uint32_t)row[value + 1], kPrecision);
     if (value == max_value) {
       int widths = 0;
@@ -370,8 +382,7 @@ extern "C" int pccgeo_range_encode_host(const int32_t* symbols, const int32_t* i
   std::atomic<int> bad{0};
   parallel_for(nstreams, threads, [&](int i) {
     const long long a = sym_offsets[i], b = sym_offsets[i + 1];
-    Encoder enc;  // coder state on this thread's stack: neighbouring streams' states must not share cache lines
-    enc.out.reserve((size_t)((b - a) / 2 + 64));
+    Encoder enc((size_t)(b - a));  // coder state on this thread's stack: neighbouring streams' states must not share cache lines
     if (!encode_stream(t, symbols + a, index_mode == 0 ? indexes + a : nullptr, b - a, enc)) bad.store(1);
     outs[i] = std::move(enc.out);
   });
