@@ -365,8 +365,8 @@ def range_encode(symbols, sym_offsets, tables, indexes=None, channel_stride=0, t
     L.check(L.lib().pccgeo_range_encode_host(L.ptr(symbols), L.ptr(indexes), L.ptr(offs), ns, L.ptr(cdf), cdf.shape[1],
                                              L.ptr(cl), L.ptr(of), cdf.shape[0], mode, int(channel_stride),
                                              L.ptr(out), cap, L.ptr(out_offs), threads), 'range_encode')
-    buf = out[:int(out_offs[-1])].tobytes()
-    return [buf[out_offs[i]:out_offs[i + 1]] for i in range(ns)]
+    view, o = memoryview(out), out_offs.tolist()
+    return [bytes(view[o[i]:o[i + 1]]) for i in range(ns)]
 
 
 def range_decode(strings, sym_offsets, tables, indexes=None, channel_stride=0, threads=0):
@@ -377,7 +377,11 @@ def range_decode(strings, sym_offsets, tables, indexes=None, channel_stride=0, t
     assert len(strings) == ns
     boffs = np.zeros(ns + 1, np.int64)
     boffs[1:] = np.cumsum([len(s) for s in strings])
-    blob = np.frombuffer(b''.join(strings) + b'\x00', np.uint8)
+    blob = np.empty(int(boffs[-1]) + 1, np.uint8)   # one gather copy (+ a pad byte: never a null pointer)
+    for s, o in zip(strings, boffs.tolist()):
+        if s:
+            blob[o:o + len(s)] = np.frombuffer(s, np.uint8)
+    blob[-1] = 0
     cdf = np.ascontiguousarray(tables['cdf'], np.int32)
     cl = np.ascontiguousarray(tables['cdf_length'], np.int32)
     of = np.ascontiguousarray(tables['offset'], np.int32)
