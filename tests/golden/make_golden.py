@@ -22,19 +22,19 @@ from pcc_geo_cnn_v2_b200.model_configs import ModelConfigType  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def oracle_for(config, seed):
+def oracle_for(config, seed, **kw):
     m = ModelConfigType[config].build()
-    w = synthetic.trained_like_weights(m, seed=seed)
+    w = synthetic.trained_like_weights(m, seed=seed, **kw)
     o = OracleModel(config)
     eb = w['entropy_bottleneck']
     o.set_params({k: v for k, v in w.items() if k != 'entropy_bottleneck'}, eb)
     return o
 
 
-def make(config, size, n_blocks, seed, name):
-    o = oracle_for(config, seed)
+def make(config, size, n_blocks, seed, name, **kw):
+    o = oracle_for(config, seed, **kw)
     blocks = synthetic.surface_blocks(n_blocks, size=size, seed=seed + 1)
-    out = {'config': config, 'size': size, 'seed': seed, 'n_blocks': n_blocks}
+    out = {'config': config, 'size': size, 'seed': seed, 'n_blocks': n_blocks, **kw}
     t128 = o.thresholds[128]
     for j, b in enumerate(blocks):
         x = sparse_to_dense(b, (1, 1, size, size, size))
@@ -61,3 +61,6 @@ if __name__ == '__main__':
     make('c1', 32, 1, 44, 'c1_32.npz')
     make('c2', 32, 1, 45, 'c2_32.npz')
     make('c3', 32, 1, 46, 'c3_32.npz')
+    if 'v1_64' in sys.argv:   # full-size blocks through the k9 / k5 layers of the V1 transforms (gains / output bias: latents over +-8, half of the scale table, non-empty decodes)
+        make('c1', 64, 2, 47, 'c1_64.npz', gain=4.0, synthesis_gain=3.0, output_bias=-1.3)
+        make('c2', 64, 2, 48, 'c2_64.npz', gain=4.0, synthesis_gain=3.0, output_bias=-1.6)

@@ -75,10 +75,12 @@ def test_golden_fixture(fixture, precision):
     g = np.load(os.path.join(GOLDEN, fixture))
     config, size, seed, nb = str(g['config']), int(g['size']), int(g['seed']), int(g['n_blocks'])
     MT.set_precision(precision)
-    m = _model(config, seed)
+    m = _model(config, seed, **{k: float(g[k]) for k in ('gain', 'synthesis_gain', 'output_bias') if k in g})
     m.compress((1, 1, size, size, size))
     blocks = [g[f'block{j}'].astype(np.float32) for j in range(nb)]
     v2 = f'z_sym0' in g
+    if size == 64:   # the full-size fixtures exercise non-trivial latents and non-empty decodes
+        assert all(np.count_nonzero(g[f'y_sym{j}']) > g[f'y_sym{j}'].size // 20 and len(g[f'points{j}']) > 500 for j in range(nb))
     # ---- encoder side: symbols / indexes / strings
     from pcc_geo_cnn_v2_b200 import ops
     from pcc_geo_cnn_v2_b200.entropy_models import GaussianConditional
@@ -115,6 +117,11 @@ def test_golden_fixture(fixture, precision):
     # ---- decoder side: oracle-made strings -> points, for the blocks whose scale indexes agree with the oracle's (an
     # index flip desynchronises the y stream of ANY two implementations -- the reference pins this step to the CPU and
     # retries for the same reason, patch_gaussian_conditional.py:105-116, decompress_octree.py:69-131)
+    # Blocks with an index flip are NOT skipped: they are decoded stage by stage with the oracle's indexes (range decoder ->
+    # the oracle's symbols exactly; synthesis + threshold -> the oracle's points), so every block of every fixture is decoded
+    # from the oracle's strings in every precision.
+    from pcc_geo_cnn_v2_b200.entropy_models import gaussian_tables
+    from pcc_geo_cnn_v2_b200.model_types import threshold_f32
     data, keep = [], []
     for j in range(nb):
         strs = tuple(g[f'string{j}_{i}'].tobytes() for i in range(2 if v2 else 1))
@@ -125,12 +132,23 @@ def test_golden_fixture(fixture, precision):
             assert np.array_equal(zsym[0], g[f'z_sym{j}'])                    # integer path: exact
             z_hat = ops.eb_dequantize(torch.from_numpy(zsym).cuda(), m.entropy_bottleneck.device_params())
             idx = GaussianConditional(m.hyper_synthesis_transform(z_hat), m.scale_table).indexes()
-            ok = np.array_equal(idx[0].cpu().numpy(), g[f'idx{j}'])
+            idx_diff = idx[0].cpu().numpy() != g[f'idx{j}']
+            assert idx_diff.mean() <= 2e-3
+            ok = not idx_diff.any()
+            gidx = g[f'idx{j}'].astype(np.int32).reshape(-1)
+            ysym = ops.range_decode([strs[0]], np.array([0, gidx.size], np.int64), gaussian_tables(m.scale_table), indexes=gidx, threads=1)
+            assert np.array_equal(ysym.reshape(g[f'y_sym{j}'].shape), g[f'y_sym{j}'])
+            y_hat = torch.from_numpy(g[f'y_sym{j}'][None]).float().cuda()
+            thr = torch.from_numpy(threshold_f32(m.thresholds, np.full(1, 128))).cuda()
+            _, bits, _ = m.synthesis_transform.packed(y_hat, thr, want_f32=False)
+            pts = ops.bits_to_points(bits.cpu().numpy(), (size, size, size), 1)[0]
+            assert (_as_set(g[f'points{j}']) ^ _as_set(pts)) <= _as_set(g[f'fragile{j}']), f'block {j} (stage-wise decode)'
         if ok:
             data.append((strs, 128))
             keep.append(j)
-    if precision == 'fp32':
-        assert len(keep) >= nb - 1, 'fp32 kernels should reproduce the oracle indexes'
+    # the end-to-end decoder must run on the oracle's strings for (nearly) every block, in the default precision too
+    assert len(keep) >= (nb - 1 if precision == 'fp32' else max(1, int(0.9 * nb)) if nb > 1 else 0), \
+        f'{len(keep)}/{nb} blocks reproduce every scale index of the oracle'
     m.decompress()
     dec, _ = m.decompress_blocks(None, data, (size, size, size)) if data else ([], [])
     for j, pts in zip(keep, dec):
