@@ -168,3 +168,62 @@ def unbounded_index_range_decode(data, indexes, cdf, cdf_length, offset, precisi
                 value += max_value
         out[i] = value + int(offset[idx])
     return out.reshape(indexes.shape)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the same coder in plain C (oracle/range_coder_c.c, built by oracle/build.py): lets the CPU baseline of bench.py and the
+# tests code full-size blocks in milliseconds WITHOUT loading the product library.  Pinned against the Python statements
+# above byte for byte (tests/test_range_coder.py).
+# ---------------------------------------------------------------------------------------------------------
+_clib = [None]
+
+
+def _c():
+    if _clib[0] is None:
+        import ctypes
+        from . import build as B
+        lib = ctypes.CDLL(B.build())
+        i64, p = ctypes.c_int64, ctypes.c_void_p
+        lib.oracle_rc_encode.restype = i64
+        lib.oracle_rc_encode.argtypes = [p, p, i64, p, i64, p, p, i64, p, i64]
+        lib.oracle_rc_decode.restype = ctypes.c_int
+        lib.oracle_rc_decode.argtypes = [p, i64, p, i64, p, i64, p, p, i64, p]
+        _clib[0] = lib
+    return _clib[0]
+
+
+def _tab(cdf, cdf_length, offset):
+    cdf = np.ascontiguousarray(cdf, np.int32)
+    return cdf, np.ascontiguousarray(cdf_length, np.int32), np.ascontiguousarray(offset, np.int32)
+
+
+def encode_c(symbols, indexes, cdf, cdf_length, offset):
+    """unbounded_index_range_encode through the C restatement -> bytes."""
+    sym = np.ascontiguousarray(np.asarray(symbols).reshape(-1), np.int32)
+    idx = np.ascontiguousarray(np.asarray(indexes).reshape(-1), np.int32)
+    assert sym.size == idx.size
+    cdf, cl, off = _tab(cdf, cdf_length, offset)
+    cap = 2 * sym.size + 64
+    while True:
+        out = np.empty(cap, np.uint8)
+        n = _c().oracle_rc_encode(sym.ctypes.data, idx.ctypes.data, sym.size, cdf.ctypes.data, cdf.shape[1], cl.ctypes.data,
+                                  off.ctypes.data, cdf.shape[0], out.ctypes.data, cap)
+        if n < 0:
+            raise ValueError('table index out of range')
+        if n <= cap:
+            return out[:n].tobytes()
+        cap = int(n) + 8
+
+
+def decode_c(data, indexes, cdf, cdf_length, offset):
+    """unbounded_index_range_decode through the C restatement -> int32 array shaped like indexes."""
+    indexes = np.asarray(indexes)
+    idx = np.ascontiguousarray(indexes.reshape(-1), np.int32)
+    cdf, cl, off = _tab(cdf, cdf_length, offset)
+    buf = np.frombuffer(bytes(data) + b'\x00', np.uint8)
+    out = np.empty(idx.size, np.int32)
+    rc = _c().oracle_rc_decode(buf.ctypes.data, len(data), idx.ctypes.data, idx.size, cdf.ctypes.data, cdf.shape[1], cl.ctypes.data,
+                               off.ctypes.data, cdf.shape[0], out.ctypes.data)
+    if rc != 0:
+        raise ValueError(f'oracle_rc_decode failed ({rc})')
+    return out.reshape(indexes.shape)

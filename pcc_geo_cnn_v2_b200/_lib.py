@@ -68,6 +68,9 @@ SIGNATURES = {
 }
 
 
+PCCGEO_OK, PCCGEO_EINVAL, PCCGEO_ECUDA, PCCGEO_ENOSPC = 0, -1, -2, -3   # include/pccgeo.h
+
+
 class PccGeoError(RuntimeError):
     pass
 

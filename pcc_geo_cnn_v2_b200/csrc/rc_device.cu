@@ -109,19 +109,23 @@ __host__ __device__ __forceinline__ int32_t rc_enc_finish(RcEnc& s) {
   while (p >= 1 && s.out[p] == 0) --p;
   return (int32_t)p;
 }
-// symbol -> (lf, ov); false when the table index is out of range
-__host__ __device__ __forceinline__ bool rc_map_symbol(int32_t sym, int row, const int32_t* cdf, int cdf_stride, const int32_t* cdf_length,
+// symbol -> (lf, ov); 0 = ok, 1 = table index out of range, 2 = the escape value does not fit the 32-bit `ov` word (|value| of the
+// order of 2^31: the host coder carries 64 bits there; callers send such a latent through the host coder -- same bytes)
+__host__ __device__ __forceinline__ int rc_map_symbol(int32_t sym, int row, const int32_t* cdf, int cdf_stride, const int32_t* cdf_length,
                                                        const int32_t* offset, int rows, uint32_t& lf, uint32_t& ov) {
   lf = 0; ov = 0;
-  if (row < 0 || row >= rows) return false;
+  if (row < 0 || row >= rows) return 1;
   const int32_t* r = cdf + (long long)row * cdf_stride;
   const int32_t max_value = cdf_length[row] - 2;
   long long value = (long long)sym - offset[row];
-  if (value < 0) { ov = (uint32_t)(-2 * value - 1) + 1u; value = max_value; }
-  else if (value >= max_value) { ov = (uint32_t)(2 * (value - max_value)) + 1u; value = max_value; }
+  unsigned long long wide = 0;
+  if (value < 0) { wide = (unsigned long long)(-2 * value - 1) + 1ull; value = max_value; }
+  else if (value >= max_value) { wide = (unsigned long long)(2 * (value - max_value)) + 1ull; value = max_value; }
+  if (wide > 0xffffffffull) return 2;
+  ov = (uint32_t)wide;
   const uint32_t lo = (uint32_t)r[value], hi = (uint32_t)r[value + 1];
   lf = lo | ((hi - lo - 1) << 16);
-  return true;
+  return 0;
 }
 
 // row of symbol i: indexes[i] (mode 0) or (position in stream / channel_stride) % rows (mode 1: one table per channel)
@@ -132,7 +136,8 @@ __global__ void rc_map_kernel(const int32_t* __restrict__ sym, const int32_t* __
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const int row = index_mode == 0 ? indexes[i] : (int)(((i % per_stream) / channel_stride) % rows);
     uint32_t a, b;
-    if (!rc_map_symbol(sym[i], row, cdf, cdf_stride, cdf_length, offset, rows, a, b)) *err = 1;
+    const int rc = rc_map_symbol(sym[i], row, cdf, cdf_stride, cdf_length, offset, rows, a, b);
+    if (rc) atomicOr(err, rc);
     lf[i] = a;
     ovf[i] = b;
   }
@@ -465,9 +470,10 @@ extern "C" int pccgeo_range_encode_emulate_host(const int32_t* symbols, const in
       const long long g = (long long)s * per_stream + i;
       const int row = index_mode == 0 ? indexes[g] : (int)((i / channel_stride) % rows);
       uint32_t lf, ov;
-      if (!rc_map_symbol(symbols[g], row, cdf, cdf_stride, cdf_length, offset, rows, lf, ov)) {
+      if (const int rc = rc_map_symbol(symbols[g], row, cdf, cdf_stride, cdf_length, offset, rows, lf, ov)) {
         free(buf);
-        set_error("range_encode_emulate: table index out of range");
+        set_error(rc == 1 ? "range_encode_emulate: table index out of range"
+                          : "range_encode_emulate: escape value beyond 32 bits (host coder only)");
         return PCCGEO_EINVAL;
       }
       rc_enc_symbol(e, lf, ov);

@@ -316,8 +316,16 @@ class CompressionModel:
     def transforms(self):
         raise NotImplementedError
 
+    def _sync_trainer(self):
+        """After train_op steps the trained conv weights live in the trainer's device buffers; bring the layer objects up to
+        date before anything else reads them (validation forward, get_weights, the codec loops)."""
+        tr = getattr(self, 'trainer', None)
+        if tr is not None and tr.dirty:
+            tr.sync_to_model()
+
     def get_weights(self):
         """{'analysis': [...], 'synthesis': [...], ['hyper_*': ...], 'entropy_bottleneck': {...}} (Keras layouts)."""
+        self._sync_trainer()
         w = {k: t.get_weights() for k, t in self.transforms().items()}
         w['entropy_bottleneck'] = self.entropy_bottleneck.get_weights()
         return w
@@ -326,6 +334,7 @@ class CompressionModel:
         for k, t in self.transforms().items():
             t.set_weights(w[k])
         self.entropy_bottleneck.set_weights(w['entropy_bottleneck'])
+        self.trainer = None   # optimiser state belongs to the replaced variables
 
     # -- batched device passes (implemented by V1 / V2) ----------------------------------------------
     def _encode_device(self, x):
@@ -387,7 +396,10 @@ class CompressionModel:
     def _pool(self):
         if getattr(self, '_executor', None) is None:
             from concurrent.futures import ThreadPoolExecutor
-            self._executor = ThreadPoolExecutor(max_workers=max(1, self.pipeline_depth), thread_name_prefix='pccgeo-host')
+            # pool threads do not inherit the caller's CUDA device: without the initializer their streams / events / copies
+            # would be created on device 0 whatever GPU this rank drives
+            self._executor = ThreadPoolExecutor(max_workers=max(1, self.pipeline_depth), thread_name_prefix='pccgeo-host',
+                                                initializer=torch.cuda.set_device, initargs=(torch.cuda.current_device(),))
         return self._executor
 
     @staticmethod
@@ -464,6 +476,7 @@ class CompressionModel:
         Returns (strings per block, x_hat fp32 CUDA (n,1,D,H,W) or None, points per block or None).
         thr_idx (n,) fixes the per-block threshold so that clip/threshold/bit-pack (fused into the last synthesis layer) and
         the point extraction ride in the same pipelined pass (compress_blocks with fixed_threshold)."""
+        self._sync_trainer()
         dims = [int(s) for s in (x_shape if x_shape is not None else self.x_shape)][-3:]
         spans = [(i, min(i + self.batch_size, len(blocks))) for i in range(0, len(blocks), self.batch_size)]
         pool = self._pool()
@@ -570,6 +583,7 @@ class CompressionModel:
 
     def decompress_blocks(self, sess, blocks, x_shape, debug=False):
         """src/model_types.py:220-238: blocks = [(strings, threshold_idx)] -> ([float32 (m,3)], debug list)."""
+        self._sync_trainer()
         dims = tuple(int(s) for s in x_shape)[-3:]
         chunks = self._chunks(list(blocks))
         pool = self._pool()
@@ -668,15 +682,16 @@ class CompressionModel:
         """Host worker: byte ranges of a coded group -> per-block tuples of bytes.  The (rare) stream that outgrew the device
         buffer sends its latent through the host coder (same bytes)."""
         per_latent = []
-        side = self._worker_stream()
         for (packed, pend), l in zip(coded, lats):
+            side = self._worker_stream(packed.device)
             lengths, offsets, err = self._wait(pend)
-            lengths, offsets, bad = lengths.copy(), offsets.copy(), bool(err[0])
+            lengths, offsets, bad = lengths.copy(), offsets.copy(), int(err[0])
             self._release(pend)
-            if bad:
+            if bad & 1:
                 raise PccGeoError('range_encode_device: table index out of range')
             total = int(offsets[-1])
-            if (lengths < 0).any() or total > packed.numel():
+            # bad & 2: an escape value beyond the device coder's 32-bit word (|value| ~ 2^31) -> host coder, same bytes
+            if (bad & 2) or (lengths < 0).any() or total > packed.numel():
                 sym = big[l['sym']].cpu().numpy()
                 offs = np.arange(n + 1, dtype=np.int64) * int(np.prod(l['shape']))
                 if l['idx'] is not None:
@@ -687,21 +702,29 @@ class CompressionModel:
                                                        channel_stride=int(np.prod(l['shape'][1:])), threads=self.coder_threads))
                 continue
             buf = _pinned.get(max(total, 1))
-            with torch.cuda.stream(side):   # the exact byte count is only known now: second, tight copy from this worker
+            with torch.cuda.device(packed.device), torch.cuda.stream(side):
+                # the exact byte count is only known now: second, tight copy from this worker, on a stream of the tensor's
+                # own device (a stream of another device would leave the copy on that device's default stream)
                 buf[:total].copy_(packed[:total], non_blocking=True)
-            side.synchronize()
+                done = torch.cuda.Event()
+                done.record(side)
+            done.synchronize()
             view = memoryview(buf.numpy())
             offs = offsets.tolist()
             per_latent.append([bytes(view[offs[i]:offs[i + 1]]) for i in range(n)])
             _pinned.put(buf)
         return list(zip(*per_latent))
 
-    def _worker_stream(self):
+    def _worker_stream(self, device):
+        """A side stream of this worker thread ON `device` (one per thread and device)."""
         import threading
         tl = self.__dict__.setdefault('_tls', threading.local())
-        if getattr(tl, 'stream', None) is None:
-            tl.stream = torch.cuda.Stream()
-        return tl.stream
+        streams = tl.__dict__.setdefault('streams', {})
+        key = torch.device(device).index
+        if key not in streams:
+            with torch.cuda.device(device):
+                streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
 
     def _upload_strings(self, strings):
         """[bytes] -> (uint8 CUDA blob, int64 CUDA offsets (n+1)); the strings are gathered straight into pinned memory."""
@@ -841,6 +864,7 @@ class CompressionModel:
         from .training import Trainer
         if getattr(self, 'trainer', None) is None:
             self.trainer = Trainer(self, gamma, alpha, lmbda, tensor_cores=getattr(self, 'train_tensor_cores', False))
+        self.trainer.gamma, self.trainer.alpha, self.trainer.lmbda = gamma, alpha, lmbda
         self.train_op = self.trainer.step
         return mb
 
@@ -861,6 +885,7 @@ class CompressionModelV1(CompressionModel):
         return {'analysis': self.analysis_transform, 'synthesis': self.synthesis_transform}
 
     def train(self, x, gamma, alpha, lmbda, noise_y=None):  # model_types.py:250-281
+        self._sync_trainer()
         y = self.analysis_transform(x)
         y_tilde, _ = self.entropy_bottleneck(y, training=True, noise=noise_y)
         x_tilde = self.synthesis_transform(y_tilde)
@@ -958,6 +983,7 @@ class CompressionModelV2(CompressionModel):
                 'hyper_analysis': self.hyper_analysis_transform, 'hyper_synthesis': self.hyper_synthesis_transform}
 
     def train(self, x, gamma, alpha, lmbda, noise_y=None, noise_z=None):  # model_types.py:327-369
+        self._sync_trainer()
         y = self.analysis_transform(x)
         z = self.hyper_analysis_transform(y)
         z_tilde, _ = self.entropy_bottleneck(z, training=True, noise=noise_z)

@@ -359,12 +359,18 @@ def range_encode(symbols, sym_offsets, tables, indexes=None, channel_stride=0, t
     if indexes is not None:
         indexes = np.ascontiguousarray(indexes, np.int32)
     cap = int(symbols.size) * 4 + 64 * ns + 64
-    out = np.empty(cap, np.uint8)
     out_offs = np.zeros(ns + 1, np.int64)
     threads = threads or min(ns, os.cpu_count() or 1) or 1
-    L.check(L.lib().pccgeo_range_encode_host(L.ptr(symbols), L.ptr(indexes), L.ptr(offs), ns, L.ptr(cdf), cdf.shape[1],
-                                             L.ptr(cl), L.ptr(of), cdf.shape[0], mode, int(channel_stride),
-                                             L.ptr(out), cap, L.ptr(out_offs), threads), 'range_encode')
+    while True:
+        out = np.empty(cap, np.uint8)
+        rc = L.lib().pccgeo_range_encode_host(L.ptr(symbols), L.ptr(indexes), L.ptr(offs), ns, L.ptr(cdf), cdf.shape[1],
+                                              L.ptr(cl), L.ptr(of), cdf.shape[0], mode, int(channel_stride),
+                                              L.ptr(out), cap, L.ptr(out_offs), threads)
+        if rc == L.PCCGEO_ENOSPC and int(out_offs[-1]) > cap:
+            cap = int(out_offs[-1])   # escape-heavy streams (up to ~5 bytes per symbol): the call reports the size it needs
+            continue
+        L.check(rc, 'range_encode')
+        break
     view, o = memoryview(out), out_offs.tolist()
     return [bytes(view[o[i]:o[i + 1]]) for i in range(ns)]
 

@@ -69,6 +69,7 @@ class Trainer:
         self.traces = {k: trace(t, fuse_residual=False) for k, t in self.transforms.items()}
         self.params = {}   # layer -> dict(w, b, mw, vw, mb, vb) device fp32, tap-major weights
         self.t = 0
+        self.dirty = False  # the device master weights are ahead of the layer objects (set by step, cleared by sync_to_model)
         eb = model.entropy_bottleneck
         self._eb_arrays = lambda: eb.matrices + eb.biases + eb.factors
         self.eb_adam = None
@@ -88,7 +89,10 @@ class Trainer:
         return self.params[layer]
 
     def sync_to_model(self):
-        """Copy the trained device parameters back into the layers (Keras layouts) so the codec path sees them."""
+        """Copy the trained device parameters back into the layers (Keras layouts) so that the model's own forward
+        (validation `train()`), `get_weights()` and the codec path see them.  The model calls this lazily whenever it is used
+        after a step (CompressionModel._sync_trainer), the way the reference's variables are simply shared by every graph."""
+        self.dirty = False
         for layer, p in self.params.items():
             w = p['w'].cpu().numpy().reshape(layer.k, layer.k, layer.k, layer.in_channels, layer.filters)
             if layer.transposed:
@@ -308,4 +312,5 @@ class Trainer:
         eb.updates[0]()                                   # entropy_bottleneck.updates[0]: refresh the quantised CDFs
         values['aux_loss'] = aux
         values['step'] = self.t
+        self.dirty = True
         return values

@@ -13,7 +13,7 @@ import torch
 
 from oracle import entropy as E
 from oracle import transforms as T
-from oracle.model import CONFIGS, focal_loss as oracle_focal_loss, sparse_to_dense
+from oracle.model import CONFIGS, OracleModel, focal_loss as oracle_focal_loss, sparse_to_dense
 from pcc_geo_cnn_v2_b200 import ops, synthetic
 from pcc_geo_cnn_v2_b200.model_configs import ModelConfigType
 from pcc_geo_cnn_v2_b200.training import Trainer
@@ -204,3 +204,36 @@ def test_training_steps_reduce_the_loss_and_keep_the_codec_consistent():
     dec, _ = m.decompress_blocks(None, data[0], (32, 32, 32))
     for a, b in zip(meta[0]['x_hat_list'], dec):
         assert np.array_equal(a, b)
+
+
+def test_train_op_weights_are_visible_to_the_model_without_manual_sync():
+    """tr_train.py flow (tr_train.py:91-134): m.train(...) builds the graph, m.train_op(x) steps it, and the SAME variables are
+    then read by the validation forward, by get_weights() (checkpoint) and by the codec loops -- no explicit sync call."""
+    m = ModelConfigType['c3p'].build()
+    m.set_weights(synthetic.trained_like_weights(m, seed=5))
+    blocks = synthetic.surface_blocks(4, size=32, seed=2)
+    x = torch.from_numpy(np.concatenate([sparse_to_dense(b, (1, 1, 32, 32, 32)) for b in blocks])).cuda()
+    g = torch.Generator(device='cuda').manual_seed(0)
+    ny = torch.rand((4, 64, 4, 4, 4), generator=g, device='cuda') - 0.5
+    nz = torch.rand((4, 64, 2, 2, 2), generator=g, device='cuda') - 0.5
+    m.train(x, 2, 0.75, 1e-2, noise_y=ny, noise_z=nz)
+    loss0 = float(m.train_loss)
+    w0 = m.get_weights()['synthesis'][0]['kernel'].copy()
+    out = [m.train_op(x, ny, nz) for _ in range(6)]
+    assert abs(out[0]['loss'] - loss0) < 1e-3 * abs(loss0)        # train_op's forward == the model's forward before any step
+    w1 = m.get_weights()['synthesis'][0]['kernel']
+    assert np.abs(w1 - w0).max() > 1e-5                             # get_weights() returns the trained variables
+    m.train(x, 2, 0.75, 1e-2, noise_y=ny, noise_z=nz)               # validation forward on the trained variables
+    nxt = m.train_op.__self__.forward_backward(x, ny, nz)[0]['loss']
+    assert abs(float(m.train_loss) - nxt) < 1e-3 * abs(nxt), (float(m.train_loss), nxt)
+    assert float(m.train_loss) < loss0
+    m.compress((1, 1, 32, 32, 32))                                  # and the codec loops run on them, encoder == decoder
+    data, meta, _ = m.compress_blocks(None, blocks, None, None, 32, 0, fixed_threshold=True)
+    dec, _ = m.decompress_blocks(None, data[0], (32, 32, 32))
+    for a, b in zip(meta[0]['x_hat_list'], dec):
+        assert np.array_equal(a, b)
+    o = OracleModel('c3p')
+    w = m.get_weights()
+    o.set_params({k: v for k, v in w.items() if k != 'entropy_bottleneck'}, w['entropy_bottleneck'])
+    ref = o.train_forward(x.cpu().numpy(), 2, 0.75, 1e-2, ny.cpu(), nz.cpu())
+    assert abs(float(m.train_loss) - float(ref['loss'])) < 1e-3 * abs(float(ref['loss']))

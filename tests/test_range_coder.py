@@ -151,3 +151,28 @@ def test_random_tables_property():
             assert ops.range_encode_emulate(sym, ns, tab, channel_stride=cs) == s2
 
     check()
+
+
+@pytest.mark.parametrize('n,spread', [(0, 1.0), (1, 1.0), (257, 1.0), (2000, 3.0), (500, 40.0), (3000, 1e6)])
+def test_c_oracle_matches_python_oracle(gc_tab, n, spread):
+    """oracle/range_coder_c.c (the coder of bench.py's CPU arm, independent of libpccgeo) == oracle/range_coder.py, byte for
+    byte and symbol for symbol, escapes of every width included; and == the product's host coder."""
+    rng = np.random.default_rng(n + 1)
+    sym, idx = _random_stream(rng, gc_tab, n, spread)
+    want = RC.unbounded_index_range_encode(sym, idx, gc_tab['cdf'], gc_tab['cdf_length'], gc_tab['offset'])
+    got = RC.encode_c(sym, idx, gc_tab['cdf'], gc_tab['cdf_length'], gc_tab['offset'])
+    assert got == want
+    assert np.array_equal(RC.decode_c(got, idx, gc_tab['cdf'], gc_tab['cdf_length'], gc_tab['offset']), sym)
+    assert ops.range_encode(sym, np.array([0, n], np.int64), gc_tab, indexes=idx, threads=1) == [want]
+    p = E.eb_init(6, np.random.default_rng(n))
+    tab = E.eb_tables(p)
+    zs = np.rint(rng.normal(size=(6, 5, 5, 5)) * 4 * spread ** 0.25).astype(np.int32)
+    cidx = np.broadcast_to(np.arange(6, dtype=np.int32).reshape(6, 1, 1, 1), zs.shape)
+    want = RC.unbounded_index_range_encode(zs, cidx, tab['cdf'], tab['cdf_length'], tab['offset'])
+    assert RC.encode_c(zs, cidx, tab['cdf'], tab['cdf_length'], tab['offset']) == want
+    assert np.array_equal(RC.decode_c(want, cidx, tab['cdf'], tab['cdf_length'], tab['offset']), zs)
+
+
+def test_c_oracle_rejects_bad_index(gc_tab):
+    with pytest.raises(ValueError):
+        RC.encode_c([0], [len(gc_tab['cdf_length'])], gc_tab['cdf'], gc_tab['cdf_length'], gc_tab['offset'])
