@@ -70,8 +70,8 @@ def get_normals_if(x, with_normals):  # model_types.py:117-118
 
 def input_fn(points, batch_size, dense_tensor_shape, data_format, repeat=True, shuffle=True, prefetch_size=1):
     """model_types.py:49-62 as a Python generator of (B, ...) fp32 CUDA batches: shuffle over the whole set every epoch
-    (numpy's global RNG, seeded by the caller like tr_train.py:20), repeat, batch (the last partial batch is kept, as
-    tf.data's batch()), and `prefetch_size` batches packed (C++ coordinate packer) ahead on a host thread."""
+    (numpy's global RNG, seeded by the caller like tr_train.py:20), repeat, then batch -- so with repeat=True batches span
+    epoch boundaries and are always full, and only without repeat the last batch is partial (tf.data's batch()) -- and `prefetch_size` batches packed (C++ coordinate packer) ahead on a host thread."""
     import queue
     import threading
     points = list(points)
@@ -80,12 +80,21 @@ def input_fn(points, batch_size, dense_tensor_shape, data_format, repeat=True, s
     dims = shape[:3] if last else shape[1:]
 
     def batches():
+        # shuffle(len) -> repeat -> batch: the element stream runs across epoch boundaries, so with repeat=True every batch is
+        # full (a batch may hold the tail of one epoch and the head of the next); without repeat the last batch is partial
+        pending = []
         while True:
             order = np.random.permutation(len(points)) if shuffle else np.arange(len(points))
-            for i in range(0, len(order), batch_size):
-                chunk = [np.asarray(points[j], np.float32) for j in order[i:i + batch_size]]
-                yield len(chunk), blocks_to_coords(chunk)
+            for j in order:
+                pending.append(np.asarray(points[j], np.float32))
+                if len(pending) == batch_size:
+                    yield len(pending), blocks_to_coords(pending)
+                    pending = []
             if not repeat:
+                if pending:
+                    yield len(pending), blocks_to_coords(pending)
+                return
+            if not len(points):
                 return
 
     q = queue.Queue(maxsize=max(1, int(prefetch_size)))
@@ -214,6 +223,36 @@ def threshold_f32(thresholds, idx):
     return t32.astype(np.float32)
 
 
+class GraphHandle:
+    """Stand-in for the TF placeholders / tensors the reference's builder methods leave on the model (m.x, m.x_hat, m.strings,
+    m.strings_t, m.x_shape_t; src/model_types.py:290-295,378-391,399-411).  There is no graph to feed: the block loops take the
+    data directly.  The handles carry what the scripts read from them -- the name and the static shape (compress_blocks uses
+    self.x.shape, model_types.py:194)."""
+
+    def __init__(self, name, shape=None, dtype='float32'):
+        self.name, self.shape, self.dtype = name, (None if shape is None else tuple(int(v) for v in shape)), dtype
+
+    def __repr__(self):
+        return f'<GraphHandle {self.name} shape={self.shape} dtype={self.dtype}>'
+
+
+def split_debug(batch_tensors, strings, static=None):
+    """{key: CUDA tensor with a leading batch axis} -> one dict of numpy arrays per block, each with batch axis 1 -- the
+    per-block `debug_tensors` a sess.run of the reference's batch-1 graph returns (model_types.py:198-199,229).  `strings`
+    (per block tuple of bytes) become the 'decompress/strings' entry of the Gaussian conditional's dbg_dec
+    (patch_gaussian_conditional.py:43-45); `static` entries (tables) are shared between the blocks."""
+    host = {k: v.detach().cpu().numpy() for k, v in batch_tensors.items() if v is not None}
+    n = len(strings)
+    out = []
+    for j in range(n):
+        d = {k: v[j:j + 1] for k, v in host.items()}
+        if static:
+            d.update(static)
+            d['decompress/strings'] = np.array([strings[j][0]], dtype=object)
+        out.append(d)
+    return out
+
+
 class _PinnedPool:
     """Recycled pinned host staging buffers.  cudaHostAlloc costs milliseconds and stalls the driver thread of the block
     loops (torch's caching host allocator falls back to it whenever every cached block still has a copy in flight), so
@@ -335,6 +374,16 @@ class CompressionModel:
             t.set_weights(w[k])
         self.entropy_bottleneck.set_weights(w['entropy_bottleneck'])
         self.trainer = None   # optimiser state belongs to the replaced variables
+
+    def load_weights(self, source):
+        """What `saver.restore(sess, checkpoint)` does in the reference's scripts (compress_octree.py:82-92): `source` is an
+        .npz path or a dict keyed by the TF variable names (weights_io.py documents the name map)."""
+        from . import weights_io
+        return weights_io.load_weights(self, source)
+
+    def save_weights(self, path):
+        from . import weights_io
+        weights_io.save_weights(self, path)
 
     # -- batched device passes (implemented by V1 / V2) ----------------------------------------------
     def _encode_device(self, x):
@@ -471,7 +520,7 @@ class CompressionModel:
         return self._copy_in(dst, a) if a.size else dst
 
     # -- public block loops --------------------------------------------------------------------------
-    def encode_blocks(self, blocks, x_shape=None, thr_idx=None, keep_x_hat=True):
+    def encode_blocks(self, blocks, x_shape=None, thr_idx=None, keep_x_hat=True, debug_out=None):
         """Batched analysis + entropy coding + synthesis.
         Returns (strings per block, x_hat fp32 CUDA (n,1,D,H,W) or None, points per block or None).
         thr_idx (n,) fixes the per-block threshold so that clip/threshold/bit-pack (fused into the last synthesis layer) and
@@ -491,8 +540,8 @@ class CompressionModel:
                 self._release(pend['bits'])
             return strings, pts
 
-        post_f, xs = [], []
-        graphs = self.use_graphs and thr_idx is not None and not keep_x_hat
+        post_f, xs, devs = [], [], []
+        graphs = self.use_graphs and thr_idx is not None and not keep_x_hat and debug_out is None
         if graphs and self.device_coder:
             return self._encode_blocks_device_coder(spans, coords_f, dims, thr_idx)
         for (a, b), cf in zip(spans, coords_f):
@@ -514,9 +563,14 @@ class CompressionModel:
             if thr_idx is not None:
                 pend['bits'] = self._d2h(dev['bits'])
             xs.append(dev.pop('x_hat'))
+            if debug_out is not None:
+                devs.append(dict(dev, x_hat=xs[-1]))
             post_f.append(pool.submit(post, dev, pend))
         res = [f.result() for f in post_f]
         strings = [s for r in res for s in r[0]]
+        if debug_out is not None:   # per-block dicts of the tensors decompress_octree.py:94-119 compares with the decoder's
+            for dev, r in zip(devs, res):
+                debug_out.extend(split_debug(self._debug_batch(dev), r[0], self._debug_static()))
         x_hat = None
         if keep_x_hat and xs:
             x_hat = torch.cat(xs) if len(xs) > 1 else xs[0]
@@ -526,26 +580,43 @@ class CompressionModel:
     def compress_blocks(self, sess, blocks, binstr, points, resolution, level, with_normals=False,
                         opt_metrics=('d1_mse',), max_deltas=(np.inf,), fixed_threshold=False, debug=False):
         """src/model_types.py:184-218.  Returns (data_list, metadata, debug_t_list)."""
+        loc = self.compress_blocks_local(blocks, resolution, with_normals, opt_metrics, max_deltas, fixed_threshold, debug)
+        threshold_list = [tuple(int(v) for v in loc['thr_idx'][:, m]) for m in range(loc['thr_idx'].shape[1])]
+        metadata = self._select_best(binstr, loc['x_hat_list'], level, loc['opt_metrics'], points, resolution, with_normals)
+        data_list = [list(zip(loc['strings'], threshold_list[x['idx']])) for x in metadata]
+        return data_list, metadata, loc['debug']
+
+    def compress_blocks_local(self, blocks, resolution, with_normals=False, opt_metrics=('d1_mse',), max_deltas=(np.inf,),
+                              fixed_threshold=False, debug=False):
+        """The per-block part of compress_blocks (model_types.py:192-212), without the whole-cloud selection that follows it:
+        -> {'strings': per block tuple of bytes, 'thr_idx': (n, n_metrics) threshold indexes, 'opt_metrics': names,
+            'x_hat_list': per metric a list of per-block float32 (m,3) points, 'debug': per-block debug dicts or None}.
+        A rank of a multi-GPU job runs this on its shard (sharding.compress_blocks_sharded)."""
         assert self.x_shape is not None, 'call compress(x_shape) first'
         n = len(blocks)
-        if fixed_threshold:
+        debug_t_list = [] if debug else [None] * n
+        if fixed_threshold and not debug:
             opt_metrics_ret = list(opt_metrics)
             thr_idx = np.full((n, len(opt_metrics_ret)), len(self.thresholds) // 2, np.int64)  # model_opt.py:27-31
             strings_list, _, pts = self.encode_blocks(blocks, thr_idx=thr_idx[:, 0], keep_x_hat=False)
             x_hat_list = [pts] * thr_idx.shape[1]  # every opt_metric gets the same fixed threshold
         else:
-            strings_list, x_hat, _ = self.encode_blocks(blocks)
-            thr_idx, opt_metrics_ret = self._optimal_thresholds(blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas)
+            # debug=True keeps every block's intermediate tensors (eager kernels, fp32 x_hat materialised): same bytes and points
+            strings_list, x_hat, _ = self.encode_blocks(blocks, debug_out=debug_t_list if debug else None)
+            if fixed_threshold or not n:
+                opt_metrics_ret = list(opt_metrics)
+                thr_idx = np.full((n, len(opt_metrics_ret)), len(self.thresholds) // 2, np.int64)
+            else:
+                thr_idx, opt_metrics_ret = self._optimal_thresholds(blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas)
             x_hat_list = []
-            for m in range(thr_idx.shape[1]):
+            for m in range(thr_idx.shape[1] if n else 0):
                 t = self._h2d(threshold_f32(self.thresholds, thr_idx[:, m]))
                 bits, _ = ops.threshold_pack(x_hat, t)
                 x_hat_list.append(ops.bits_to_points(bits.cpu().numpy(), tuple(x_hat.shape[2:]), self.coder_threads))
-        threshold_list = [tuple(int(v) for v in thr_idx[:, m]) for m in range(thr_idx.shape[1])]
-        metadata = self._select_best(binstr, x_hat_list, level, opt_metrics_ret, points, resolution, with_normals)
-        data_list = [list(zip(strings_list, threshold_list[x['idx']])) for x in metadata]
-        debug_t_list = [None] * n
-        return data_list, metadata, debug_t_list
+            if not n:
+                x_hat_list = [[] for _ in range(thr_idx.shape[1])]
+        return {'strings': strings_list, 'thr_idx': thr_idx, 'opt_metrics': opt_metrics_ret, 'x_hat_list': x_hat_list,
+                'debug': debug_t_list}
 
     def _optimal_thresholds(self, blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas):
         """Per-block threshold search (reference src/model_opt.py:21-77).  D1 metrics: every threshold's nearest-neighbour
@@ -617,7 +688,8 @@ class CompressionModel:
                     x_hat, dbg = self._decode_dev2(ctx, self._h2d(threshold_f32(self.thresholds, idx)), debug)
                 pend = self._d2h(dbg['bits'])
                 f4.append(pool.submit(self._points_task, pend, dims))
-                dbgs.append([dbg if debug else None] * len(chunk))
+                dbgs.append(split_debug(self._debug_batch(dbg), [c[0] for c in chunk], self._debug_static()) if debug
+                            else [None] * len(chunk))
         pts = [f.result() for f in f4]
         return [p for r in pts for p in r], [d for r in dbgs for d in r]
 
@@ -816,6 +888,13 @@ class CompressionModel:
             raise PccGeoError('range_decode_device: corrupt stream')
         return [p for r in pts for p in r], [None] * len(flat)
 
+    def _debug_batch(self, dev):
+        """The reference's debug_tensors of one batch (model_types.py:295,309): {key: CUDA tensor with a batch axis}."""
+        return {'y_hat': dev['y_hat'], 'x_hat': dev['x_hat']}
+
+    def _debug_static(self):
+        return None
+
     def _points_task(self, pend, dims):
         pts = ops.bits_to_points(self._wait(pend)[0], dims, self.coder_threads)
         self._release(pend)
@@ -894,9 +973,15 @@ class CompressionModelV1(CompressionModel):
 
     def compress(self, x_shape):  # model_types.py:283-295
         self.x_shape = tuple(int(s) for s in x_shape)
+        self.x, self.x_hat = GraphHandle('x', self.x_shape), GraphHandle('x_hat', self.x_shape)
+        self.strings = (GraphHandle('y_string', (self.x_shape[0],), 'string'),)
+        self.debug_tensors = {k: GraphHandle(k) for k in ('y_hat', 'x_hat')}
 
     def decompress(self):  # model_types.py:297-309
-        pass
+        self.strings_t = [GraphHandle('y_string', None, 'string')]
+        self.x_shape_t = GraphHandle('x_shape', (3,), 'int32')
+        self.x_hat = GraphHandle('x_hat')
+        self.debug_tensors = {k: GraphHandle(k) for k in ('y_hat', 'x_hat')}
 
     def _latents(self, x):
         y = self.analysis_transform(x)
@@ -922,8 +1007,7 @@ class CompressionModelV1(CompressionModel):
         if after_latents is not None:
             after_latents(dev)
         x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
-        self.x, self.x_hat = x, x_hat
-        self.debug_tensors = {'y_hat': y_hat, 'x_hat': x_hat}
+        self.last_x, self.last_x_hat = x, x_hat          # the most recent batch's tensors (CUDA), for interactive use
         dev['x_hat'], dev['bits'] = x_hat, bits
         return dev
 
@@ -953,7 +1037,7 @@ class CompressionModelV1(CompressionModel):
     def _decode_dev2(self, ctx, thresholds=None, want_x_hat=True):
         y_hat = ctx['y_hat']
         x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
-        self.x_hat = x_hat
+        self.last_x_hat = x_hat
         return x_hat, {'y_hat': y_hat, 'x_hat': x_hat, 'bits': bits}
 
 
@@ -998,9 +1082,15 @@ class CompressionModelV2(CompressionModel):
 
     def compress(self, x_shape):  # model_types.py:371-391
         self.x_shape = tuple(int(s) for s in x_shape)
+        self.x, self.x_hat = GraphHandle('x', self.x_shape), GraphHandle('x_hat', self.x_shape)
+        self.strings = tuple(GraphHandle(k, (self.x_shape[0],), 'string') for k in ('y_string', 'z_string'))
+        self.debug_tensors = {k: GraphHandle(k) for k in ('z_hat', 'sigma_hat', 'decompress/indexes', 'decompress/symbols', 'y_hat', 'x_hat')}
 
     def decompress(self):  # model_types.py:393-411
-        pass
+        self.strings_t = [GraphHandle(k, None, 'string') for k in ('y_string', 'z_string')]
+        self.x_shape_t = GraphHandle('x_shape', (3,), 'int32')
+        self.x_hat = GraphHandle('x_hat')
+        self.debug_tensors = {k: GraphHandle(k) for k in ('z_hat', 'sigma_hat', 'decompress/indexes', 'decompress/symbols', 'y_hat', 'x_hat')}
 
     def _latents(self, x):
         y = self.analysis_transform(x)
@@ -1032,10 +1122,22 @@ class CompressionModelV2(CompressionModel):
         if after_latents is not None:
             after_latents(dev)
         x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
-        self.x, self.x_hat = x, x_hat
-        self.debug_tensors = {'z_hat': z_hat, 'sigma_hat': sigma_hat, 'indexes': idx, 'y_hat': y_hat, 'x_hat': x_hat}
+        self.last_x, self.last_x_hat = x, x_hat
         dev['x_hat'], dev['bits'] = x_hat, bits
         return dev
+
+    def _debug_batch(self, dev):
+        """model_types.py:390-391,410-411: z_hat, sigma_hat, the Gaussian conditional's dbg_dec, y_hat, x_hat."""
+        return {'z_hat': dev['z_hat'], 'sigma_hat': dev['sigma_hat'], 'decompress/build/_scale': dev['sigma_hat'],
+                'decompress/build/_indexes': dev['indexes'], 'decompress/indexes': dev['indexes'],
+                'decompress/symbols': dev['y_hat'].to(torch.int32), 'decompress/outputs': dev['y_hat'],
+                'y_hat': dev['y_hat'], 'x_hat': dev['x_hat']}
+
+    def _debug_static(self):
+        t = gaussian_tables(self.scale_table)
+        return {'decompress/build/scale_table': self.scale_table, 'decompress/build/_quantized_cdf': t['cdf'],
+                'decompress/quantized_cdf': t['cdf'], 'decompress/build/_cdf_length': t['cdf_length'],
+                'decompress/build/_offset': t['offset'], 'decompress/build/fill': np.int32(len(self.scale_table) - 1)}
 
     @staticmethod
     def _latent_tensors(dev):
@@ -1070,7 +1172,7 @@ class CompressionModelV2(CompressionModel):
     def _decode_dev2(self, ctx, thresholds=None, want_x_hat=True):
         y_hat = ops.i32_to_f32(self._h2d(ctx['ysym']))
         x_hat, bits = self._synthesize(y_hat, thresholds, want_x_hat)
-        self.x_hat = x_hat
+        self.last_x_hat = x_hat
         return x_hat, {'z_hat': ctx['z_hat'], 'sigma_hat': ctx['sigma_hat'], 'indexes': ctx['indexes'], 'y_hat': y_hat,
                        'x_hat': x_hat, 'bits': bits}
 

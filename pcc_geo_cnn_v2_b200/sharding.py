@@ -104,13 +104,38 @@ def gather_block_data(local_block_data, group=None, device=None, dst=None):
     return out
 
 
-def compress_blocks_sharded(model, blocks, **kwargs):
-    """model.compress_blocks over this rank's shard + gather: returns the full data_list[0] on every rank."""
-    rank, world = dist.get_rank(), dist.get_world_size()
+def merge_local_results(parts):
+    """Rank-ordered per-shard results of CompressionModel.compress_blocks_local -> the same dict for the whole block list."""
+    parts = [p for p in parts if p is not None]
+    nm = max((p['thr_idx'].shape[1] for p in parts), default=1)
+    names = next((p['opt_metrics'] for p in parts if len(p['strings'])), parts[0]['opt_metrics'] if parts else [])
+    return {'strings': [s for p in parts for s in p['strings']],
+            'thr_idx': np.concatenate([p['thr_idx'].reshape(-1, nm) for p in parts]) if parts else np.zeros((0, nm), np.int64),
+            'opt_metrics': list(names),
+            'x_hat_list': [[q for p in parts for q in p['x_hat_list'][m]] for m in range(nm)]}
+
+
+def compress_blocks_sharded(model, blocks, binstr=None, points=None, resolution=0, level=0, with_normals=False,
+                            opt_metrics=('d1_mse',), max_deltas=(np.inf,), fixed_threshold=False, dst=0, group=None):
+    """CompressionModel.compress_blocks (reference src/model_types.py:184-218) over all ranks: every rank runs the per-block part
+    on its contiguous shard of the Morton-ordered block list (networks, entropy coding, per-block threshold search for
+    fixed_threshold=False), and rank `dst` alone runs what needs the whole cloud -- select_best_per_opt_metric
+    (model_types.py:128-176) -- on the gathered results.  Returns (data_list, metadata) on rank dst, (None, None) elsewhere.
+    Exchange: without points/binstr (block-level callers) only the byte strings + threshold indexes travel
+    (gather_block_data); with them also the per-metric threshold table and decoded points (all_gather_object)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
     b, e = shard_range(len(blocks), rank, world)
-    local = []
-    if e > b:
-        data_list, _, _ = model.compress_blocks(None, blocks[b:e], None, None, kwargs.pop('resolution', 0), kwargs.pop('level', 0),
-                                                fixed_threshold=True, **kwargs)
-        local = data_list[0]
-    return gather_block_data(local)
+    loc = model.compress_blocks_local(blocks[b:e], resolution, with_normals, opt_metrics, max_deltas, fixed_threshold)
+    if points is None or binstr is None:
+        data = gather_block_data(list(zip(loc['strings'], [int(v) for v in loc['thr_idx'][:, 0]])), group=group, dst=dst)
+        if data is None:
+            return None, None
+        return [data], [{'idx': 0, 'metrics': {}, 'x_hat_list': None, 'blocks_depart': None, 'blocks_full': None}]
+    parts = [None] * world
+    dist.all_gather_object(parts, {k: loc[k] for k in ('strings', 'thr_idx', 'opt_metrics', 'x_hat_list')}, group=group)
+    if rank != dst:
+        return None, None
+    full = merge_local_results(parts)
+    threshold_list = [tuple(int(v) for v in full['thr_idx'][:, m]) for m in range(full['thr_idx'].shape[1])]
+    metadata = model._select_best(binstr, full['x_hat_list'], level, full['opt_metrics'], points, resolution, with_normals)
+    return [list(zip(full['strings'], threshold_list[x['idx']])) for x in metadata], metadata

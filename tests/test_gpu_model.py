@@ -246,8 +246,10 @@ def test_training_host_glue_matches_reference_semantics():
     sums = [float(b.sum()) for b in got]
     assert sums == [float(len(pts[order[0]]) + len(pts[order[1]])), float(len(pts[order[2]]) + len(pts[order[3]])), float(len(pts[order[4]]))]
     it = MT.input_fn(pts, 3, (1, 16, 16, 16), 'channels_first', repeat=True, shuffle=False)
-    first_epoch = [next(it) for _ in range(2)]
-    assert float(next(it).sum()) == float(first_epoch[0].sum())   # repeats from the start
+    got = [next(it) for _ in range(3)]   # shuffle -> repeat -> batch: batches are always full and span the epoch boundary
+    assert [tuple(b.shape) for b in got] == [(3, 1, 16, 16, 16)] * 3
+    ln = [len(p) for p in pts]
+    assert [float(b.sum()) for b in got] == [float(ln[0] + ln[1] + ln[2]), float(ln[3] + ln[4] + ln[0]), float(ln[1] + ln[2] + ln[3])]
     x = torch.tensor([[-0.2, 0.4, 0.5, 0.51, 1.7]], device='cuda')
     assert MT.quantize_tensor(x).tolist() == [[0, 0, 0, 1, 1]]
     xq = torch.tensor([1, 1, 0, 0, 1, 0], device='cuda', dtype=torch.uint8)
@@ -255,3 +257,40 @@ def test_training_host_glue_matches_reference_semantics():
     bc = MT.binary_classification_summaries(xq, xt)
     assert abs(float(bc['bc/precision']) - 2 / 3) < 1e-12 and abs(float(bc['bc/recall']) - 2 / 3) < 1e-12
     assert abs(float(bc['bc/accuracy']) - 4 / 6) < 1e-12 and abs(float(bc['bc/specificity']) - 2 / 3) < 1e-12
+
+
+@pytest.mark.parametrize('config,size,bias', [('c3p', 64, -0.7), ('c1', 32, 0.4)])
+def test_debug_contract_of_decompress_octree(config, size, bias):
+    """compress_octree.py --debug saves the encoder's per-block debug tensors and decoded blocks; decompress_octree.py --debug
+    (decompress_octree.py:64-131) re-decodes and requires, key by key, the decoder's debug tensors to match the encoder's
+    (numbers: atol 1e-3 / rtol 1e-7 via assert_allclose; objects: equality) and the decoded blocks to be equal."""
+    m = _model(config, 7, output_bias=bias)
+    m.batch_size = 3
+    blocks = synthetic.surface_blocks(5, size=size, seed=12)
+    m.compress((1, 1, size, size, size))
+    assert m.x.shape == (1, 1, size, size, size) and len(m.strings) == (2 if config == 'c3p' else 1)
+    data_list, meta, dbg_enc = m.compress_blocks(None, blocks, None, None, size, 0, fixed_threshold=True, debug=True)
+    plain, meta_plain, dbg_none = m.compress_blocks(None, blocks, None, None, size, 0, fixed_threshold=True, debug=False)
+    assert dbg_none == [None] * len(blocks)
+    assert [d[0] for d in plain[0]] == [d[0] for d in data_list[0]]          # debug mode changes neither bytes nor points
+    assert all(np.array_equal(a, b) for a, b in zip(meta[0]['x_hat_list'], meta_plain[0]['x_hat_list']))
+    m.decompress()
+    assert m.x_shape_t.shape == (3,) and len(m.strings_t) == len(m.strings)
+    dec, dbg_dec = m.decompress_blocks(None, data_list[0], (size, size, size), debug=True)
+    assert len(dbg_enc) == len(dbg_dec) == len(blocks)
+    want_keys = {'y_hat', 'x_hat'} | ({'z_hat', 'sigma_hat', 'decompress/indexes', 'decompress/symbols', 'decompress/outputs',
+                                       'decompress/strings', 'decompress/build/scale_table', 'decompress/quantized_cdf'}
+                                      if config == 'c3p' else set())
+    for j, (de, dd) in enumerate(zip(dbg_enc, dbg_dec)):
+        assert want_keys <= set(dd) and set(dd) == set(de)
+        for key in dd:                                                       # the loop of decompress_octree.py:94-119
+            v1, v2 = np.asarray(dd[key]), np.asarray(de[key])
+            if v1.dtype == object:
+                np.testing.assert_equal(v1, v2, err_msg=f'Values did not match for key {key}')
+            else:
+                assert np.issubdtype(v1.dtype, np.number)
+                np.testing.assert_allclose(v1, v2, rtol=1e-7, atol=0.001, err_msg=f'Values did not match for key {key}')
+        assert dd['x_hat'].shape == (1, 1, size, size, size) and dd['y_hat'].shape[0] == 1
+        np.testing.assert_equal(dec[j], meta[0]['x_hat_list'][j])
+        # the debug x_hat is the tensor the points come from
+        assert np.array_equal(np.argwhere(np.clip(dd['x_hat'][0, 0], 0, 1) > m.thresholds[128]).astype(np.float32), dec[j])
