@@ -511,6 +511,26 @@ def run_steps(steps, out_id, x, pack=None, keep=None, extra=None):
     return y
 
 
+def layer_runner(layer, xb, in_shape, terms, residual_b=None):
+    """(callable, kernel name) running ONE conv layer on a blocked bf16 input into a preallocated blocked output through the same
+    kernel dispatch as run_steps -- what bench.py times alone for the roofline of the dominant layer."""
+    if layer.ys_eligible(in_shape):
+        out, _ = ops.conv3d_umma_ys(xb, in_shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'), layer.filters, layer.relu, terms, residual_b)
+        return (lambda: ops.conv3d_umma_ys(xb, in_shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'), layer.filters, layer.relu, terms,
+                                           residual_b, out)), 'conv3d_umma_ys_kernel'
+    if layer.umma_eligible(in_shape):
+        out, _ = ops.conv3d_umma(xb, in_shape, layer.dev(f'w_umma{terms}'), layer.dev('bias'), layer.filters, layer.stride, layer.transposed,
+                                 layer.relu, terms, residual_b)
+        return (lambda: ops.conv3d_umma(xb, in_shape, layer.dev(f'w_umma{terms}'), layer.dev('bias'), layer.filters, layer.stride,
+                                        layer.transposed, layer.relu, terms, residual_b, out)), f'conv3d_umma_kernel<{ops.round_up(layer.filters, 16)}>'
+    if layer.gemm_eligible(in_shape):
+        out, _ = ops.conv3d_gemm(xb, in_shape, layer.dev(f'w_gemm{terms}'), layer.dev('bias'), layer.filters, layer.stride, layer.transposed,
+                                 layer.relu, terms, residual_b)
+        return (lambda: ops.conv3d_gemm(xb, in_shape, layer.dev(f'w_gemm{terms}'), layer.dev('bias'), layer.filters, layer.stride,
+                                        layer.transposed, layer.relu, terms, residual_b, out)), 'conv3d_gemm_kernel'
+    raise ValueError('layer is not served by a tensor-core kernel')
+
+
 def run_layer(layer, x, residual=None):
     """One conv layer (fp32 in / fp32 out) through the same kernel dispatch as a transform; residual is added in the epilogue."""
     steps = [('conv', layer, 0, 1, 2 if residual is not None else None)]

@@ -349,6 +349,7 @@ class CompressionModel:
         self.device_coder = env == '1' if env in ('0', '1') else cores < 16
         self.coder_group_blocks = 1024
         self.coder_overlap = False
+        self.symbol_bytes = self.index_bytes = 4   # width of the symbols / scale indexes that cross PCIe with the host coder
         self._graphs, self._statics, self._graph_epoch = {}, {}, -1
 
     # -- weights -------------------------------------------------------------------------------------
