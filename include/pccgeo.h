@@ -82,6 +82,15 @@ int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, c
                        void* yb, int n, int cin, int d, int h, int wd, int cout, int stride, int transposed,
                        int relu, int terms, void* stream);
 
+/* hi/lo-stacked variant of pccgeo_conv3d_umma for the stride-1 3x3x3 layers with <= 16 input and output channels in two-term
+ * (bf16x3-class) precision -- the second and third layer of AnalysisBlock / SynthesisBlock at 16 filters
+ * (src/model_transforms.py:62-81), the dominant layers of the c3p synthesis transform: the bf16 hi and lo halves of the weights
+ * are stacked in the MMA N dimension next to the three z-taps (N = 96), so each tap costs two MMAs (a_hi, a_lo) instead of
+ * three; all four partial products are accumulated.  Same tensors as pccgeo_conv3d_umma(terms = 2); own weight image. */
+long long pccgeo_umma_hl_pack_weights_host(const float* w_host, void* wpacked_host, int cin, int cout, int transposed);
+int pccgeo_conv3d_umma_hl(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
+                          int n, int cin, int d, int h, int wd, int cout, int transposed, int relu, void* stream);
+
 /* y-stacked variant of pccgeo_conv3d_umma for stride-1 3x3x3 layers with <= 16 input and output channels (the second and
  * third layer of AnalysisBlock / SynthesisBlock at 16 filters, src/model_transforms.py:62-81): z AND y taps are stacked in
  * the MMA N dimension (3 MMAs of N=144 per input plane and precision pair instead of 9 of N=48); the epilogue adds the

@@ -65,6 +65,7 @@ struct UmmaConvParams {
   int ytiles, xtiles, items;
   int nstage, nslots, slot_shift;
   int wbytes_term;       // bytes of one precision term of the weight image
+  int wterms;            // precision terms of the weight image (HL mode: 1 -- hi and lo weights sit side by side in N)
   int swap;              // debug: swap LBO/SBO roles
   long long term_stride_out;  // elements between precision terms of y / res
 };
@@ -84,15 +85,20 @@ static_assert(sizeof(SmemHeader) <= HEADER_BYTES, "header too large");
 template <int COUT, int KC, int UP>
 constexpr int umma_ctas_per_sm() { return (UP == 1 && COUT == 16 && KC == 1) ? 2 : 1; }
 
-template <int COUT, int TERMS, int KC, int UP>
+// HL = 1 (COUT = 16, TERMS = 2, stride 1): the hi and lo halves of the weights are stacked in N next to the z-taps, so one
+// MMA of N = 96 per activation term does the work of two of N = 48: per tap a_hi x [w_hi|w_lo] and a_lo x [w_hi|w_lo] (the
+// fourth product a_lo*w_lo comes for free and only adds accuracy).  An output plane's slot holds two accumulators
+// (x*w_hi | x*w_lo) that the epilogue adds.  18 MMAs per plane instead of 27: fewer A-operand fetches, the bound of small-N MMAs.
+template <int COUT, int TERMS, int KC, int UP, int HL = 0>
 __global__ void __launch_bounds__(NUM_THREADS, umma_ctas_per_sm<COUT, KC, UP>())
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvParams p) {
-  constexpr int SC = UP == 2 ? 4 * COUT : COUT;   // TMEM columns of one output-plane slot
+  static_assert(!HL || (COUT == 16 && TERMS == 2 && UP == 1), "HL mode: 16 output channels, two terms, stride 1");
+  constexpr int SC = UP == 2 ? 4 * COUT : (HL ? 2 * COUT : COUT);   // TMEM columns of one output-plane slot
   constexpr int NSHIFT = UP == 2 ? 4 : 9;         // distinct (y,x) input shifts = MMAs per k-chunk and precision pair
   extern __shared__ __align__(1024) uint8_t smem[];
   SmemHeader* hdr = reinterpret_cast<SmemHeader*>(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wbytes_all = p.wbytes_term * p.terms;
+  const int wbytes_all = p.wbytes_term * p.wterms;
   uint8_t* wsm = smem + HEADER_BYTES;
   const int stage_bytes = p.terms * p.CGi * PLANE_CG_BYTES;
   uint8_t* stages = wsm + ((wbytes_all + 127) & ~127);
@@ -147,7 +153,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
     const uint32_t lbo_b = p.swap ? 128 : b_kcore, sbo_b = p.swap ? b_kcore : 128;
     constexpr uint32_t b_tile16 = 2 * b_kcore / 16;     // one (shift,kc) tile, in 16-byte units
     constexpr uint32_t b_plane16 = (SC / 8) * 128 / 16; // one stacked output plane (SC rows), in 16-byte units
-    constexpr int npairs = TERMS == 2 ? 3 : 1;
+    constexpr int npairs = HL ? 2 : (TERMS == 2 ? 3 : 1);   // HL: (a_hi, a_lo) x one stacked weight tile
     const uint32_t slot_mask = p.nslots - 1;             // nslots is a power of two
     const uint64_t bdesc0 = make_smem_desc(smem_u32(wsm), lbo_b, sbo_b);
     const uint32_t b_lo0 = (uint32_t)bdesc0, b_hi = (uint32_t)(bdesc0 >> 32);
@@ -196,7 +202,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
               for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
                 for (int pr = 0; pr < npairs; ++pr) {
-                  const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+                  const uint32_t ta = HL ? pr : (pr == 2 ? 1 : 0), tb = HL ? 0 : (pr == 1 ? 1 : 0);
                   umma_bf16_lh(seg_d0, a_lo0 + a_sh16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16), a_hi,
                                seg_b0 + tb * w_term16 + (uint32_t)(sh * KC + kc) * b_tile16, b_hi, seg_i0, 1u);
                 }
@@ -211,7 +217,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
               for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
                 for (int pr = 0; pr < npairs; ++pr) {
-                  const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+                  const uint32_t ta = HL ? pr : (pr == 2 ? 1 : 0), tb = HL ? 0 : (pr == 1 ? 1 : 0);
                   const uint32_t a_lo = a_lo0 + a_sh16 + ta * a_term16 + (uint32_t)(2 * kc) * (PLANE_CG_BYTES / 16);
                   const uint32_t b_off = tb * w_term16 + (uint32_t)(sh * KC + kc) * b_tile16;
                   umma_bf16_lh(seg_d0, a_lo, a_hi, seg_b0 + b_off, b_hi, seg_i0, 1u);
@@ -308,6 +314,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
 #pragma unroll
           for (int c = 0; c < COUT; ++c) {
             v[c] = __uint_as_float(r[c]) + bias_r[c];
+            if (HL) v[c] = (__uint_as_float(r[c]) + __uint_as_float(r[(HL ? COUT : 0) + c])) + bias_r[c];
             if (p.relu) v[c] = fmaxf(v[c], 0.f);
           }
           const long long vox = (long long)pl * HWo + vox0;
@@ -444,16 +451,16 @@ static float bf16_to_f32_host(uint16_t h) {
   return f;
 }
 
-template <int COUT, int TERMS, int KC, int UP>
+template <int COUT, int TERMS, int KC, int UP, int HL = 0>
 static int launch_umma(const CUtensorMap& tmap, const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
   static bool attr_set = false;
   static size_t attr_smem = 0;
   if (!attr_set || smem > attr_smem) {
-    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<COUT, TERMS, KC, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_umma_kernel<COUT, TERMS, KC, UP, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
     attr_smem = 227 * 1024;
   }
-  conv3d_umma_kernel<COUT, TERMS, KC, UP><<<grid, NUM_THREADS, smem, st>>>(tmap, p);
+  conv3d_umma_kernel<COUT, TERMS, KC, UP, HL><<<grid, NUM_THREADS, smem, st>>>(tmap, p);
   return check_launch("conv3d_umma_kernel");
 }
 
@@ -495,10 +502,33 @@ extern "C" int pccgeo_blocked_to_f32(const void* xb, float* x, int n, int c, int
 //   stride-2 transposed (UP=2): shift = sy*2+sx (4) with input offset -sy / -sx, SC = 4*Cout_p,
 //     n = j*SC + (yc*2+xc)*Cout_p + co: output plane 2z+j takes tap kz = j; output parity class (yc,xc) takes tap
 //     k = 0 at offset 0 / k = 2 at offset -1 when even, k = 1 at offset 0 when odd (zero rows where a class has no tap).
-extern "C" long long pccgeo_umma_pack_weights_host(const float* w, void* out, int cin, int cout, int stride, int transposed,
-                                                   int terms) {
+static long long umma_pack_weights_impl(const float* w, void* out, int cin, int cout, int stride, int transposed, int terms, int hl) {
   if (cin <= 0 || cout <= 0 || (terms != 1 && terms != 2)) { set_error("umma_pack_weights: bad argument"); return PCCGEO_EINVAL; }
   const bool up2 = stride == 2 && transposed;
+  if (hl) {
+    // HL image (one "term"): [shift 9][kcore 2][ngroup 12][8 n][8 k]; n = j*32 + half*16 + co with half 0 = bf16(w), 1 = w - bf16(w)
+    if (stride != 1 || cin > 16 || cout > 16 || terms != 2) { set_error("umma_pack_weights_hl: stride-1 layers with <= 16 channels and two terms only"); return PCCGEO_EINVAL; }
+    const long long bytes = 9LL * 2 * 12 * 64 * 2;
+    if (!out) return bytes;
+    if (!w) { set_error("umma_pack_weights_hl: null weights"); return PCCGEO_EINVAL; }
+    uint16_t* o = (uint16_t*)out;
+    memset(o, 0, (size_t)bytes);
+    for (int kyx = 0; kyx < 9; ++kyx)
+      for (int j = 0; j < 3; ++j)
+        for (int co = 0; co < cout; ++co)
+          for (int ci = 0; ci < cin; ++ci) {
+            int kz = 2 - j, ky = kyx / 3, kx = kyx % 3;
+            if (transposed) { kz = 2 - kz; ky = 2 - ky; kx = 2 - kx; }
+            const float val = w[((long long)((kz * 3 + ky) * 3 + kx) * cin + ci) * cout + co];
+            const uint16_t hi = f32_to_bf16_rn_host(val), lo = f32_to_bf16_rn_host(val - bf16_to_f32_host(hi));
+            const int kcore = ci >> 3, ki = ci & 7;
+            for (int half = 0; half < 2; ++half) {
+              const int nrow = j * 32 + half * 16 + co;
+              o[((((long long)kyx * 2 + kcore) * 12 + (nrow >> 3)) * 8 + (nrow & 7)) * 8 + ki] = half ? lo : hi;
+            }
+          }
+    return bytes;
+  }
   if (stride != 1 && !up2) { set_error("umma_pack_weights: stride-%d forward convs are not supported by the TMA kernel", stride); return PCCGEO_EINVAL; }
   const int cip = round_up_i(cin, 16), cop = round_up_i(cout, 16), KC = cip / 16;
   const int SC = up2 ? 4 * cop : cop, nshift = up2 ? 4 : 9;
@@ -541,9 +571,18 @@ extern "C" long long pccgeo_umma_pack_weights_host(const float* w, void* out, in
   return per_term * terms;
 }
 
-extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
-                                  int n, int cin, int d, int h, int wd, int cout, int stride, int transposed, int relu,
-                                  int terms, void* stream) {
+extern "C" long long pccgeo_umma_pack_weights_host(const float* w, void* out, int cin, int cout, int stride, int transposed,
+                                                   int terms) {
+  return umma_pack_weights_impl(w, out, cin, cout, stride, transposed, terms, 0);
+}
+
+extern "C" long long pccgeo_umma_hl_pack_weights_host(const float* w, void* out, int cin, int cout, int transposed) {
+  return umma_pack_weights_impl(w, out, cin, cout, 1, transposed, 2, 1);
+}
+
+static int conv3d_umma_impl(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
+                            int n, int cin, int d, int h, int wd, int cout, int stride, int transposed, int relu,
+                            int terms, int hl, void* stream) {
   PCCGEO_REQUIRE(xb && wpacked && yb, "conv3d_umma: null pointer");
   PCCGEO_REQUIRE(terms == 1 || terms == 2, "conv3d_umma: terms must be 1 or 2");
   const bool up2 = stride == 2 && transposed;  // stride 1: taps are already flipped in the packed image
@@ -560,9 +599,11 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   p.bias = bias; p.res = (const __nv_bfloat16*)residual_b; p.y = (__nv_bfloat16*)yb; p.wimg = (const uint8_t*)wpacked;
   p.N = n; p.D = d; p.H = h; p.W = wd; p.CGi = cip / 8; p.CGo = cop / 8; p.terms = terms; p.relu = relu; p.cout_real = cout;
   p.ytiles = h / TY; p.xtiles = wd / TX; p.items = n * p.ytiles * p.xtiles;
-  const int SC = up2 ? 4 * cop : cop;
+  PCCGEO_REQUIRE(!hl || (!up2 && cip == 16 && cop == 16 && terms == 2), "conv3d_umma_hl: stride-1 layers with <= 16 channels and two terms only");
+  const int SC = up2 ? 4 * cop : (hl ? 2 * cop : cop);
   PCCGEO_REQUIRE(3 * SC <= 256, "conv3d_umma: %d output channels are too many for one stride-2 transposed MMA", cout);
   p.wbytes_term = (up2 ? 4 : 9) * (cip / 16) * 2 * (3 * SC / 8) * 128;
+  p.wterms = hl ? 1 : terms;
   p.swap = g_opt_swap_lbo_sbo;
   p.term_stride_out = (long long)n * cop * d * h * wd * (up2 ? 8 : 1);
   // TMEM ring: power of two, >= 4 planes; stride 1 uses up to 256 columns, the stride-2 transposed form all 512
@@ -571,7 +612,7 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   p.slot_shift = 0;
   while ((1 << p.slot_shift) < p.nslots) ++p.slot_shift;
   const int stage_bytes = terms * p.CGi * PLANE_CG_BYTES;
-  const int wall = (p.wbytes_term * terms + 127) & ~127;
+  const int wall = (p.wbytes_term * p.wterms + 127) & ~127;
   const int ctas_per_sm = (!up2 && cop == 16 && cip == 16 && !g_opt_one_cta) ? 2 : 1;
   const int avail = (ctas_per_sm == 2 ? 113 : 227) * 1024 - HEADER_BYTES - wall;
   PCCGEO_REQUIRE(avail >= 3 * stage_bytes, "conv3d_umma: weights (%d B) leave no room for the input pipeline", wall);
@@ -595,6 +636,7 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
   if (g_opt_max_ctas > 0 && grid > g_opt_max_ctas) grid = g_opt_max_ctas;
   cudaStream_t st = (cudaStream_t)stream;
   const int kc = cip / 16;
+  if (hl) return launch_umma<16, 2, 1, 1, 1>(tmap, p, smem, grid, st);
   if (up2) {
 #define PCCGEO_DISPATCH_UP2(CO, T, K) if (cop == CO && terms == T && kc == K) return launch_umma<CO, T, K, 2>(tmap, p, smem, grid, st);
     PCCGEO_DISPATCH_UP2(16, 1, 1) PCCGEO_DISPATCH_UP2(16, 1, 2) PCCGEO_DISPATCH_UP2(16, 1, 4)
@@ -613,4 +655,16 @@ extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const flo
 #undef PCCGEO_DISPATCH
   set_error("conv3d_umma: unsupported channel configuration %d -> %d", cin, cout);
   return PCCGEO_EINVAL;
+}
+
+extern "C" int pccgeo_conv3d_umma(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
+                                  int n, int cin, int d, int h, int wd, int cout, int stride, int transposed, int relu,
+                                  int terms, void* stream) {
+  return conv3d_umma_impl(xb, wpacked, bias, residual_b, yb, n, cin, d, h, wd, cout, stride, transposed, relu, terms, 0, stream);
+}
+
+extern "C" int pccgeo_conv3d_umma_hl(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
+                                     int n, int cin, int d, int h, int wd, int cout, int transposed, int relu, void* stream) {
+  (void)transposed;   // the taps are already flipped in the packed image
+  return conv3d_umma_impl(xb, wpacked, bias, residual_b, yb, n, cin, d, h, wd, cout, 1, 0, relu, 2, 1, stream);
 }

@@ -87,6 +87,9 @@ class Layer:
 # parity-tested, off by default.
 _ys_enabled = [False]
 
+# The hi/lo-stacked 16-channel kernel (conv3d_umma.cu, HL mode): two N=96 MMAs per tap instead of three N=48 ones.
+_hl_enabled = [True]
+
 # bumped whenever any layer's parameters change: captured CUDA graphs (model_types) hold device pointers of packed weights
 params_epoch = [0]
 
@@ -163,6 +166,8 @@ class _ConvBase(Layer):
             elif key.startswith('w_ummays'):
                 terms = int(key[-1])
                 self._dev[key] = ops.umma_ys_pack_weights(self.tap_major(), self.in_channels, self.filters, self.transposed, terms)
+            elif key == 'w_ummahl':
+                self._dev[key] = ops.umma_hl_pack_weights(self.tap_major(), self.in_channels, self.filters, self.transposed)
             elif key.startswith('w_out1'):
                 terms = int(key[-1])
                 self._dev[key] = ops.out1_pack_weights(self.tap_major(), self.in_channels, self.transposed, terms)
@@ -183,6 +188,12 @@ class _ConvBase(Layer):
         if self.k == 3 and self.stride == 2 and self.transposed:
             return c >= 8 and cp <= 32 and fp <= 16 and tiled
         return self.k == 3 and self.stride == 1 and c >= 8 and cp <= 32 and fp <= 32 and tiled
+
+    def hl_eligible(self, in_shape, terms):
+        """hi/lo-stacked form of the TMA kernel: two-term precision, stride 1, <= 16 channels in and out."""
+        n, c, d, h, w = in_shape
+        return (_hl_enabled[0] and terms == 2 and self.k == 3 and self.stride == 1 and 8 <= c <= 16 and self.filters <= 16
+                and self.umma_eligible(in_shape))
 
     def ys_eligible(self, in_shape):
         """y-stacked TMA kernel: 3x3x3 stride-1 layers with 9..16 input and output channels on volumes tall enough for its
@@ -478,6 +489,11 @@ def run_steps(steps, out_id, x, pack=None, keep=None, extra=None):
                 yb, shp = ops.conv3d_umma_ys(v.as_blk(terms), v.shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'),
                                              layer.filters, layer.relu, terms, rb)
                 vals[dst] = _Val(blk=yb, shape=shp, terms=terms)
+            elif layer.hl_eligible(v.shape, terms):
+                rb = vals[res].as_blk(terms) if res is not None else None
+                yb, shp = ops.conv3d_umma_hl(v.as_blk(terms), v.shape, layer.dev('w_ummahl'), layer.dev('bias'), layer.filters,
+                                             layer.transposed, layer.relu, rb)
+                vals[dst] = _Val(blk=yb, shape=shp, terms=terms)
             elif terms and layer.umma_eligible(v.shape):
                 rb = vals[res].as_blk(terms) if res is not None else None
                 yb, shp = ops.conv3d_umma(v.as_blk(terms), v.shape, layer.dev(f'w_umma{terms}'), layer.dev('bias'),
@@ -518,6 +534,10 @@ def layer_runner(layer, xb, in_shape, terms, residual_b=None):
         out, _ = ops.conv3d_umma_ys(xb, in_shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'), layer.filters, layer.relu, terms, residual_b)
         return (lambda: ops.conv3d_umma_ys(xb, in_shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'), layer.filters, layer.relu, terms,
                                            residual_b, out)), 'conv3d_umma_ys_kernel'
+    if layer.hl_eligible(in_shape, terms):
+        out, _ = ops.conv3d_umma_hl(xb, in_shape, layer.dev('w_ummahl'), layer.dev('bias'), layer.filters, layer.transposed, layer.relu, residual_b)
+        return (lambda: ops.conv3d_umma_hl(xb, in_shape, layer.dev('w_ummahl'), layer.dev('bias'), layer.filters, layer.transposed,
+                                           layer.relu, residual_b, out)), 'conv3d_umma_kernel<16,hl>'
     if layer.umma_eligible(in_shape):
         out, _ = ops.conv3d_umma(xb, in_shape, layer.dev(f'w_umma{terms}'), layer.dev('bias'), layer.filters, layer.stride, layer.transposed,
                                  layer.relu, terms, residual_b)

@@ -603,7 +603,7 @@ class CompressionModel:
             x_hat_list = [pts] * thr_idx.shape[1]  # every opt_metric gets the same fixed threshold
         else:
             # debug=True keeps every block's intermediate tensors (eager kernels, fp32 x_hat materialised): same bytes and points
-            strings_list, x_hat, _ = self.encode_blocks(blocks, debug_out=debug_t_list if debug else None)
+            strings_list, x_hat, _ = self.encode_blocks(blocks, **({'debug_out': debug_t_list} if debug else {}))
             if fixed_threshold or not n:
                 opt_metrics_ret = list(opt_metrics)
                 thr_idx = np.full((n, len(opt_metrics_ret)), len(self.thresholds) // 2, np.int64)

@@ -88,6 +88,31 @@ def conv3d_umma(xb, in_shape, wpacked, bias, cout, stride, transposed, relu, ter
     return out, shp
 
 
+def umma_hl_pack_weights(w_tap_host, cin, cout, transposed):
+    """numpy fp32 (27, Cin, Cout) -> device uint8 image for pccgeo_conv3d_umma_hl (hi/lo weight halves stacked in N)."""
+    w = np.ascontiguousarray(w_tap_host, np.float32)
+    size = L.lib().pccgeo_umma_hl_pack_weights_host(L.ptr(w), None, cin, cout, int(transposed))
+    if size < 0:
+        L.check(int(size), 'umma_hl_pack_weights')
+    img = np.zeros(int(size), np.uint8)
+    rc = L.lib().pccgeo_umma_hl_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, int(transposed))
+    if rc < 0:
+        L.check(int(rc), 'umma_hl_pack_weights')
+    return torch.from_numpy(img).cuda()
+
+
+def conv3d_umma_hl(xb, in_shape, wpacked, bias, cout, transposed, relu, residual_b=None, out=None):
+    """Two-term blocked-layout conv, stride 1, <= 16 channels in and out, on the hi/lo-stacked kernel.  Returns (yb, out_shape)."""
+    L.require_cuda()
+    n, cin, d, h, w = in_shape
+    shp = (n, cout, d, h, w)
+    if out is None:
+        out = torch.empty(blocked_numel(*shp, 2), device=xb.device, dtype=torch.bfloat16)
+    L.check(L.lib().pccgeo_conv3d_umma_hl(L.ptr(xb), L.ptr(wpacked), L.ptr(bias), L.ptr(residual_b), L.ptr(out),
+                                          n, cin, d, h, w, cout, int(transposed), int(relu), L.stream_ptr()), 'conv3d_umma_hl')
+    return out, shp
+
+
 def umma_ys_pack_weights(w_tap_host, cin, cout, transposed, terms):
     """numpy fp32 (27, Cin, Cout) -> device uint8 image for pccgeo_conv3d_umma_ys."""
     w = np.ascontiguousarray(w_tap_host, np.float32)

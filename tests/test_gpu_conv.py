@@ -111,6 +111,43 @@ def test_umma_full_size_layer_matches_fp32_kernel(terms):
     assert torch.equal(yb, yb2)
 
 
+HL_CASES = [
+    # transposed, cin, cout, (D,H,W), n
+    (False, 16, 16, (4, 16, 8), 1), (True, 16, 16, (16, 16, 16), 2), (False, 12, 9, (3, 16, 8), 1), (True, 16, 16, (1, 16, 8), 1),
+    (False, 16, 16, (40, 32, 32), 5), (True, 16, 16, (20, 16, 24), 3), (True, 16, 16, (64, 64, 64), 2),
+]
+
+
+@pytest.mark.parametrize('transposed,cin,cout,shape,n', HL_CASES)
+def test_umma_hl_conv_matches_oracle(transposed, cin, cout, shape, n):
+    """hi/lo-stacked form of the TMA kernel (two N=96 MMAs per tap; all four partial products): fp32-class accuracy vs the
+    float64 oracle, with bias, ReLU and the fused residual; bit-identical from launch to launch; at least as accurate as the
+    three-product kernel it replaces."""
+    rng = np.random.default_rng(hash((transposed, cin, cout, shape, n)) % 2 ** 31)
+    x, kern, bias = _case(rng, transposed, 3, 1, cin, cout, shape, n)
+    res = torch.from_numpy(rng.normal(size=(n, cout) + shape).astype(np.float32))
+    want = _oracle(x, kern, bias, 1, True, transposed, res)
+    wp = ops.umma_hl_pack_weights(_tap_major(kern, transposed).numpy(), cin, cout, transposed)
+    xb = ops.f32_to_blocked(x.cuda(), 2)
+    rb = ops.f32_to_blocked(res.cuda(), 2)
+    yb, shp = ops.conv3d_umma_hl(xb, tuple(x.shape), wp, bias.cuda(), cout, transposed, True, rb)
+    got = ops.blocked_to_f32(yb, shp, 2)
+    assert shp == tuple(want.shape)
+    scale = float(want.abs().max())
+    err = float((got.cpu().double() - want).abs().max())
+    assert err < 3e-5 * scale, f'max err {err:.3e} vs scale {scale:.3e}'
+    yb2, _ = ops.conv3d_umma_hl(xb, tuple(x.shape), wp, bias.cuda(), cout, transposed, True, rb)
+    assert torch.equal(yb, yb2)
+    w3 = ops.umma_pack_weights(_tap_major(kern, transposed).numpy(), cin, cout, 1, transposed, 2)
+    y3, _ = ops.conv3d_umma(xb, tuple(x.shape), w3, bias.cuda(), cout, 1, transposed, True, 2, rb)
+    err3 = float((ops.blocked_to_f32(y3, shp, 2).cpu().double() - want).abs().max())
+    assert err <= 1.5 * err3 + 1e-7 * scale, (err, err3)
+    # no bias / no relu / no residual
+    want2 = _oracle(x, kern, None, 1, False, transposed)
+    y2, _ = ops.conv3d_umma_hl(xb, tuple(x.shape), wp, None, cout, transposed, False)
+    assert float((ops.blocked_to_f32(y2, shp, 2).cpu().double() - want2).abs().max()) < 3e-5 * float(want2.abs().max())
+
+
 UMMA_UP2_CASES = [
     # cin, cout, (D,H,W) of the input, n
     (32, 16, (4, 16, 8), 1), (32, 16, (16, 16, 16), 2), (16, 16, (1, 16, 8), 1), (32, 16, (7, 32, 24), 3), (24, 12, (5, 16, 8), 2),
