@@ -131,16 +131,34 @@ conv3d_gemm_kernel(const GemmConvParams p) {
     auto advance = [&](Cursor& c) {
       if (++c.ti == c.t_end) { c.tile += gridDim.x; open_tile(c); }
     };
-    auto issue_loads = [&](const Cursor& c, const int4& tap, int4* dst) {
+    // gather of one (tile, tap) pair straight into a ring stage with 16-byte cp.async (zero-filled when the tap falls outside
+    // the volume): nothing is staged in registers, so several taps are in flight per thread -- with register staging only ONE
+    // tap was, and every tap cost a full L2 round trip (ncu: the MMA warp waited for `full` 83 % of the time)
+    auto issue_loads = [&](const Cursor& c, const int4& tap, uint32_t dst) {
       const int iz = c.iz0 + tap.x, iy = c.iy0 + tap.y, ix = c.ix0 + tap.z;
       const bool inb = c.valid && iz >= 0 && iz < p.Din && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-      const __nv_bfloat16* src = c.xn + (iz * HWin + (long long)iy * p.Win + ix) * 8;
+      const __nv_bfloat16* src = inb ? c.xn + (iz * HWin + (long long)iy * p.Win + ix) * 8 : p.x;
+      const uint32_t nbytes = inb ? 16u : 0u;
 #pragma unroll
       for (int tt = 0; tt < TERMS; ++tt)
 #pragma unroll
-        for (int cg = 0; cg < CGI; ++cg)
-          dst[tt * CGI + cg] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8))
-                                   : make_int4(0, 0, 0, 0);
+        for (int cg = 0; cg < CGI; ++cg) {
+          const __nv_bfloat16* sp = inb ? src + tt * p.term_stride_in + (long long)cg * DHWin * 8 : src;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(tt * CGI + cg) * 2048u), "l"(sp), "r"(nbytes)
+                       : "memory");
+        }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto wait_pending = [](int n) {   // block until at most n of this thread's cp.async groups are still in flight
+      switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+      }
     };
     Cursor cur;
     cur.tile = blockIdx.x;
@@ -148,20 +166,20 @@ conv3d_gemm_kernel(const GemmConvParams p) {
     cur.valid = false;
     cur.xn = p.x;
     open_tile(cur);
-    int4 v[TERMS * CGI], vn[TERMS * CGI];
-    int4 tp = make_int4(0, 0, 0, 0);
-    if (cur.tile < p.total_tiles) {
-      tp = __ldg(p.taps + cur.ti);
-      issue_loads(cur, tp, v);
-    }
+    // stage s is published (`full`) LOOK iterations after its loads were issued; LOOK < nstage, so the `empty` wait of an
+    // iteration only ever depends on stages that were already published
+    const int LOOK = p.nstage - 1 < 7 ? p.nstage - 1 : 7;
+    uint32_t s_done = 0;
+    int inflight = 0;
+    auto publish_oldest = [&]() {
+      wait_pending(inflight - 1);
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&hdr->full[s_done]));
+      if (++s_done == (uint32_t)p.nstage) s_done = 0;
+      --inflight;
+    };
     while (cur.tile < p.total_tiles) {
-      Cursor nxt = cur;
-      advance(nxt);
-      int4 tpn = tp;
-      if (nxt.tile < p.total_tiles) {
-        tpn = __ldg(p.taps + nxt.ti);
-        issue_loads(nxt, tpn, vn);
-      }
+      const int4 tp = __ldg(p.taps + cur.ti);
       mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1);
       uint8_t* st = stages + (size_t)s * p.stage_bytes;
       if (r == 0) {
@@ -171,16 +189,13 @@ conv3d_gemm_kernel(const GemmConvParams p) {
         mbar_expect_tx_only(full, bytes);
         bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)group * NACC * p.wchunk_bytes, bytes, full);
       }
-#pragma unroll
-      for (int i = 0; i < TERMS * CGI; ++i) *reinterpret_cast<int4*>(st + i * 2048 + row_off) = v[i];
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&hdr->full[s]));
+      issue_loads(cur, tp, smem_u32(st) + row_off);
+      ++inflight;
       if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
-#pragma unroll
-      for (int i = 0; i < TERMS * CGI; ++i) v[i] = vn[i];
-      tp = tpn;
-      cur = nxt;
+      advance(cur);
+      if (inflight > LOOK) publish_oldest();
     }
+    while (inflight > 0) publish_oldest();
   } else if (warp == 4) {
     // ================= MMA issuer =================
     constexpr uint32_t b_kc16 = 2 * (COUT / 8) * 128 / 16;     // one k-chunk of B (two K core matrices), 16-byte units
