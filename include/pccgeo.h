@@ -91,6 +91,14 @@ long long pccgeo_umma_hl_pack_weights_host(const float* w_host, void* wpacked_ho
 int pccgeo_conv3d_umma_hl(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
                           int n, int cin, int d, int h, int wd, int cout, int transposed, int relu, void* stream);
 
+/* zy-ring form of pccgeo_conv3d_umma for the same layers (stride-1 3x3x3, <= 16 channels in and out; conv or transposed conv):
+ * the M tile is 16 blocks x 8 x-voxels of one input row and BOTH the y and the z taps are accumulated by the tensor core in a
+ * two-dimensional TMEM ring, so one MMA of N = 144 per x-offset and precision product replaces nine of N = 48 (a third of the
+ * A-operand fetches per MAC).  Same tensors as pccgeo_conv3d_umma; own weight image.  W % 8 == 0; efficient for N % 16 == 0. */
+long long pccgeo_umma_zy_pack_weights_host(const float* w_host, void* wpacked_host, int cin, int cout, int transposed, int terms);
+int pccgeo_conv3d_umma_zy(const void* xb, const void* wpacked, const float* bias, const void* residual_b, void* yb,
+                          int n, int cin, int d, int h, int wd, int cout, int relu, int terms, void* stream);
+
 /* y-stacked variant of pccgeo_conv3d_umma for stride-1 3x3x3 layers with <= 16 input and output channels (the second and
  * third layer of AnalysisBlock / SynthesisBlock at 16 filters, src/model_transforms.py:62-81): z AND y taps are stacked in
  * the MMA N dimension (3 MMAs of N=144 per input plane and precision pair instead of 9 of N=48); the epilogue adds the

@@ -26,6 +26,8 @@ SIGNATURES = {
     'pccgeo_conv3d_umma': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_umma_hl_pack_weights_host': (i64, [vp, vp, i32, i32, i32]),
     'pccgeo_conv3d_umma_hl': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_umma_zy_pack_weights_host': (i64, [vp, vp, i32, i32, i32, i32]),
+    'pccgeo_conv3d_umma_zy': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_umma_ys_pack_weights_host': (i64, [vp, vp, i32, i32, i32, i32]),
     'pccgeo_conv3d_umma_ys': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_out1_pack_weights_host': (i64, [vp, vp, i32, i32, i32]),

@@ -32,6 +32,8 @@
 
 namespace pccgeo {
 
+int g_gather_mode = 1;   // pccgeo_set_option("gemm_gather_mode")
+
 constexpr int GM = 128;
 constexpr int G_THREADS = 9 * 32;
 constexpr int G_MAX_STAGES = 8;
@@ -52,6 +54,7 @@ struct GemmConvParams {
   int tiles_per_cls, total_tiles;
   long long term_stride_in, term_stride_out;
   int nstage, wchunk_bytes, a_stage_bytes, stage_bytes;
+  int gather_mode;   // 0: register-staged LDG gather, 1: cp.async.ca with multi-stage lookahead, 2: cp.async.cg
 };
 
 struct __align__(8) GemmSmemHeader {
@@ -144,8 +147,10 @@ conv3d_gemm_kernel(const GemmConvParams p) {
 #pragma unroll
         for (int cg = 0; cg < CGI; ++cg) {
           const __nv_bfloat16* sp = inb ? src + tt * p.term_stride_in + (long long)cg * DHWin * 8 : src;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(tt * CGI + cg) * 2048u), "l"(sp), "r"(nbytes)
-                       : "memory");
+          if (p.gather_mode == 2)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(tt * CGI + cg) * 2048u), "l"(sp), "r"(nbytes) : "memory");
+          else
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(tt * CGI + cg) * 2048u), "l"(sp), "r"(nbytes) : "memory");
         }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -160,12 +165,24 @@ conv3d_gemm_kernel(const GemmConvParams p) {
         default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
       }
     };
+    auto issue_loads_reg = [&](const Cursor& c, const int4& tap, int4* dst) {
+      const int iz = c.iz0 + tap.x, iy = c.iy0 + tap.y, ix = c.ix0 + tap.z;
+      const bool inb = c.valid && iz >= 0 && iz < p.Din && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+      const __nv_bfloat16* src = c.xn + (iz * HWin + (long long)iy * p.Win + ix) * 8;
+#pragma unroll
+      for (int tt = 0; tt < TERMS; ++tt)
+#pragma unroll
+        for (int cg = 0; cg < CGI; ++cg)
+          dst[tt * CGI + cg] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8))
+                                   : make_int4(0, 0, 0, 0);
+    };
     Cursor cur;
     cur.tile = blockIdx.x;
     cur.ti = cur.t_end = cur.iz0 = cur.iy0 = cur.ix0 = 0;
     cur.valid = false;
     cur.xn = p.x;
     open_tile(cur);
+    if (p.gather_mode != 0) {
     // stage s is published (`full`) LOOK iterations after its loads were issued; LOOK < nstage, so the `empty` wait of an
     // iteration only ever depends on stages that were already published
     const int LOOK = p.nstage - 1 < 7 ? p.nstage - 1 : 7;
@@ -196,6 +213,42 @@ conv3d_gemm_kernel(const GemmConvParams p) {
       if (inflight > LOOK) publish_oldest();
     }
     while (inflight > 0) publish_oldest();
+    } else {
+    // register-staged gather (one tap in flight per thread)
+    int4 v[TERMS * CGI], vn[TERMS * CGI];
+    int4 tp = make_int4(0, 0, 0, 0);
+    if (cur.tile < p.total_tiles) {
+      tp = __ldg(p.taps + cur.ti);
+      issue_loads_reg(cur, tp, v);
+    }
+    while (cur.tile < p.total_tiles) {
+      Cursor nxt = cur;
+      advance(nxt);
+      int4 tpn = tp;
+      if (nxt.tile < p.total_tiles) {
+        tpn = __ldg(p.taps + nxt.ti);
+        issue_loads_reg(nxt, tpn, vn);
+      }
+      mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1);
+      uint8_t* st = stages + (size_t)s * p.stage_bytes;
+      if (r == 0) {
+        const uint32_t full = smem_u32(&hdr->full[s]);
+        const uint32_t group = (uint32_t)tp.w & 0xffffu;
+        const uint32_t bytes = (NACC == 1 ? 1u : (uint32_t)__popc((uint32_t)tp.w >> 16)) * (uint32_t)p.wchunk_bytes;
+        mbar_expect_tx_only(full, bytes);
+        bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)group * NACC * p.wchunk_bytes, bytes, full);
+      }
+#pragma unroll
+      for (int i = 0; i < TERMS * CGI; ++i) *reinterpret_cast<int4*>(st + i * 2048 + row_off) = v[i];
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&hdr->full[s]));
+      if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
+#pragma unroll
+      for (int i = 0; i < TERMS * CGI; ++i) v[i] = vn[i];
+      tp = tpn;
+      cur = nxt;
+    }
+    }
   } else if (warp == 4) {
     // ================= MMA issuer =================
     constexpr uint32_t b_kc16 = 2 * (COUT / 8) * 128 / 16;     // one k-chunk of B (two K core matrices), 16-byte units
@@ -541,6 +594,7 @@ extern "C" int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const vo
   p.nstage = avail / p.stage_bytes;
   if (p.nstage > G_MAX_STAGES) p.nstage = G_MAX_STAGES;
   PCCGEO_REQUIRE(p.nstage >= 2, "conv3d_gemm: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
+  p.gather_mode = g_gather_mode;
   const size_t smem = G_HEADER_BYTES + (size_t)p.nstage * p.stage_bytes;
   int grid = p.total_tiles < 148 * ctas_per_sm ? p.total_tiles : 148 * ctas_per_sm;
   cudaStream_t st = (cudaStream_t)stream;

@@ -90,6 +90,9 @@ _ys_enabled = [False]
 # The hi/lo-stacked 16-channel kernel (conv3d_umma.cu, HL mode): two N=96 MMAs per tap instead of three N=48 ones.
 _hl_enabled = [True]
 
+# The zy-ring 16-channel kernel (conv3d_umma_zy.cu): y and z taps accumulated in a 2-D TMEM ring, N = 144 MMAs.
+_zy_enabled = [True]
+
 # bumped whenever any layer's parameters change: captured CUDA graphs (model_types) hold device pointers of packed weights
 params_epoch = [0]
 
@@ -166,6 +169,9 @@ class _ConvBase(Layer):
             elif key.startswith('w_ummays'):
                 terms = int(key[-1])
                 self._dev[key] = ops.umma_ys_pack_weights(self.tap_major(), self.in_channels, self.filters, self.transposed, terms)
+            elif key.startswith('w_ummazy'):
+                terms = int(key[-1])
+                self._dev[key] = ops.umma_zy_pack_weights(self.tap_major(), self.in_channels, self.filters, self.transposed, terms)
             elif key == 'w_ummahl':
                 self._dev[key] = ops.umma_hl_pack_weights(self.tap_major(), self.in_channels, self.filters, self.transposed)
             elif key.startswith('w_out1'):
@@ -188,6 +194,13 @@ class _ConvBase(Layer):
         if self.k == 3 and self.stride == 2 and self.transposed:
             return c >= 8 and cp <= 32 and fp <= 16 and tiled
         return self.k == 3 and self.stride == 1 and c >= 8 and cp <= 32 and fp <= 32 and tiled
+
+    def zy_eligible(self, in_shape, terms):
+        """zy-ring kernel: stride-1 3x3x3 layers with 9..16 channels in and out, batches that fill its 16-block M tiles and
+        volumes large enough for its (16 blocks x 8 x x <= 10 rows) work items to occupy the GPU."""
+        n, c, d, h, w = in_shape
+        return (_zy_enabled[0] and terms and self.k == 3 and self.stride == 1 and 8 <= c <= 16 and 8 < self.filters <= 16 and w % 8 == 0
+                and n % 16 == 0 and (n // 16) * (w // 8) * h >= 148 * 4)
 
     def hl_eligible(self, in_shape, terms):
         """hi/lo-stacked form of the TMA kernel: two-term precision, stride 1, <= 16 channels in and out."""
@@ -489,6 +502,11 @@ def run_steps(steps, out_id, x, pack=None, keep=None, extra=None):
                 yb, shp = ops.conv3d_umma_ys(v.as_blk(terms), v.shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'),
                                              layer.filters, layer.relu, terms, rb)
                 vals[dst] = _Val(blk=yb, shape=shp, terms=terms)
+            elif layer.zy_eligible(v.shape, terms):
+                rb = vals[res].as_blk(terms) if res is not None else None
+                yb, shp = ops.conv3d_umma_zy(v.as_blk(terms), v.shape, layer.dev(f'w_ummazy{terms}'), layer.dev('bias'), layer.filters,
+                                             layer.relu, terms, rb)
+                vals[dst] = _Val(blk=yb, shape=shp, terms=terms)
             elif layer.hl_eligible(v.shape, terms):
                 rb = vals[res].as_blk(terms) if res is not None else None
                 yb, shp = ops.conv3d_umma_hl(v.as_blk(terms), v.shape, layer.dev('w_ummahl'), layer.dev('bias'), layer.filters,
@@ -534,6 +552,10 @@ def layer_runner(layer, xb, in_shape, terms, residual_b=None):
         out, _ = ops.conv3d_umma_ys(xb, in_shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'), layer.filters, layer.relu, terms, residual_b)
         return (lambda: ops.conv3d_umma_ys(xb, in_shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'), layer.filters, layer.relu, terms,
                                            residual_b, out)), 'conv3d_umma_ys_kernel'
+    if layer.zy_eligible(in_shape, terms):
+        out, _ = ops.conv3d_umma_zy(xb, in_shape, layer.dev(f'w_ummazy{terms}'), layer.dev('bias'), layer.filters, layer.relu, terms, residual_b)
+        return (lambda: ops.conv3d_umma_zy(xb, in_shape, layer.dev(f'w_ummazy{terms}'), layer.dev('bias'), layer.filters, layer.relu, terms,
+                                           residual_b, out)), 'conv3d_umma_zy_kernel'
     if layer.hl_eligible(in_shape, terms):
         out, _ = ops.conv3d_umma_hl(xb, in_shape, layer.dev('w_ummahl'), layer.dev('bias'), layer.filters, layer.transposed, layer.relu, residual_b)
         return (lambda: ops.conv3d_umma_hl(xb, in_shape, layer.dev('w_ummahl'), layer.dev('bias'), layer.filters, layer.transposed,

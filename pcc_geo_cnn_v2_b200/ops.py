@@ -113,6 +113,31 @@ def conv3d_umma_hl(xb, in_shape, wpacked, bias, cout, transposed, relu, residual
     return out, shp
 
 
+def umma_zy_pack_weights(w_tap_host, cin, cout, transposed, terms):
+    """numpy fp32 (27, Cin, Cout) -> device uint8 image for pccgeo_conv3d_umma_zy (three z-rotations of the y/z-stacked taps)."""
+    w = np.ascontiguousarray(w_tap_host, np.float32)
+    size = L.lib().pccgeo_umma_zy_pack_weights_host(L.ptr(w), None, cin, cout, int(transposed), terms)
+    if size < 0:
+        L.check(int(size), 'umma_zy_pack_weights')
+    img = np.zeros(int(size), np.uint8)
+    rc = L.lib().pccgeo_umma_zy_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, int(transposed), terms)
+    if rc < 0:
+        L.check(int(rc), 'umma_zy_pack_weights')
+    return torch.from_numpy(img).cuda()
+
+
+def conv3d_umma_zy(xb, in_shape, wpacked, bias, cout, relu, terms, residual_b=None, out=None):
+    """Blocked-layout conv, stride 1, <= 16 channels in and out, on the zy-ring kernel.  Returns (yb, out_shape)."""
+    L.require_cuda()
+    n, cin, d, h, w = in_shape
+    shp = (n, cout, d, h, w)
+    if out is None:
+        out = torch.empty(blocked_numel(*shp, terms), device=xb.device, dtype=torch.bfloat16)
+    L.check(L.lib().pccgeo_conv3d_umma_zy(L.ptr(xb), L.ptr(wpacked), L.ptr(bias), L.ptr(residual_b), L.ptr(out),
+                                          n, cin, d, h, w, cout, int(relu), terms, L.stream_ptr()), 'conv3d_umma_zy')
+    return out, shp
+
+
 def umma_ys_pack_weights(w_tap_host, cin, cout, transposed, terms):
     """numpy fp32 (27, Cin, Cout) -> device uint8 image for pccgeo_conv3d_umma_ys."""
     w = np.ascontiguousarray(w_tap_host, np.float32)

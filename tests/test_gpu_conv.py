@@ -148,6 +148,45 @@ def test_umma_hl_conv_matches_oracle(transposed, cin, cout, shape, n):
     assert float((ops.blocked_to_f32(y2, shp, 2).cpu().double() - want2).abs().max()) < 3e-5 * float(want2.abs().max())
 
 
+ZY_CASES = [
+    # transposed, cin, cout, (D,H,W), n
+    (False, 16, 16, (4, 16, 8), 1), (True, 16, 16, (16, 16, 16), 2), (False, 12, 9, (3, 5, 8), 3), (True, 16, 16, (1, 1, 8), 1),
+    (False, 16, 16, (2, 23, 16), 17), (True, 16, 16, (7, 64, 24), 16), (True, 16, 16, (20, 16, 24), 3), (False, 16, 16, (64, 64, 64), 32),
+    (True, 16, 16, (5, 3, 8), 33),
+]
+
+
+@pytest.mark.parametrize('terms,tol', [(2, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize('transposed,cin,cout,shape,n', ZY_CASES)
+def test_umma_zy_conv_matches_oracle(transposed, cin, cout, shape, n, terms, tol):
+    """zy-ring kernel (y and z taps accumulated in a 2-D TMEM ring, N = 144 MMAs, tiles of 16 blocks x 8 x x <= 10 rows): fp32-class
+    accuracy vs the float64 oracle with bias, ReLU and the fused residual, over ragged batches (not a multiple of 16), ragged row
+    tiles, single-plane / single-row volumes and the headline shape; bit-identical from launch to launch."""
+    rng = np.random.default_rng(hash((transposed, cin, cout, shape, n)) % 2 ** 31)
+    big = n * np.prod(shape) > 2 ** 21
+    x, kern, bias = _case(rng, transposed, 3, 1, cin, cout, shape, n)
+    res = torch.from_numpy(rng.normal(size=(n, cout) + shape).astype(np.float32))
+    wp = ops.umma_zy_pack_weights(_tap_major(kern, transposed).numpy(), cin, cout, transposed, terms)
+    xb = ops.f32_to_blocked(x.cuda(), terms)
+    rb = ops.f32_to_blocked(res.cuda(), terms)
+    yb, shp = ops.conv3d_umma_zy(xb, tuple(x.shape), wp, bias.cuda(), cout, True, terms, rb)
+    got = ops.blocked_to_f32(yb, shp, terms)
+    if big:   # the headline shape: the fp32 CUDA-core kernel is the checker (the float64 CPU oracle would take minutes)
+        want = ops.conv3d_f32(x.cuda(), _tap_major(kern, transposed).cuda(), bias.cuda(), cout, 3, 1, transposed, True, res.cuda()).cpu().double()
+    else:
+        want = _oracle(x, kern, bias, 1, True, transposed, res)
+    assert shp == tuple(want.shape)
+    scale = float(want.abs().max())
+    err = float((got.cpu().double() - want).abs().max())
+    assert err < tol * scale, f'max err {err:.3e} vs scale {scale:.3e}'
+    yb2, _ = ops.conv3d_umma_zy(xb, tuple(x.shape), wp, bias.cuda(), cout, True, terms, rb)
+    assert torch.equal(yb, yb2)
+    if not big:   # no bias / no relu / no residual
+        want2 = _oracle(x, kern, None, 1, False, transposed)
+        y2, _ = ops.conv3d_umma_zy(xb, tuple(x.shape), wp, None, cout, False, terms)
+        assert float((ops.blocked_to_f32(y2, shp, terms).cpu().double() - want2).abs().max()) < tol * float(want2.abs().max())
+
+
 UMMA_UP2_CASES = [
     # cin, cout, (D,H,W) of the input, n
     (32, 16, (4, 16, 8), 1), (32, 16, (16, 16, 16), 2), (16, 16, (1, 16, 8), 1), (32, 16, (7, 32, 24), 3), (24, 12, (5, 16, 8), 2),

@@ -1,4 +1,4 @@
-"""A/B of the 16->16 layer kernels at the headline size (batch 32, 64^3, two terms): the three-product TMA kernel vs its
+"""A/B/C of the 16->16 layer kernels at the headline size (batch 32, 64^3, two terms): the three-product TMA kernel vs its
 hi/lo-stacked form, timed alone (burst, 20 launches) and in a sustained 1.5 s loop (power-capped clocks).
     python tools/ab_hl.py [B] [size]"""
 import os
@@ -20,8 +20,10 @@ xb = ops.f32_to_blocked(x, 2)
 yb = torch.empty_like(xb)
 w3 = ops.umma_pack_weights(w, 16, 16, 1, True, 2)
 whl = ops.umma_hl_pack_weights(w, 16, 16, True)
+wzy = ops.umma_zy_pack_weights(w, 16, 16, True, 2)
 runs = {'three-product (N=48 x 27)': lambda: ops.conv3d_umma(xb, tuple(x.shape), w3, bias, 16, 1, True, True, 2, None, yb),
-        'hi/lo-stacked (N=96 x 18)': lambda: ops.conv3d_umma_hl(xb, tuple(x.shape), whl, bias, 16, True, True, None, yb)}
+        'hi/lo-stacked (N=96 x 18)': lambda: ops.conv3d_umma_hl(xb, tuple(x.shape), whl, bias, 16, True, True, None, yb),
+        'zy-ring (N=144 x 9 per row)': lambda: ops.conv3d_umma_zy(xb, tuple(x.shape), wzy, bias, 16, True, 2, None, yb)}
 flop = 2 * 27 * 16 * 16 * B * S ** 3
 
 

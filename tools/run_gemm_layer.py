@@ -10,6 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pcc_geo_cnn_v2_b200 import ops  # noqa: E402
 
 B, C, CO, S, stride, tr, reps = [int(a) for a in (sys.argv[1:] + ['32', '64', '64', '16', '1', '1', '5'][len(sys.argv) - 1:])]
+if os.environ.get('PCCGEO_GATHER_MODE'):
+    from pcc_geo_cnn_v2_b200 import _lib
+    _lib.check(_lib.lib().pccgeo_set_option(b'gemm_gather_mode', int(os.environ['PCCGEO_GATHER_MODE'])), 'set_option')
 rng = np.random.default_rng(0)
 x = torch.randn(B, C, S, S, S, device='cuda').relu_()
 w = (rng.normal(size=(27, C, CO)) / np.sqrt(27 * C)).astype(np.float32)
@@ -28,4 +31,4 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 so = S * stride if tr else S // stride
 vox = B * (S ** 3 if (tr or stride == 1) else so ** 3)
-print(f'B={B} {C}->{CO} S={S} stride={stride} transposed={tr}: {ms:.4f} ms/launch, {2 * 27 * C * CO * vox / ms / 1e9:.1f} TFLOP/s algorithmic')
+print(f"gather_mode={os.environ.get('PCCGEO_GATHER_MODE', 'default')} " f'B={B} {C}->{CO} S={S} stride={stride} transposed={tr}: {ms:.4f} ms/launch, {2 * 27 * C * CO * vox / ms / 1e9:.1f} TFLOP/s algorithmic')
