@@ -32,7 +32,7 @@
 
 namespace pccgeo {
 
-int g_gather_mode = 1;   // pccgeo_set_option("gemm_gather_mode")
+int g_gather_mode = 0;   // pccgeo_set_option("gemm_gather_mode")
 
 constexpr int GM = 128;
 constexpr int G_THREADS = 9 * 32;

@@ -22,8 +22,9 @@
 // that fall outside the volume and are drained and discarded, so every input plane issues the same MMAs.
 //   warp 0      TMA producer: per input row and precision term one 5-D box {10 x * 8 ch, 1 y, 1 z, 2 channel groups, 16 blocks}
 //               = 5 KB into a ring of stages; out-of-range x / block coordinates are zero-filled.
-//   warp 1      MMA issuer (one elected lane).
-//   warps 2..   epilogue groups of four warps (one per TMEM lane quadrant) taking finished output rows in turn:
+//   warp 1      MMA issuer (one elected lane): waits for `go`, issues 9 MMAs, commits.
+//   warp 2      scout: takes the waits that are not the issuer's own (data landed, accumulators drained) and signals `go`.
+//   warps 3..   epilogue groups of four warps (one per TMEM lane quadrant) taking finished output rows in turn:
 //               tcgen05.ld -> zero the slot (tcgen05.st) -> release -> +bias -> ReLU -> +residual -> bf16 hi[/lo] -> stores.
 #include <cuda.h>
 #include <string.h>
@@ -42,7 +43,9 @@ constexpr int CG_BYTES = PX * 16;           // 160 B between the two channel gro
 constexpr int TERM_BYTES = UNITS * UNIT_BYTES;   // 5120 B per precision term and input row
 constexpr int MAX_YO = 10;                  // output rows per tile: 10 * 3 * 16 = 480 TMEM columns
 constexpr int NGROUPS = 3;                  // epilogue groups of 4 warps
-constexpr int NUM_THREADS = 64 + NGROUPS * 128;
+constexpr int NUM_THREADS = NGROUPS * 128 + 96;   // epilogue groups, TMA producer, scout, MMA issuer
+constexpr int W_TMA = 4 * NGROUPS, W_SCOUT = W_TMA + 1, W_MMA = W_TMA + 2;   // the issuer gets the highest warp id: the warp
+                                                                             // schedulers favour it over the epilogue warps
 constexpr int MAX_STAGES = 12, MAX_SLOTS = 3 * MAX_YO;
 constexpr int BT_BYTES = 2 * 18 * 128;      // one B tile: N = 144 rows x K = 16 bf16 = 4608 B; [kcore 2][18 groups][8 n][8 k]
 constexpr int HEADER_BYTES = 1024;
@@ -60,8 +63,10 @@ struct Params {
 };
 
 struct __align__(8) Header {
-  uint64_t in_full[MAX_STAGES], in_empty[MAX_STAGES];
+  uint64_t in_full[MAX_STAGES], in_empty[MAX_STAGES], go[MAX_STAGES];
   uint64_t acc_full[MAX_SLOTS], acc_empty[MAX_SLOTS];
+  uint4 rows[MAX_YO + 2];   // per input row of the tile: {first TMEM column of its window, idesc, first B row group (16 B units),
+                            //  first slot of the first-touched output rows | count << 8 | first slot of the completed rows << 16 | count << 24}
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -78,6 +83,20 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void rows_done(int yi, int yi1, int y0, int Yo, int& lo, int& hi) {
   lo = yi - 1 > y0 ? yi - 1 : y0;
   hi = (yi == yi1 && yi <= y0 + Yo - 1) ? yi : yi - 1;
+}
+// one mbarrier probe (no spin): true when the phase with this parity has completed
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 
 template <int TERMS>
@@ -101,15 +120,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
   const int nslots = 3 * Yo;
 
   // ---- one-time setup ----
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
-    for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&hdr->in_full[i]), 1); mbar_init(smem_u32(&hdr->in_empty[i]), 1); }
+    for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&hdr->in_full[i]), 1); mbar_init(smem_u32(&hdr->in_empty[i]), 1); mbar_init(smem_u32(&hdr->go[i]), 1); }
     for (int i = 0; i < nslots; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 4); }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&hdr->tmem_base)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < yi1 - yi0 + 1) {
+    // the row pattern of the tile is the same for every plane: describe each input row once
+    const int yi = yi0 + threadIdx.x;
+    const int wlo = yi - 1 > y0 ? yi - 1 : y0, whi = yi + 1 < y1 - 1 ? yi + 1 : y1 - 1;
+    // first-touched output rows: the whole window for the tile's first input row, else row yi+1 (if it is in the tile);
+    // both these and the completed rows are contiguous ranges: {first slot index, count}
+    const int flo = yi == yi0 ? wlo : yi + 1, fhi = whi;
+    int rlo, rhi;
+    rows_done(yi, yi1, y0, Yo, rlo, rhi);
+    const uint32_t fcnt = fhi >= flo ? fhi - flo + 1 : 0, dcnt = rhi >= rlo ? rhi - rlo + 1 : 0;
+    hdr->rows[threadIdx.x] = make_uint4((uint32_t)(wlo - y0) * 48u, make_idesc((whi - wlo + 1) * 48), (uint32_t)(wlo - (yi - 1)) * (6 * 128 / 16),
+                                        (uint32_t)(flo - y0) * 3u | fcnt << 8 | (uint32_t)((rlo - y0) * 3) << 16 | dcnt << 24);
   }
   for (int i = threadIdx.x * 16; i < WBYTES; i += NUM_THREADS * 16)
     *reinterpret_cast<int4*>(wsm + i) = __ldg(reinterpret_cast<const int4*>(p.wimg + i));
@@ -119,7 +151,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, hdr->tmem_base, 0);
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t s = 0, phase = 0;
@@ -135,7 +167,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
           if (++s == (uint32_t)p.nstage) { s = 0; phase ^= 1; }
         }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     // Output (pz, y') -- pz in [-1, D] counting the two virtual planes -- lives in slot (y'-y0)*3 + (pz+1)%3 and is that slot's
     // use number (pz+1)/3.  All waits are taken by the whole warp (uniform); one elected lane issues the tcgen05 instructions.
@@ -145,50 +177,95 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
     const uint32_t a_hi = (uint32_t)(adesc >> 32), a_lo_proto = (uint32_t)adesc;
     const uint32_t b_hi = (uint32_t)(bdesc >> 32), b_lo0 = (uint32_t)bdesc;
     const uint32_t stages16 = smem_u32(stages) / 16;
+    // The issuing thread's instruction stream is the critical path (one warp runs ~5 cycles per dependent instruction and the
+    // MMA queue holds only a few instructions): the scout warp takes every wait that is not the issuer's own (data landed,
+    // accumulators drained) and signals `go`; the row records are broadcast with shuffles so that the descriptor arithmetic
+    // stays on the uniform datapath; the next row's record is fetched between the MMAs of the current row (while the queue
+    // drains); the common case -- one completed output row, interior plane -- commits without any index arithmetic.
+    const int nrows = yi1 - yi0 + 1;
+    const bool leader = elect_one();
     uint32_t s = 0, in_phase = 0;
+    uint32_t a_s = a_lo_proto + stages16;
+    uint32_t go_bar = smem_u32(&hdr->go[0]), empty_bar = smem_u32(&hdr->in_empty[0]);
+    const uint32_t full_base = smem_u32(&hdr->acc_full[0]);
+    auto fetch = [&](int j, uint32_t& d0, uint32_t& idesc, uint32_t& brel, uint32_t& rw) {
+      const uint4 rl = hdr->rows[j];
+      d0 = tmem_base + __shfl_sync(0xffffffffu, rl.x, 0);
+      idesc = __shfl_sync(0xffffffffu, rl.y, 0);
+      brel = __shfl_sync(0xffffffffu, rl.z, 0);
+      rw = __shfl_sync(0xffffffffu, rl.w, 0);
+    };
+    uint32_t d0, idesc, brel, rw;
+    fetch(0, d0, idesc, brel, rw);
+    uint32_t zs_done8 = 0;   // byte offset of z-slot (z % 3) inside a row's three acc_full barriers: plane z-1 has gp = z
     for (int z = 0; z < D; ++z) {
-      const uint32_t rot = (uint32_t)(z + 1) % 3u;
-      for (int yi = yi0; yi <= yi1; ++yi) {
-        mbar_wait(smem_u32(&hdr->in_full[s]), in_phase);
-        // window of output rows fed by this input row
-        const int wlo = yi - 1 > y0 ? yi - 1 : y0, whi = yi + 1 < y1 - 1 ? yi + 1 : y1 - 1;
-        // accumulators touched for the first time by this row must have been drained (and zeroed) by the epilogue
-        for (int yo = wlo; yo <= whi; ++yo) {
-          if (!(yo == yi + 1 || yi == yi0)) continue;
-          for (int pz = (z == 0 ? -1 : z + 1); pz <= z + 1; ++pz) {
-            const uint32_t gp = (uint32_t)(pz + 1);
-            mbar_wait(smem_u32(&hdr->acc_empty[(yo - y0) * 3 + (int)(gp % 3u)]), (gp / 3u) & 1u);
-          }
-        }
+      const uint32_t b_z = b_lo0 + (((uint32_t)(z + 1) % 3u) * 3u) * TERMS * (BT_BYTES / 16);
+      const bool fast_z = z != D - 1;
+      for (int j = 0; j < nrows; ++j) {
+        const uint32_t b0 = b_z + brel;
+        mbar_wait(go_bar, in_phase);
         tc_fence_after();
-        const uint32_t a_lo0 = a_lo_proto + stages16 + s * (STAGE_BYTES / 16);
-        const uint32_t d0 = tmem_base + (uint32_t)(wlo - y0) * 48u;
-        const uint32_t idesc = make_idesc((whi - wlo + 1) * 48);
-        const uint32_t b_row16 = (uint32_t)(wlo - (yi - 1)) * (6 * 128 / 16);     // first B row group of the window
-        if (elect_one()) {
+        if (leader) {
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-            for (int pr = 0; pr < npairs; ++pr) {
-              const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-              umma_bf16_lh(d0, a_lo0 + ta * (TERM_BYTES / 16) + (uint32_t)kx, a_hi,
-                           b_lo0 + ((rot * 3 + (uint32_t)kx) * TERMS + tb) * (BT_BYTES / 16) + b_row16, b_hi, idesc, 1u);
-            }
+          for (int i = 0; i < 4; ++i) {
+            const int kx = i / npairs, pr = i % npairs;
+            if (i >= 3 * npairs) break;
+            const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+            umma_bf16_lh(d0, a_s + ta * (TERM_BYTES / 16) + (uint32_t)kx, a_hi, b0 + ((uint32_t)kx * TERMS + tb) * (BT_BYTES / 16), b_hi, idesc, 1u);
           }
-          umma_commit(smem_u32(&hdr->in_empty[s]));
-          int rlo, rhi;
-          rows_done(yi, yi1, y0, Yo, rlo, rhi);
-          const int plo = z - 1, phi = z == D - 1 ? D : z - 1;
-          for (int pz = plo; pz <= phi; ++pz)
-            for (int yo = rlo; yo <= rhi; ++yo) umma_commit(smem_u32(&hdr->acc_full[(yo - y0) * 3 + (pz + 1) % 3]));
         }
-        __syncwarp();
-        if (++s == (uint32_t)p.nstage) { s = 0; in_phase ^= 1; }
+        // next row's record (wraps to the first row of the next plane); consumed after this row's last MMA
+        uint32_t nd0, nidesc, nbrel, nrw;
+        fetch(j + 1 < nrows ? j + 1 : 0, nd0, nidesc, nbrel, nrw);
+        if (leader) {
+#pragma unroll
+          for (int i = 4; i < 3 * npairs; ++i) {
+            const int kx = i / npairs, pr = i % npairs;
+            const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+            umma_bf16_lh(d0, a_s + ta * (TERM_BYTES / 16) + (uint32_t)kx, a_hi, b0 + ((uint32_t)kx * TERMS + tb) * (BT_BYTES / 16), b_hi, idesc, 1u);
+          }
+          umma_commit(empty_bar);
+          const uint32_t dfirst = (rw >> 16) & 0xffu, dcnt = rw >> 24;
+          if (fast_z && dcnt <= 1) {
+            if (dcnt) umma_commit(full_base + dfirst * 8 + zs_done8);
+          } else {
+            const uint32_t gdone1 = z == D - 1 ? (uint32_t)z + 2u : (uint32_t)z;
+            for (uint32_t g = (uint32_t)z; g <= gdone1; ++g)
+              for (uint32_t k = 0; k < dcnt; ++k) umma_commit(full_base + (dfirst + 3 * k + g % 3u) * 8);
+          }
+        }
+        d0 = nd0; idesc = nidesc; brel = nbrel; rw = nrw;
+        a_s += STAGE_BYTES / 16; go_bar += 8; empty_bar += 8;
+        if (++s == (uint32_t)p.nstage) {
+          s = 0; in_phase ^= 1; a_s = a_lo_proto + stages16;
+          go_bar = smem_u32(&hdr->go[0]); empty_bar = smem_u32(&hdr->in_empty[0]);
+        }
+      }
+      zs_done8 = zs_done8 == 16 ? 0 : zs_done8 + 8;
+    }
+  } else if (warp == W_SCOUT) {
+    // ================= scout =================
+    // row (z, yi) may be issued once its data has landed and the accumulators it touches for the first time -- plane z+1
+    // (planes -1, 0, 1 for z = 0), rows from the row record -- have been drained and zeroed by the epilogue
+    if (lane == 0) {
+      const int nrows = yi1 - yi0 + 1;
+      uint32_t s = 0, phase = 0;
+      for (int z = 0; z < D; ++z) {
+        const uint32_t gnew0 = z == 0 ? 0u : (uint32_t)z + 2u, gnew1 = (uint32_t)z + 2u;
+        for (int j = 0; j < nrows; ++j) {
+          const uint32_t rw = hdr->rows[j].w;
+          const uint32_t ffirst = rw & 0xffu, fcnt = (rw >> 8) & 0xffu;
+          for (uint32_t g = gnew0; g <= gnew1; ++g)
+            for (uint32_t k = 0; k < fcnt; ++k) mbar_wait(smem_u32(&hdr->acc_empty[ffirst + 3 * k + g % 3u]), (g / 3u) & 1u);
+          mbar_wait(smem_u32(&hdr->in_full[s]), phase);
+          mbar_arrive(smem_u32(&hdr->go[s]));
+          if (++s == (uint32_t)p.nstage) { s = 0; phase ^= 1; }
+        }
       }
     }
   } else {
     // ================= epilogue =================
-    const int ew = warp - 2;
+    const int ew = warp;
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access (warp id % 4)
     const int grp = ew >> 2;
     const int row = quad * 32 + lane; // M row = TMEM lane
@@ -208,15 +285,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
       if (lane == 0)
         for (int i = 0; i < nslots; ++i) mbar_arrive(smem_u32(&hdr->acc_empty[i]));
     }
-    uint32_t q = 0;
+    // group g drains output rows y0+g, y0+g+NGROUPS, ...: per accumulator slot the uses come in plane order, which is all the
+    // hand-over protocol needs; no scan over the other groups' units
     for (int z = 0; z < D; ++z) {
       const int plo = z - 1, phi = z == D - 1 ? D : z - 1;
-      for (int yi = yi0; yi <= yi1; ++yi) {
-        int rlo, rhi;
-        rows_done(yi, yi1, y0, Yo, rlo, rhi);
-        for (int pz = plo; pz <= phi; ++pz)
-          for (int yo = rlo; yo <= rhi; ++yo, ++q) {
-            if ((int)(q % NGROUPS) != grp) continue;
+      for (int yo = y0 + grp; yo < y1; yo += NGROUPS) {
+        for (int pz = plo; pz <= phi; ++pz) {
+          {
             const bool real = pz >= 0 && pz < D;
             const long long vox = (long long)pz * HW + (long long)yo * p.W + x;
             // the residual operand does not depend on the accumulator: fetch it before waiting
@@ -278,6 +353,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
               }
             }
           }
+        }
       }
     }
   }
@@ -285,7 +361,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
