@@ -99,6 +99,39 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
+// tcgen05.mma / tcgen05.commit predicated on `lead` (1 in exactly one lane): no branch around the instruction, so the issue loop
+// has no divergence / reconvergence points
+__device__ __forceinline__ void umma_bf16_lh_if(uint32_t lead, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 q, %6, 0;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(lead)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t lead, uint32_t bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar),
+      "r"(lead)
+      : "memory");
+}
+// the rare commits of the issue loop (last plane: three planes complete per row; bottom tile: two rows complete at once)
+__device__ __noinline__ void commit_many(uint32_t lead, uint32_t full_base, uint32_t dfirst, uint32_t dcnt, uint32_t g0, uint32_t g1) {
+  for (uint32_t g = g0; g <= g1; ++g)
+    for (uint32_t k = 0; k < dcnt; ++k) umma_commit_if(lead, full_base + ((dfirst + k) * 3 + g % 3u) * 8);
+}
+
 template <int TERMS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -178,63 +211,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
     const uint32_t b_hi = (uint32_t)(bdesc >> 32), b_lo0 = (uint32_t)bdesc;
     const uint32_t stages16 = smem_u32(stages) / 16;
     // The issuing thread's instruction stream is the critical path (one warp runs ~5 cycles per dependent instruction and the
-    // MMA queue holds only a few instructions): the scout warp takes every wait that is not the issuer's own (data landed,
-    // accumulators drained) and signals `go`; the row records are broadcast with shuffles so that the descriptor arithmetic
-    // stays on the uniform datapath; the next row's record is fetched between the MMAs of the current row (while the queue
-    // drains); the common case -- one completed output row, interior plane -- commits without any index arithmetic.
+    // MMA queue holds only a few instructions).  So: the scout warp takes every wait that is not the issuer's own (data landed,
+    // accumulators drained) and signals `go`; everything a row needs is computed from block-uniform values (no shared-memory
+    // table, no vector-to-uniform register moves); the tcgen05 instructions are predicated on the elected lane instead of
+    // branched around; the rare multi-commit cases live in a separate function.
     const int nrows = yi1 - yi0 + 1;
-    const bool leader = elect_one();
+    const uint32_t lead = elect_one() ? 1u : 0u;
     uint32_t s = 0, in_phase = 0;
     uint32_t a_s = a_lo_proto + stages16;
     uint32_t go_bar = smem_u32(&hdr->go[0]), empty_bar = smem_u32(&hdr->in_empty[0]);
     const uint32_t full_base = smem_u32(&hdr->acc_full[0]);
-    auto fetch = [&](int j, uint32_t& d0, uint32_t& idesc, uint32_t& brel, uint32_t& rw) {
-      const uint4 rl = hdr->rows[j];
-      d0 = tmem_base + __shfl_sync(0xffffffffu, rl.x, 0);
-      idesc = __shfl_sync(0xffffffffu, rl.y, 0);
-      brel = __shfl_sync(0xffffffffu, rl.z, 0);
-      rw = __shfl_sync(0xffffffffu, rl.w, 0);
-    };
-    uint32_t d0, idesc, brel, rw;
-    fetch(0, d0, idesc, brel, rw);
+    constexpr uint32_t idesc0 = make_idesc(0);
     uint32_t zs_done8 = 0;   // byte offset of z-slot (z % 3) inside a row's three acc_full barriers: plane z-1 has gp = z
     for (int z = 0; z < D; ++z) {
       const uint32_t b_z = b_lo0 + (((uint32_t)(z + 1) % 3u) * 3u) * TERMS * (BT_BYTES / 16);
       const bool fast_z = z != D - 1;
-      for (int j = 0; j < nrows; ++j) {
-        const uint32_t b0 = b_z + brel;
+      for (int yi = yi0; yi <= yi1; ++yi) {
+        const int wlo = yi - 1 > y0 ? yi - 1 : y0, whi = yi + 1 < y1 - 1 ? yi + 1 : y1 - 1;
+        const uint32_t d0 = tmem_base + (uint32_t)(wlo - y0) * 48u;
+        const uint32_t idesc = idesc0 | ((uint32_t)(whi - wlo + 1) * 6u) << 17;
+        const uint32_t b0 = b_z + (uint32_t)(wlo - yi + 1) * (6 * 128 / 16);
+        const int rhi = (yi == yi1 && yi <= y1 - 1) ? yi : yi - 1;    // completed output rows: [wlo, rhi]
         mbar_wait(go_bar, in_phase);
         tc_fence_after();
-        if (leader) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int kx = i / npairs, pr = i % npairs;
-            if (i >= 3 * npairs) break;
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int pr = 0; pr < npairs; ++pr) {
             const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-            umma_bf16_lh(d0, a_s + ta * (TERM_BYTES / 16) + (uint32_t)kx, a_hi, b0 + ((uint32_t)kx * TERMS + tb) * (BT_BYTES / 16), b_hi, idesc, 1u);
+            umma_bf16_lh_if(lead, d0, a_s + ta * (TERM_BYTES / 16) + (uint32_t)kx, a_hi, b0 + ((uint32_t)kx * TERMS + tb) * (BT_BYTES / 16), b_hi, idesc);
           }
         }
-        // next row's record (wraps to the first row of the next plane); consumed after this row's last MMA
-        uint32_t nd0, nidesc, nbrel, nrw;
-        fetch(j + 1 < nrows ? j + 1 : 0, nd0, nidesc, nbrel, nrw);
-        if (leader) {
-#pragma unroll
-          for (int i = 4; i < 3 * npairs; ++i) {
-            const int kx = i / npairs, pr = i % npairs;
-            const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-            umma_bf16_lh(d0, a_s + ta * (TERM_BYTES / 16) + (uint32_t)kx, a_hi, b0 + ((uint32_t)kx * TERMS + tb) * (BT_BYTES / 16), b_hi, idesc, 1u);
-          }
-          umma_commit(empty_bar);
-          const uint32_t dfirst = (rw >> 16) & 0xffu, dcnt = rw >> 24;
-          if (fast_z && dcnt <= 1) {
-            if (dcnt) umma_commit(full_base + dfirst * 8 + zs_done8);
-          } else {
-            const uint32_t gdone1 = z == D - 1 ? (uint32_t)z + 2u : (uint32_t)z;
-            for (uint32_t g = (uint32_t)z; g <= gdone1; ++g)
-              for (uint32_t k = 0; k < dcnt; ++k) umma_commit(full_base + (dfirst + 3 * k + g % 3u) * 8);
-          }
-        }
-        d0 = nd0; idesc = nidesc; brel = nbrel; rw = nrw;
+        umma_commit_if(lead, empty_bar);
+        if (fast_z && rhi == wlo) umma_commit_if(lead, full_base + (uint32_t)(wlo - y0) * 24u + zs_done8);
+        else if (rhi >= wlo) commit_many(lead, full_base, (uint32_t)(wlo - y0), (uint32_t)(rhi - wlo + 1), (uint32_t)z, fast_z ? (uint32_t)z : (uint32_t)z + 2u);
         a_s += STAGE_BYTES / 16; go_bar += 8; empty_bar += 8;
         if (++s == (uint32_t)p.nstage) {
           s = 0; in_phase ^= 1; a_s = a_lo_proto + stages16;

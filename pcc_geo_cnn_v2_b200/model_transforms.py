@@ -91,7 +91,7 @@ _ys_enabled = [False]
 _hl_enabled = [True]
 
 # The zy-ring 16-channel kernel (conv3d_umma_zy.cu): y and z taps accumulated in a 2-D TMEM ring, N = 144 MMAs.
-_zy_enabled = [False]
+_zy_enabled = [True]
 
 # bumped whenever any layer's parameters change: captured CUDA graphs (model_types) hold device pointers of packed weights
 params_epoch = [0]
