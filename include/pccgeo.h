@@ -168,6 +168,9 @@ size_t pccgeo_reduce_ws_doubles(void);
  * sparse_to_dense (src/model_types.py:108-114): scatter 1.0f at integer coords.  coords: int16 (npts,4) =
  * (block, z, y, x); x must be zero-initialised by the caller (cudaMemsetAsync). */
 int pccgeo_densify(const int16_t* coords, long long npts, float* x, int n, int d, int h, int wd, void* stream);
+/* same, for rows that carry GLOBAL block indexes (the output of pccgeo_octree_partition_scatter): rows of blocks
+ * [block0, block0 + n) are written, the others skipped */
+int pccgeo_densify_from(const int16_t* coords, long long npts, int block0, float* x, int n, int d, int h, int wd, void* stream);
 /* decompress_blocks / compress_blocks thresholding (src/model_types.py:201-202,209,233-234):
  * bit = min(x_hat,1) > threshold[block]; packed little-endian, 32 voxels per uint32 word in C order;
  * counts[block] = number of set bits.  voxels per block must be a multiple of 32. */
@@ -266,6 +269,17 @@ int pccgeo_bits_to_points_host(const uint32_t* bits, int n_blocks, int d, int h,
  * input of pccgeo_densify.  Values are truncated like numpy's float -> int16 cast. */
 int pccgeo_blocks_to_coords_host(const void* const* blocks, const long long* counts, const long long* row_bytes,
                                  int n_blocks, int is_f64, int16_t* out, int threads);
+
+/* partition_octree (src/utils/octree_coding.py:68-113) on the GPU: stable counting sort of the points by the Morton key of their
+ * block.  Two asynchronous stages around one small read-back (the number of occupied blocks): see csrc/octree.cu.
+ * rows: device float64 (n, cols >= 3), coordinates in [0, block_size * 2^level); out_rows: grouped rows in local coordinates
+ * (points of a block keep their input order) and / or out_coords: int16 (block, i0, i1, i2) rows for pccgeo_densify_from;
+ * offsets: device int64 (n_blocks + 1). */
+size_t pccgeo_octree_ws_bytes(long long n, int level);
+size_t pccgeo_octree_ws2_bytes(long long n, int n_blocks);
+int pccgeo_octree_partition_keys(const double* rows, long long n, int cols, double block_size, int level, void* ws, void* stream);
+int pccgeo_octree_partition_scatter(const double* rows, long long n, int cols, double block_size, int level, int n_blocks,
+                                    const void* ws, void* ws2, double* out_rows, int16_t* out_coords, long long* offsets, void* stream);
 
 /* Host half of partition_octree (src/utils/octree_coding.py:103-111): stable counting sort of float64 point rows (n, cols)
  * by block index, block origins (n_blocks, 3) subtracted from the first three columns; offsets = (n_blocks + 1) prefix sums. */

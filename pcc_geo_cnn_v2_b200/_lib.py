@@ -67,6 +67,11 @@ SIGNATURES = {
     'pccgeo_threshold_hist': (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     'pccgeo_threshold_sum_ab': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_blocks_to_coords_host': (i32, [vp, vp, vp, i32, i32, vp, i32]),
+    'pccgeo_densify_from': (i32, [vp, i64, i32, vp, i32, i32, i32, i32, vp]),
+    'pccgeo_octree_ws_bytes': (C.c_size_t, [i64, i32]),
+    'pccgeo_octree_ws2_bytes': (C.c_size_t, [i64, i32]),
+    'pccgeo_octree_partition_keys': (i32, [vp, i64, i32, C.c_double, i32, vp, vp]),
+    'pccgeo_octree_partition_scatter': (i32, [vp, i64, i32, C.c_double, i32, i32, vp, vp, vp, vp, vp, vp]),
     'pccgeo_group_points_host': (i32, [vp, vp, i64, i32, i32, vp, vp, vp]),
     'pccgeo_bits_to_points_host': (i32, [vp, i32, i32, i32, i32, vp, vp, i64, i32]),
 }

@@ -3,7 +3,8 @@
     blob, info = compress_point_cloud(model, points, resolution, octree_level, ...)      # compress_octree.py:60-113
     points_hat = decompress_point_cloud(model, blob)                                      # decompress_octree.py:30-60,127-140
 
-Everything between the file formats runs on this package's modules: octree partitioning (C++ counting sort), the batched
+Everything between the file formats runs on this package's modules: octree partitioning (GPU counting sort, csrc/octree.cu; or the
+C++ host version), the batched
 GPU block loops, the per-block threshold search on the GPU, the byte-compatible container, gzip."""
 import gzip
 import io
@@ -11,17 +12,22 @@ import io
 import numpy as np
 
 from .model_syntax import load_compressed_file, save_compressed_file
-from .octree_coding import departition_octree, partition_octree
+from .octree_coding import departition_octree, partition_octree, partition_octree_gpu
 
 
 def compress_point_cloud(model, points, resolution, octree_level, opt_metrics=('d1_mse',), max_deltas=(np.inf,),
-                         fixed_threshold=False, with_normals=False):
+                         fixed_threshold=False, with_normals=False, partition='gpu'):
     """-> (list of gzip'd container bytes, one per selected opt-metric group; list of metadata dicts with 'metrics' and
     'blocks_full', as compress_octree.py writes them to .enc.metric.json / the decoded PLY)"""
     assert resolution > 0, 'resolution must be positive'
     points = np.asarray(points, np.float64)
     block_size = resolution // (2 ** octree_level)
-    blocks, binstr = partition_octree(points, [0, 0, 0], [resolution] * 3, octree_level)
+    if partition == 'gpu' and 1 <= octree_level <= 6 and len(points):
+        # octree partition on the GPU (csrc/octree.cu); with a fixed threshold the blocks never return to the host: the block
+        # loops densify batches straight from the grouped device rows
+        blocks, binstr = partition_octree_gpu(points, [0, 0, 0], [resolution] * 3, octree_level, device=bool(fixed_threshold))
+    else:
+        blocks, binstr = partition_octree(points, [0, 0, 0], [resolution] * 3, octree_level)
     model.compress((1, 1, block_size, block_size, block_size))
     data_list, data, _ = model.compress_blocks(None, blocks, binstr, points, resolution, octree_level, with_normals=with_normals,
                                                opt_metrics=tuple(opt_metrics), max_deltas=tuple(max_deltas),

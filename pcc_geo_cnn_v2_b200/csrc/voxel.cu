@@ -6,9 +6,10 @@
 namespace pccgeo {
 
 __global__ void densify_kernel(const int16_t* __restrict__ coords, long long npts, float* __restrict__ x, int N, int D,
-                               int H, int W, int* __restrict__ err) {
+                               int H, int W, int* __restrict__ err, int block0) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += (long long)gridDim.x * blockDim.x) {
-    const short4 c = reinterpret_cast<const short4*>(coords)[i];  // (block, z, y, x)
+    short4 c = reinterpret_cast<const short4*>(coords)[i];  // (block, z, y, x)
+    c.x = (short)(c.x - block0);
     if (c.x < 0 || c.x >= N || c.y < 0 || c.y >= D || c.z < 0 || c.z >= H || c.w < 0 || c.w >= W) continue;
     x[(((long long)c.x * D + c.y) * H + c.z) * W + c.w] = 1.0f;
   }
@@ -63,7 +64,17 @@ extern "C" int pccgeo_densify(const int16_t* coords, long long npts, float* x, i
   PCCGEO_REQUIRE(coords, "densify: null coords");
   long long b = (npts + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
-  densify_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(coords, npts, x, n, d, h, wd, nullptr);
+  densify_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(coords, npts, x, n, d, h, wd, nullptr, 0);
+  return check_launch("densify_kernel");
+}
+
+extern "C" int pccgeo_densify_from(const int16_t* coords, long long npts, int block0, float* x, int n, int d, int h, int wd, void* stream) {
+  PCCGEO_REQUIRE(x && n > 0 && d > 0 && h > 0 && wd > 0 && npts >= 0 && block0 >= 0, "densify_from: bad argument");
+  if (npts == 0) return PCCGEO_OK;
+  PCCGEO_REQUIRE(coords, "densify_from: null coords");
+  long long b = (npts + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  densify_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(coords, npts, x, n, d, h, wd, nullptr, block0);
   return check_launch("densify_kernel");
 }
 

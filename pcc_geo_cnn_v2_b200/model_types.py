@@ -253,6 +253,16 @@ def split_debug(batch_tensors, strings, static=None):
     return out
 
 
+class _DeviceSpan:
+    """One batch of a DeviceBlocks input, with the future-like surface of the host packing tasks."""
+
+    def __init__(self, coords, block0):
+        self.coords, self.block0 = coords, block0
+
+    def result(self):
+        return self.coords
+
+
 class _PinnedPool:
     """Recycled pinned host staging buffers.  cudaHostAlloc costs milliseconds and stalls the driver thread of the block
     loops (torch's caching host allocator falls back to it whenever every cached block still has a copy in flight), so
@@ -424,12 +434,12 @@ class CompressionModel:
                                        'thr': torch.zeros(n, device='cuda'), **self._static_latents(n, dims)}
         return st
 
-    def device_encode(self, coords_dev, n, dims, thr):
+    def device_encode(self, coords_dev, n, dims, thr, block0=None):
         """densify -> analysis [-> hyper] -> quantise (latents) -> synthesis + threshold + pack, as stage graphs.
         coords_dev: CUDA int16 (npts,4); thr: CUDA fp32 (n,) or a host array.  -> (latent dict, bits).  `on_latents`
         work (the symbol D2H) goes between the two graphs: see encode_blocks."""
         st = self._static(n, dims)
-        ops.densify(coords_dev, n, *dims, out=st['x'])
+        ops.densify(coords_dev, n, *dims, out=st['x'], block0=block0)
         lat = self._stage('latents', n, dims, lambda: self._latents(st['x']))
         return lat, st
 
@@ -505,6 +515,8 @@ class CompressionModel:
     @staticmethod
     def _h2d_staged(staged):
         """(pinned host tensor, pool buffer) from a host worker -> new CUDA tensor (async on the current stream)."""
+        if torch.is_tensor(staged):   # already on the device (octree partition on the GPU)
+            return staged
         host, buf = staged
         dst = torch.empty(host.shape, dtype=host.dtype, device='cuda')
         if host.numel():
@@ -530,7 +542,12 @@ class CompressionModel:
         dims = [int(s) for s in (x_shape if x_shape is not None else self.x_shape)][-3:]
         spans = [(i, min(i + self.batch_size, len(blocks))) for i in range(0, len(blocks), self.batch_size)]
         pool = self._pool()
-        coords_f = [pool.submit(blocks_to_coords, blocks[a:b], self.coder_threads, True) for a, b in spans]
+        from .octree_coding import DeviceBlocks
+        if isinstance(blocks, DeviceBlocks):
+            # blocks partitioned on the GPU (octree_coding.partition_octree_gpu): batches are slices of the grouped device rows
+            coords_f = [_DeviceSpan(blocks.coords[int(blocks.offsets[a]):int(blocks.offsets[b])], a) for a, b in spans]
+        else:
+            coords_f = [pool.submit(blocks_to_coords, blocks[a:b], self.coder_threads, True) for a, b in spans]
 
         def post(dev, pend):
             strings = self._encode_host(dev, self._wait(pend['sym']))
@@ -549,13 +566,13 @@ class CompressionModel:
             if len(post_f) >= self.pipeline_depth + 4:  # bound the driver's run-ahead (staging memory in flight)
                 post_f[len(post_f) - self.pipeline_depth - 4].result()
             if graphs:
-                lat, st = self.device_encode(self._h2d_staged(cf.result()), b - a, dims, None)
+                lat, st = self.device_encode(self._h2d_staged(cf.result()), b - a, dims, None, block0=getattr(cf, 'block0', None))
                 pend = {'sym': self._d2h(*self._latent_tensors(lat))}
                 pend['bits'] = self._d2h(self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b])))
                 xs.append(None)
                 post_f.append(pool.submit(post, lat, pend))
                 continue
-            x = ops.densify(self._h2d_staged(cf.result()), b - a, *dims)
+            x = ops.densify(self._h2d_staged(cf.result()), b - a, *dims, block0=getattr(cf, 'block0', None))
             pend = {}
             t = self._h2d(threshold_f32(self.thresholds, thr_idx[a:b])) if thr_idx is not None else None
             # the symbol D2H is enqueued BEFORE synthesis is launched: range coding overlaps the synthesis kernels
@@ -608,7 +625,8 @@ class CompressionModel:
                 opt_metrics_ret = list(opt_metrics)
                 thr_idx = np.full((n, len(opt_metrics_ret)), len(self.thresholds) // 2, np.int64)
             else:
-                thr_idx, opt_metrics_ret = self._optimal_thresholds(blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas)
+                host_blocks = blocks.to_host() if hasattr(blocks, 'to_host') else blocks
+                thr_idx, opt_metrics_ret = self._optimal_thresholds(host_blocks, x_hat, resolution, with_normals, opt_metrics, max_deltas)
             x_hat_list = []
             for m in range(thr_idx.shape[1] if n else 0):
                 t = self._h2d(threshold_f32(self.thresholds, thr_idx[:, m]))
@@ -731,7 +749,8 @@ class CompressionModel:
                         big[k] = torch.empty((g1 - g0,) + tuple(l['shape']), dtype=torch.int32, device='cuda')
                         big[k].record_stream(side)
             for a, b in group:
-                lat, st = self.device_encode(self._h2d_staged(cf_of[(a, b)].result()), b - a, dims, None)
+                cf = cf_of[(a, b)]
+                lat, st = self.device_encode(self._h2d_staged(cf.result()), b - a, dims, None, block0=getattr(cf, 'block0', None))
                 for k, t in big.items():
                     t[a - g0:b - g0].copy_(lat[k].view(t[a - g0:b - g0].shape))
                 pend = self._d2h(self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b])))

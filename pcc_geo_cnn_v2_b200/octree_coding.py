@@ -83,6 +83,76 @@ def partition_octree(points, bbox_min, bbox_max, level):
     return blocks, _binstr(uniq, level)
 
 
+class DeviceBlocks:
+    """Result of partition_octree_gpu(..., device=True): the blocks stay on the GPU as int16 (block, i0, i1, i2) rows grouped by
+    block (global block index, Morton order) -- the block loops densify batches straight from it (no host partition, no
+    per-batch coordinate packing, no H2D of coordinates).  len() / counts / to_host() give the reference's view."""
+
+    def __init__(self, coords, offsets, rows=None, cols=3):
+        self.coords, self.offsets, self._rows, self.cols = coords, np.asarray(offsets, np.int64), rows, cols
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    @property
+    def counts(self):
+        return np.diff(self.offsets)
+
+    def to_host(self):
+        """list of float64 (n_i, cols) arrays in local coordinates, as partition_octree returns them"""
+        if self._rows is not None:
+            out = self._rows.cpu().numpy()
+        else:
+            out = self.coords[:, 1:].cpu().numpy().astype(np.float64)
+        return [out[self.offsets[i]:self.offsets[i + 1]] for i in range(len(self))]
+
+
+def partition_octree_gpu(points, bbox_min, bbox_max, level, device=False):
+    """partition_octree (octree_coding.py:68-113) as a stable counting sort on the GPU (csrc/octree.cu): same blocks, block
+    order, in-block point order and occupancy bytes.  device=False -> (list of float64 blocks on the host, binstr) exactly like
+    partition_octree; device=True -> (DeviceBlocks, binstr) for compress_blocks without the coordinates ever returning to the
+    host.  1 <= level <= 6."""
+    import torch
+    points = np.asarray(points)
+    if len(points) == 0 or level == 0:
+        return [points], None
+    np.testing.assert_array_equal(np.asarray(bbox_min), [0, 0, 0])
+    geo_level = int(np.ceil(np.log2(np.max(np.asarray(bbox_max)))))
+    assert geo_level >= level and 1 <= level <= 6
+    block_size = float(2 ** (geo_level - level))
+    L.require_cuda()
+    rows = torch.from_numpy(np.ascontiguousarray(points, np.float64)).cuda()
+    n, cols = rows.shape
+    lib = L.lib()
+    ws_bytes = int(lib.pccgeo_octree_ws_bytes(n, level))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+    L.check(lib.pccgeo_octree_partition_keys(L.ptr(rows), n, cols, block_size, level, L.ptr(ws), L.stream_ptr()), 'octree_partition_keys')
+    meta = ws[ws_bytes - 64:ws_bytes - 56].view(torch.int32).cpu().numpy()     # the one read-back: number of occupied blocks
+    if int(meta[1]):
+        raise ValueError('partition_octree: coordinates outside [0, block_size * 2^level)')
+    nb = int(meta[0])
+    ws2 = torch.empty(int(lib.pccgeo_octree_ws2_bytes(n, nb)), dtype=torch.uint8, device='cuda')
+    offsets = torch.empty(nb + 1, dtype=torch.int64, device='cuda')
+    out_rows = None if device and cols == 3 else torch.empty_like(rows)
+    coords = torch.empty((n, 4), dtype=torch.int16, device='cuda') if device else None
+    L.check(lib.pccgeo_octree_partition_scatter(L.ptr(rows), n, cols, block_size, level, nb, L.ptr(ws), L.ptr(ws2), L.ptr(out_rows),
+                                                L.ptr(coords), L.ptr(offsets), L.stream_ptr()), 'octree_partition_scatter')
+    n_keys = 1 << (3 * level)
+    kb = (n * 4 + 255) // 256 * 256
+    present = ws[kb:kb + 4 * n_keys].view(torch.int32).cpu().numpy()
+    ukeys = np.flatnonzero(present).astype(np.uint64)
+    uniq = np.zeros((len(ukeys), 3), np.uint32)
+    for b in range(level):
+        for axis in range(3):
+            uniq[:, axis] |= (((ukeys >> np.uint64(3 * b + axis)) & np.uint64(1)) << np.uint64(b)).astype(np.uint32)
+    binstr = _binstr(uniq, level)
+    offs = offsets.cpu().numpy()
+    if device:
+        return DeviceBlocks(coords, offs, out_rows, cols), binstr
+    host = out_rows.cpu().numpy()
+    return [host[offs[i]:offs[i + 1]] for i in range(nb)], binstr
+
+
 def departition_octree(blocks, binstr_list, bbox_min, bbox_max, level):
     """octree_coding.py:116-169: adds every block's origin back (blocks in the order partition_octree emits them)."""
     bbox_min, bbox_max = np.asarray(bbox_min), np.asarray(bbox_max)

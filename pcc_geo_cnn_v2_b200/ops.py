@@ -292,8 +292,9 @@ def i32_to_f32(sym):
 
 
 # ---- voxel helpers -------------------------------------------------------------------------------------
-def densify(coords_i16, n, d, h, w, out=None):
-    """coords_i16: CUDA int16 (npts, 4) rows (block, z, y, x) -> fp32 (n,1,d,h,w) occupancy."""
+def densify(coords_i16, n, d, h, w, out=None, block0=None):
+    """coords_i16: CUDA int16 (npts, 4) rows (block, z, y, x) -> fp32 (n,1,d,h,w) occupancy.  block0: the rows carry global
+    block indexes (octree partition on the device); blocks [block0, block0 + n) are written."""
     L.require_cuda()
     if out is None:
         out = torch.zeros((n, 1, d, h, w), device='cuda', dtype=torch.float32)
@@ -302,6 +303,10 @@ def densify(coords_i16, n, d, h, w, out=None):
     npts = 0 if coords_i16 is None else coords_i16.shape[0]
     if npts:
         assert coords_i16.is_cuda and coords_i16.dtype == torch.int16 and coords_i16.is_contiguous()
+    if block0 is not None:
+        L.check(L.lib().pccgeo_densify_from(L.ptr(coords_i16) if npts else None, npts, int(block0), L.ptr(out), n, d, h, w, L.stream_ptr()),
+                'densify_from')
+        return out
     L.check(L.lib().pccgeo_densify(L.ptr(coords_i16) if npts else None, npts, L.ptr(out), n, d, h, w, L.stream_ptr()), 'densify')
     return out
 
