@@ -69,6 +69,12 @@ int pccgeo_f32_to_blocked(const float* x, void* xb, int n, int c, int d, int h, 
 /* blocked bf16 -> fp32 (N,C,D,H,W) (sums the terms) */
 int pccgeo_blocked_to_f32(const void* xb, float* x, int n, int c, int d, int h, int wd, int terms, void* stream);
 
+/* First layer of the V2 / progressive analysis transforms -- Conv3D(F <= 16, (3,3,3), strides 2, 'same') + BiasAdd + Relu on the
+ * one-channel occupancy volume (src/model_transforms.py:67) -- writing the blocked bf16 layout directly (no fp32 intermediate).
+ * x: fp32 (N,1,D,H,W), even dims; w: tap-major fp32 (27, 1, cout); yb: blocked (terms, N, 2, D/2, H/2, W/2, 8). */
+int pccgeo_conv3d_first(const float* x, const float* w, const float* bias, void* yb, int n, int d, int h, int wd, int cout,
+                        int relu, int terms, void* stream);
+
 /* Pack tap-major fp32 weights (27, Cin, Cout) into the UMMA B-operand image used by pccgeo_conv3d_umma.
  * Returns the image size in bytes when wpacked == NULL.  `transposed`, `stride` select the layer type
  * (they change which taps are stacked together); HOST pointers in, HOST image out. */

@@ -24,6 +24,7 @@ SIGNATURES = {
     'pccgeo_blocked_to_f32': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_umma_pack_weights_host': (i64, [vp, vp, i32, i32, i32, i32, i32]),
     'pccgeo_conv3d_umma': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_conv3d_first': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_umma_hl_pack_weights_host': (i64, [vp, vp, i32, i32, i32]),
     'pccgeo_conv3d_umma_hl': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_umma_zy_pack_weights_host': (i64, [vp, vp, i32, i32, i32, i32]),

@@ -15,7 +15,9 @@
 //             every class that uses that offset (3^3 kernel: 8 gathers feed 27 MMAs instead of 27 gathers).
 //
 // Pipeline per CTA (persistent over tiles):
-//   warps 0-3  gather producers: thread r owns tile row r; per tap it loads the row's Cin channels from the blocked
+//   warps 0-3 (0-7 for wide layers)  gather producers: thread r owns tile row r (wide layers: two threads per row, each half
+//              of the (term, channel group) vectors -- a lone producer warp per scheduler runs ~5 cycles per dependent
+//              instruction and was the bound: ncu showed the MMA warp waiting for `full` 83 % of the time); per tap it loads the row's Cin channels from the blocked
 //              bf16 layout (16-byte LDG per channel group and precision term, zeros when out of bounds) and stores
 //              them into the UMMA no-swizzle K-major layout of a ring stage (conflict-free 16-byte STS);
 //              fence.proxy.async + mbarrier arrive.  The loads of the next (tile, tap) pair are already in flight
@@ -32,10 +34,8 @@
 
 namespace pccgeo {
 
-int g_gather_mode = 0;   // pccgeo_set_option("gemm_gather_mode")
-
 constexpr int GM = 128;
-constexpr int G_THREADS = 9 * 32;
+__host__ __device__ constexpr int g_threads(int pg) { return (4 * pg + 5) * 32; }   // pg producer groups of 4 warps, MMA warp, 4 epilogue warps
 constexpr int G_MAX_STAGES = 8;
 constexpr int G_HEADER_BYTES = 1024;
 
@@ -54,7 +54,6 @@ struct GemmConvParams {
   int tiles_per_cls, total_tiles;
   long long term_stride_in, term_stride_out;
   int nstage, wchunk_bytes, a_stage_bytes, stage_bytes;
-  int gather_mode;   // 0: register-staged LDG gather, 1: cp.async.ca with multi-stage lookahead, 2: cp.async.cg
 };
 
 struct __align__(8) GemmSmemHeader {
@@ -80,9 +79,17 @@ struct GemmTmem {
 };
 
 // small class-mode configurations (<= 8 gather vectors per tap, <= 32 output channels) fit twice on an SM
+// PG = 2 producer groups (two threads per tile row) for the configurations that run one CTA per SM
 template <int COUT, int TERMS, int KC, int NACC>
-__global__ void __launch_bounds__(G_THREADS, (TERMS * 2 * KC <= 8 && COUT <= 32 && GemmTmem<COUT, NACC>::kCols <= 256) ? 2 : 1)
+__host__ __device__ constexpr int gemm_ctas_per_sm() { return (TERMS * 2 * KC <= 8 && COUT <= 32 && GemmTmem<COUT, NACC>::kCols <= 256) ? 2 : 1; }
+template <int COUT, int TERMS, int KC, int NACC>
+__host__ __device__ constexpr int gemm_pg() { return (gemm_ctas_per_sm<COUT, TERMS, KC, NACC>() == 1 && TERMS * 2 * KC >= 4) ? 2 : 1; }
+
+template <int COUT, int TERMS, int KC, int NACC>
+__global__ void __launch_bounds__(g_threads(gemm_pg<COUT, TERMS, KC, NACC>()), gemm_ctas_per_sm<COUT, TERMS, KC, NACC>())
 conv3d_gemm_kernel(const GemmConvParams p) {
+  constexpr int PG = gemm_pg<COUT, TERMS, KC, NACC>();
+  constexpr int W_MMA = 4 * PG;
   extern __shared__ __align__(1024) uint8_t smem[];
   GemmSmemHeader* hdr = reinterpret_cast<GemmSmemHeader*>(smem);
   uint8_t* stages = smem + G_HEADER_BYTES;
@@ -92,11 +99,11 @@ conv3d_gemm_kernel(const GemmConvParams p) {
   constexpr uint32_t tmem_cols = GemmTmem<COUT, NACC>::kCols;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&hdr->full[i]), GM); mbar_init(smem_u32(&hdr->empty[i]), 1); }
+    for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&hdr->full[i]), GM * PG); mbar_init(smem_u32(&hdr->empty[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 4); }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&hdr->tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -105,9 +112,10 @@ conv3d_gemm_kernel(const GemmConvParams p) {
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, hdr->tmem_base, 0);
 
-  if (warp < 4) {
+  if (warp < W_MMA) {
     // ================= gather producers =================
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & (GM - 1), half = threadIdx.x >> 7;   // half: which of the PG interleaved vector subsets
+    constexpr int NV = TERMS * CGI / PG;                              // vectors (16 B) per thread and tap
     const long long HWin = (long long)p.Hin * p.Win, DHWin = HWin * p.Din;
     const uint32_t row_off = (uint32_t)(r >> 3) * 128 + (uint32_t)(r & 7) * 16;
     uint32_t s = 0, ph = 0;
@@ -134,47 +142,15 @@ conv3d_gemm_kernel(const GemmConvParams p) {
     auto advance = [&](Cursor& c) {
       if (++c.ti == c.t_end) { c.tile += gridDim.x; open_tile(c); }
     };
-    // gather of one (tile, tap) pair straight into a ring stage with 16-byte cp.async (zero-filled when the tap falls outside
-    // the volume): nothing is staged in registers, so several taps are in flight per thread -- with register staging only ONE
-    // tap was, and every tap cost a full L2 round trip (ncu: the MMA warp waited for `full` 83 % of the time)
-    auto issue_loads = [&](const Cursor& c, const int4& tap, uint32_t dst) {
-      const int iz = c.iz0 + tap.x, iy = c.iy0 + tap.y, ix = c.ix0 + tap.z;
-      const bool inb = c.valid && iz >= 0 && iz < p.Din && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-      const __nv_bfloat16* src = inb ? c.xn + (iz * HWin + (long long)iy * p.Win + ix) * 8 : p.x;
-      const uint32_t nbytes = inb ? 16u : 0u;
-#pragma unroll
-      for (int tt = 0; tt < TERMS; ++tt)
-#pragma unroll
-        for (int cg = 0; cg < CGI; ++cg) {
-          const __nv_bfloat16* sp = inb ? src + tt * p.term_stride_in + (long long)cg * DHWin * 8 : src;
-          if (p.gather_mode == 2)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(tt * CGI + cg) * 2048u), "l"(sp), "r"(nbytes) : "memory");
-          else
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)(tt * CGI + cg) * 2048u), "l"(sp), "r"(nbytes) : "memory");
-        }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto wait_pending = [](int n) {   // block until at most n of this thread's cp.async groups are still in flight
-      switch (n) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-      }
-    };
-    auto issue_loads_reg = [&](const Cursor& c, const int4& tap, int4* dst) {
+    auto issue_loads = [&](const Cursor& c, const int4& tap, int4* dst) {
       const int iz = c.iz0 + tap.x, iy = c.iy0 + tap.y, ix = c.ix0 + tap.z;
       const bool inb = c.valid && iz >= 0 && iz < p.Din && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
       const __nv_bfloat16* src = c.xn + (iz * HWin + (long long)iy * p.Win + ix) * 8;
 #pragma unroll
-      for (int tt = 0; tt < TERMS; ++tt)
-#pragma unroll
-        for (int cg = 0; cg < CGI; ++cg)
-          dst[tt * CGI + cg] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8))
-                                   : make_int4(0, 0, 0, 0);
+      for (int j = 0; j < NV; ++j) {
+        const int i = j * PG + half, tt = i / CGI, cg = i % CGI;   // vector i = (term, channel group)
+        dst[j] = inb ? __ldg(reinterpret_cast<const int4*>(src + tt * p.term_stride_in + (long long)cg * DHWin * 8)) : make_int4(0, 0, 0, 0);
+      }
     };
     Cursor cur;
     cur.tile = blockIdx.x;
@@ -182,44 +158,11 @@ conv3d_gemm_kernel(const GemmConvParams p) {
     cur.valid = false;
     cur.xn = p.x;
     open_tile(cur);
-    if (p.gather_mode != 0) {
-    // stage s is published (`full`) LOOK iterations after its loads were issued; LOOK < nstage, so the `empty` wait of an
-    // iteration only ever depends on stages that were already published
-    const int LOOK = p.nstage - 1 < 7 ? p.nstage - 1 : 7;
-    uint32_t s_done = 0;
-    int inflight = 0;
-    auto publish_oldest = [&]() {
-      wait_pending(inflight - 1);
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&hdr->full[s_done]));
-      if (++s_done == (uint32_t)p.nstage) s_done = 0;
-      --inflight;
-    };
-    while (cur.tile < p.total_tiles) {
-      const int4 tp = __ldg(p.taps + cur.ti);
-      mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1);
-      uint8_t* st = stages + (size_t)s * p.stage_bytes;
-      if (r == 0) {
-        const uint32_t full = smem_u32(&hdr->full[s]);
-        const uint32_t group = (uint32_t)tp.w & 0xffffu;
-        const uint32_t bytes = (NACC == 1 ? 1u : (uint32_t)__popc((uint32_t)tp.w >> 16)) * (uint32_t)p.wchunk_bytes;
-        mbar_expect_tx_only(full, bytes);
-        bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)group * NACC * p.wchunk_bytes, bytes, full);
-      }
-      issue_loads(cur, tp, smem_u32(st) + row_off);
-      ++inflight;
-      if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
-      advance(cur);
-      if (inflight > LOOK) publish_oldest();
-    }
-    while (inflight > 0) publish_oldest();
-    } else {
-    // register-staged gather (one tap in flight per thread)
-    int4 v[TERMS * CGI], vn[TERMS * CGI];
+    int4 v[NV], vn[NV];
     int4 tp = make_int4(0, 0, 0, 0);
     if (cur.tile < p.total_tiles) {
       tp = __ldg(p.taps + cur.ti);
-      issue_loads_reg(cur, tp, v);
+      issue_loads(cur, tp, v);
     }
     while (cur.tile < p.total_tiles) {
       Cursor nxt = cur;
@@ -227,11 +170,11 @@ conv3d_gemm_kernel(const GemmConvParams p) {
       int4 tpn = tp;
       if (nxt.tile < p.total_tiles) {
         tpn = __ldg(p.taps + nxt.ti);
-        issue_loads_reg(nxt, tpn, vn);
+        issue_loads(nxt, tpn, vn);
       }
       mbar_wait(smem_u32(&hdr->empty[s]), ph ^ 1);
       uint8_t* st = stages + (size_t)s * p.stage_bytes;
-      if (r == 0) {
+      if (threadIdx.x == 0) {
         const uint32_t full = smem_u32(&hdr->full[s]);
         const uint32_t group = (uint32_t)tp.w & 0xffffu;
         const uint32_t bytes = (NACC == 1 ? 1u : (uint32_t)__popc((uint32_t)tp.w >> 16)) * (uint32_t)p.wchunk_bytes;
@@ -239,17 +182,16 @@ conv3d_gemm_kernel(const GemmConvParams p) {
         bulk_g2s(smem_u32(st + p.a_stage_bytes), p.wchunks + (size_t)group * NACC * p.wchunk_bytes, bytes, full);
       }
 #pragma unroll
-      for (int i = 0; i < TERMS * CGI; ++i) *reinterpret_cast<int4*>(st + i * 2048 + row_off) = v[i];
+      for (int j = 0; j < NV; ++j) *reinterpret_cast<int4*>(st + (j * PG + half) * 2048 + row_off) = v[j];
       fence_proxy_async();
       mbar_arrive(smem_u32(&hdr->full[s]));
       if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
 #pragma unroll
-      for (int i = 0; i < TERMS * CGI; ++i) v[i] = vn[i];
+      for (int j = 0; j < NV; ++j) v[j] = vn[j];
       tp = tpn;
       cur = nxt;
     }
-    }
-  } else if (warp == 4) {
+  } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     constexpr uint32_t b_kc16 = 2 * (COUT / 8) * 128 / 16;     // one k-chunk of B (two K core matrices), 16-byte units
     constexpr uint32_t b_term16 = KC * b_kc16;
@@ -380,7 +322,7 @@ conv3d_gemm_kernel(const GemmConvParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -495,7 +437,7 @@ static int launch_gemm(const GemmConvParams& p, size_t smem, int grid, cudaStrea
     PCCGEO_CUDA(cudaFuncSetAttribute(conv3d_gemm_kernel<COUT, TERMS, KC, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv3d_gemm_kernel<COUT, TERMS, KC, NACC><<<grid, G_THREADS, smem, st>>>(p);
+  conv3d_gemm_kernel<COUT, TERMS, KC, NACC><<<grid, g_threads(gemm_pg<COUT, TERMS, KC, NACC>()), smem, st>>>(p);
   return check_launch("conv3d_gemm_kernel");
 }
 
@@ -594,7 +536,6 @@ extern "C" int pccgeo_conv3d_gemm(const void* xb, const void* wimg_dev, const vo
   p.nstage = avail / p.stage_bytes;
   if (p.nstage > G_MAX_STAGES) p.nstage = G_MAX_STAGES;
   PCCGEO_REQUIRE(p.nstage >= 2, "conv3d_gemm: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
-  p.gather_mode = g_gather_mode;
   const size_t smem = G_HEADER_BYTES + (size_t)p.nstage * p.stage_bytes;
   int grid = p.total_tiles < 148 * ctas_per_sm ? p.total_tiles : 148 * ctas_per_sm;
   cudaStream_t st = (cudaStream_t)stream;

@@ -42,7 +42,6 @@ namespace pccgeo {
 static int g_opt_swap_lbo_sbo = 0;
 static int g_opt_max_ctas = 0;
 static int g_opt_one_cta = 0;
-extern int g_gather_mode;   // conv3d_gemm.cu
 
 // --------------------------------------------------------------------------------------------------------
 // kernel
@@ -474,7 +473,6 @@ extern "C" int pccgeo_set_option(const char* name, long long value) {
   if (!strcmp(name, "umma_swap_lbo_sbo")) { g_opt_swap_lbo_sbo = (int)value; return PCCGEO_OK; }
   if (!strcmp(name, "umma_max_ctas")) { g_opt_max_ctas = (int)value; return PCCGEO_OK; }
   if (!strcmp(name, "umma_one_cta_per_sm")) { g_opt_one_cta = (int)value; return PCCGEO_OK; }
-  if (!strcmp(name, "gemm_gather_mode")) { g_gather_mode = (int)value; return PCCGEO_OK; }
   set_error("set_option: unknown option %s", name);
   return PCCGEO_EINVAL;
 }

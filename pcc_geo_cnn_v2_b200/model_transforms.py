@@ -195,6 +195,12 @@ class _ConvBase(Layer):
             return c >= 8 and cp <= 32 and fp <= 16 and tiled
         return self.k == 3 and self.stride == 1 and c >= 8 and cp <= 32 and fp <= 32 and tiled
 
+    def first_eligible(self, in_shape, terms, src_is_f32):
+        """fused first layer: one input channel, 3x3x3, stride 2, <= 16 filters, even dims, fp32 input -> blocked output"""
+        n, c, d, h, w = in_shape
+        return (terms and src_is_f32 and c == 1 and self.k == 3 and self.stride == 2 and not self.transposed and self.filters <= 16
+                and d % 2 == 0 and h % 2 == 0 and w % 2 == 0)
+
     def zy_eligible(self, in_shape, terms):
         """zy-ring kernel: stride-1 3x3x3 layers with 9..16 channels in and out, batches that fill its 16-block M tiles and
         volumes large enough for its (16 blocks x 8 x x <= 10 rows) work items to occupy the GPU."""
@@ -497,6 +503,9 @@ def run_steps(steps, out_id, x, pack=None, keep=None, extra=None):
                 if pack:
                     return xh, bits, counts
                 vals[dst] = _Val(f32=xh, shape=tuple(xh.shape))
+            elif res is None and dst != out_id and layer.first_eligible(v.shape, terms, v.f32 is not None):
+                yb, shp = ops.conv3d_first(v.f32, layer.dev('w_tap'), layer.dev('bias'), layer.filters, layer.relu, terms)
+                vals[dst] = _Val(blk=yb, shape=shp, terms=terms)
             elif terms and layer.ys_eligible(v.shape):
                 rb = vals[res].as_blk(terms) if res is not None else None
                 yb, shp = ops.conv3d_umma_ys(v.as_blk(terms), v.shape, layer.dev(f'w_ummays{terms}'), layer.dev('bias'),

@@ -62,6 +62,20 @@ def blocked_to_f32(xb, shape, terms, out=None):
     return out
 
 
+def conv3d_first(x, w_tap, bias, cout, relu, terms, out=None):
+    """One-channel fp32 volume (N,1,D,H,W) -> stride-2 3x3x3 conv + bias + ReLU in the blocked bf16 layout.  Returns (yb, out_shape)."""
+    L.require_cuda()
+    x = _f32c(x)
+    n, c, d, h, w = x.shape
+    assert c == 1
+    shp = (n, cout, d // 2, h // 2, w // 2)
+    if out is None:
+        out = torch.empty(blocked_numel(*shp, terms), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().pccgeo_conv3d_first(L.ptr(x), L.ptr(w_tap), L.ptr(bias), L.ptr(out), n, d, h, w, cout, int(relu), terms, L.stream_ptr()),
+            'conv3d_first')
+    return out, shp
+
+
 def umma_pack_weights(w_tap_host, cin, cout, stride, transposed, terms):
     """numpy fp32 (27, Cin, Cout) -> device uint8 image for pccgeo_conv3d_umma."""
     w = np.ascontiguousarray(w_tap_host, np.float32)

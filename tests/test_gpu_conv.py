@@ -320,3 +320,22 @@ def test_gemm_conv_matches_oracle(transposed, k, s, cin, cout, shape, n, terms, 
     got2 = ops.blocked_to_f32(yb2, shp, terms)
     want2 = _oracle(x, kern, None, s, False, transposed)
     assert float((got2.cpu().double() - want2).abs().max()) < tol * float(want2.abs().max())
+
+
+@pytest.mark.parametrize('terms,tol', [(2, 1e-5), (1, 1e-2)])
+@pytest.mark.parametrize('cout,shape,n', [(16, (16, 16, 16), 2), (16, (64, 64, 64), 3), (12, (8, 6, 4), 5), (16, (2, 2, 2), 1)])
+def test_fused_first_layer_matches_oracle(cout, shape, n, terms, tol):
+    """Conv3D(F, 3, strides 2, 'same') + bias + ReLU on the one-channel occupancy volume, written straight into the blocked
+    bf16 layout (conv3d_first.cu), against the float64 oracle -- on occupancy-like {0,1} input and on a dense real-valued one."""
+    rng = np.random.default_rng(cout + shape[0])
+    for dense in (False, True):
+        x = torch.from_numpy(rng.normal(size=(n, 1) + shape).astype(np.float32)) if dense else \
+            torch.from_numpy((rng.random((n, 1) + shape) < 0.05).astype(np.float32))
+        kern = torch.from_numpy((rng.normal(size=(3, 3, 3, 1, cout)) / np.sqrt(27)).astype(np.float32))
+        bias = torch.from_numpy(rng.normal(size=(cout,)).astype(np.float32) * 0.1)
+        want = _oracle(x, kern, bias, 2, True, False)
+        yb, shp = ops.conv3d_first(x.cuda(), _tap_major(kern, False).cuda(), bias.cuda(), cout, True, terms)
+        got = ops.blocked_to_f32(yb, shp, terms)
+        assert shp == tuple(want.shape)
+        scale = float(want.abs().max()) + 1e-6
+        assert float((got.cpu().double() - want).abs().max()) < tol * scale
