@@ -11,7 +11,7 @@
 namespace pccgeo {
 
 template <int TERMS>
-__global__ void __launch_bounds__(256, 4) conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(256, 3) conv3d_first_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                            __nv_bfloat16* __restrict__ y, int N, int D, int H, int W, int cout, int relu) {
   __shared__ float ws[27 * 16];
   __shared__ float bs[16];
@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(256, 4) conv3d_first_kernel(const float* __res
     float acc[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-#pragma unroll
-    for (int kz = 0; kz < 3; ++kz) {
+#pragma unroll 1
+    for (int kz = 0; kz < 3; ++kz) {   // one plane of taps at a time: 9 inputs live, not 27
       const int iz = 2 * oz + kz;
       if (iz >= D) continue;
 #pragma unroll
