@@ -52,6 +52,9 @@ constexpr int PLANE_CG_BYTES = PY * PX * 16;   // one channel group of one input
 constexpr int ROW_PITCH = PX * 16;             // 160 B between y rows  (SBO of A)
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+// warps 0..7 epilogue, 8 TMA producer, 9 MMA issuer: the warp schedulers favour high warp ids, and the issuing thread's
+// instruction stream is the critical path (conv3d_umma_zy.cu measured it: +8 % as the last warp instead of warp 1)
+constexpr int W_TMA = NUM_EPI_WARPS, W_MMA = NUM_EPI_WARPS + 1;
 constexpr int MAX_STAGES = 8, MAX_SLOTS = 32;
 
 struct UmmaConvParams {
@@ -105,13 +108,13 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
   const int tmem_cols = p.nslots * SC;                        // power of two >= 32 (host guarantees)
 
   // ---- one-time setup ----
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
     for (int i = 0; i < p.nstage; ++i) { mbar_init(smem_u32(&hdr->in_full[i]), 1); mbar_init(smem_u32(&hdr->in_empty[i]), 1); }
     for (int i = 0; i < p.nslots; ++i) { mbar_init(smem_u32(&hdr->acc_full[i]), 1); mbar_init(smem_u32(&hdr->acc_empty[i]), 4); }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&hdr->tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -125,7 +128,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, hdr->tmem_base, 0);  // shuffle => provably warp-uniform
 
   const int D = p.D;
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t s = 0, phase = 0;  // stage ring position / phase
@@ -142,7 +145,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ================= MMA issuer =================
     // The whole warp walks the (uniform) loop so that address arithmetic stays on the uniform datapath; only the
     // tcgen05 instructions themselves are issued by one elected lane.  Nothing in the per-MMA path divides or
@@ -242,7 +245,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
     }
   } else {
     // ================= epilogue =================
-    const int ew = warp - 2;          // 0..7
+    const int ew = warp;              // 0..7
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access (warp id % 4)
     const int grp = ew >> 2;          // planes with (g & 1) == grp
     const int row = quad * 32 + lane; // M row = TMEM lane
@@ -359,7 +362,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const UmmaConvPar
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
