@@ -343,7 +343,11 @@ class CompressionModel:
         # host threads: this rank's share of the cores (one process per GPU under torchrun); `pipeline_depth` host workers
         # run the C++ stages of different batches concurrently, each call with `coder_threads` threads (sweep on the
         # 16-core B200 host: 3 workers x 8 threads)
-        cores = max(1, (os.cpu_count() or 4) // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))
+        try:
+            usable = len(os.sched_getaffinity(0))   # respects taskset / cgroup cpusets (os.cpu_count() does not)
+        except AttributeError:
+            usable = os.cpu_count() or 4
+        cores = max(1, usable // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))
         self.coder_threads = max(1, cores // 2)
         self.pipeline_depth = 3
         self.x = self.x_hat = self.strings = self.debug_tensors = None
@@ -351,8 +355,10 @@ class CompressionModel:
         self.use_graphs = True   # capture the per-batch kernel sequences of the block loops into CUDA graphs
         # entropy-code on the GPU (csrc/rc_device.cu: one warp per stream, all streams of up to `coder_group_blocks` blocks in
         # one launch) instead of in the host workers; byte-identical strings.  Used by the CUDA-graph block loops.
-        # Default: on when this rank has fewer than 16 host cores (several GPUs per host; measured cross-over, DESIGN.md
-        # section 8), PCCGEO_DEVICE_CODER=0/1 overrides.  A group's coding costs a fixed few milliseconds (the length
+        # Default: on when this rank has fewer than 16 host cores (several GPUs per host).  Measured on the rate-realistic
+        # workload (round 2, blocks/s end to end, host / device coder): 16 cores 6.73 k / 6.70 k, 12 cores (2 ranks) 6.4 k / 6.2 k
+        # per GPU, 8 cores 5.4 k / 6.8 k, 4 cores 4.6 k / 6.8 k -- the device coder does not depend on the host at all.
+        # PCCGEO_DEVICE_CODER=0/1 overrides.  A group's coding costs a fixed few milliseconds (the length
         # of one stream's serial chain), so groups are large; `coder_overlap` moves it to a side stream under the next
         # group's transforms (off: its one-warp CTAs displace the persistent conv CTAs and cost more than they hide).
         env = os.environ.get('PCCGEO_DEVICE_CODER', '')
