@@ -42,6 +42,7 @@ namespace pccgeo {
 static int g_opt_swap_lbo_sbo = 0;
 static int g_opt_max_ctas = 0;
 static int g_opt_one_cta = 0;
+namespace zy { extern int g_zy_groups; }   // conv3d_umma_zy.cu
 
 // --------------------------------------------------------------------------------------------------------
 // kernel
@@ -476,6 +477,7 @@ extern "C" int pccgeo_set_option(const char* name, long long value) {
   if (!strcmp(name, "umma_swap_lbo_sbo")) { g_opt_swap_lbo_sbo = (int)value; return PCCGEO_OK; }
   if (!strcmp(name, "umma_max_ctas")) { g_opt_max_ctas = (int)value; return PCCGEO_OK; }
   if (!strcmp(name, "umma_one_cta_per_sm")) { g_opt_one_cta = (int)value; return PCCGEO_OK; }
+  if (!strcmp(name, "zy_groups") && (value == 2 || value == 3)) { zy::g_zy_groups = (int)value; return PCCGEO_OK; }
   set_error("set_option: unknown option %s", name);
   return PCCGEO_EINVAL;
 }

@@ -42,10 +42,8 @@ constexpr int UNIT_BYTES = CGI * PX * 16;   // one block's row: 2 channel groups
 constexpr int CG_BYTES = PX * 16;           // 160 B between the two channel groups                            (LBO of A)
 constexpr int TERM_BYTES = UNITS * UNIT_BYTES;   // 5120 B per precision term and input row
 constexpr int MAX_YO = 10;                  // output rows per tile: 10 * 3 * 16 = 480 TMEM columns
-constexpr int NGROUPS = 3;                  // epilogue groups of 4 warps
-constexpr int NUM_THREADS = NGROUPS * 128 + 96;   // epilogue groups, TMA producer, scout, MMA issuer
-constexpr int W_TMA = 4 * NGROUPS, W_SCOUT = W_TMA + 1, W_MMA = W_TMA + 2;   // the issuer gets the highest warp id: the warp
-                                                                             // schedulers favour it over the epilogue warps
+int g_zy_groups = 3;                        // epilogue groups of 4 warps (pccgeo_set_option("zy_groups"): 2 or 3)
+constexpr int num_threads(int ng) { return ng * 128 + 96; }   // epilogue groups, TMA producer, scout, MMA issuer
 constexpr int MAX_STAGES = 12, MAX_SLOTS = 3 * MAX_YO;
 constexpr int BT_BYTES = 2 * 18 * 128;      // one B tile: N = 144 rows x K = 16 bf16 = 4608 B; [kcore 2][18 groups][8 n][8 k]
 constexpr int HEADER_BYTES = 1024;
@@ -132,11 +130,14 @@ __device__ __noinline__ void commit_many(uint32_t lead, uint32_t full_base, uint
     for (uint32_t k = 0; k < dcnt; ++k) umma_commit_if(lead, full_base + ((dfirst + k) * 3 + g % 3u) * 8);
 }
 
-template <int TERMS>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p) {
+template <int TERMS, int NGROUPS>
+__global__ void __launch_bounds__(NGROUPS * 128 + 96, 1) conv3d_umma_zy_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Header* hdr = reinterpret_cast<Header*>(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NUM_THREADS = NGROUPS * 128 + 96;
+  constexpr int W_TMA = 4 * NGROUPS, W_SCOUT = W_TMA + 1, W_MMA = W_TMA + 2;   // the issuer gets the highest warp id: the warp
+                                                                               // schedulers favour it over the epilogue warps
   constexpr int WBYTES = 3 * 3 * TERMS * BT_BYTES;
   constexpr int STAGE_BYTES = TERMS * TERM_BYTES;
   uint8_t* wsm = smem + HEADER_BYTES;
@@ -223,6 +224,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
     const uint32_t full_base = smem_u32(&hdr->acc_full[0]);
     constexpr uint32_t idesc0 = make_idesc(0);
     uint32_t zs_done8 = 0;   // byte offset of z-slot (z % 3) inside a row's three acc_full barriers: plane z-1 has gp = z
+    // the probe of the NEXT row's `go` barrier is issued between the MMAs of the current row: its ~90-cycle latency then
+    // overlaps with queued MMAs instead of sitting between two rows (the scout runs ahead, so the probe normally succeeds)
+    bool ready = mbar_try(go_bar, in_phase);
     for (int z = 0; z < D; ++z) {
       const uint32_t b_z = b_lo0 + (((uint32_t)(z + 1) % 3u) * 3u) * TERMS * (BT_BYTES / 16);
       const bool fast_z = z != D - 1;
@@ -232,24 +236,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3d_umma_zy_kernel(const __
         const uint32_t idesc = idesc0 | ((uint32_t)(whi - wlo + 1) * 6u) << 17;
         const uint32_t b0 = b_z + (uint32_t)(wlo - yi + 1) * (6 * 128 / 16);
         const int rhi = (yi == yi1 && yi <= y1 - 1) ? yi : yi - 1;    // completed output rows: [wlo, rhi]
-        mbar_wait(go_bar, in_phase);
+        if (!ready) mbar_wait(go_bar, in_phase);
         tc_fence_after();
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-          for (int pr = 0; pr < npairs; ++pr) {
-            const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
-            umma_bf16_lh_if(lead, d0, a_s + ta * (TERM_BYTES / 16) + (uint32_t)kx, a_hi, b0 + ((uint32_t)kx * TERMS + tb) * (BT_BYTES / 16), b_hi, idesc);
-          }
-        }
-        umma_commit_if(lead, empty_bar);
-        if (fast_z && rhi == wlo) umma_commit_if(lead, full_base + (uint32_t)(wlo - y0) * 24u + zs_done8);
-        else if (rhi >= wlo) commit_many(lead, full_base, (uint32_t)(wlo - y0), (uint32_t)(rhi - wlo + 1), (uint32_t)z, fast_z ? (uint32_t)z : (uint32_t)z + 2u);
+        const uint32_t a_cur = a_s, empty_cur = empty_bar;
         a_s += STAGE_BYTES / 16; go_bar += 8; empty_bar += 8;
         if (++s == (uint32_t)p.nstage) {
           s = 0; in_phase ^= 1; a_s = a_lo_proto + stages16;
           go_bar = smem_u32(&hdr->go[0]); empty_bar = smem_u32(&hdr->in_empty[0]);
         }
+#pragma unroll
+        for (int i = 0; i < 3 * npairs; ++i) {
+          const int kx = i / npairs, pr = i % npairs;
+          const uint32_t ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
+          umma_bf16_lh_if(lead, d0, a_cur + ta * (TERM_BYTES / 16) + (uint32_t)kx, a_hi, b0 + ((uint32_t)kx * TERMS + tb) * (BT_BYTES / 16), b_hi, idesc);
+          if (i == (3 * npairs) / 2) ready = mbar_try(go_bar, in_phase);   // next row (a failed probe at the very end is harmless)
+        }
+        umma_commit_if(lead, empty_cur);
+        if (fast_z && rhi == wlo) umma_commit_if(lead, full_base + (uint32_t)(wlo - y0) * 24u + zs_done8);
+        else if (rhi >= wlo) commit_many(lead, full_base, (uint32_t)(wlo - y0), (uint32_t)(rhi - wlo + 1), (uint32_t)z, fast_z ? (uint32_t)z : (uint32_t)z + 2u);
       }
       zs_done8 = zs_done8 == 16 ? 0 : zs_done8 + 8;
     }
@@ -489,13 +493,14 @@ extern "C" int pccgeo_conv3d_umma_zy(const void* xb, const void* wpacked, const 
 
   const int grid = p.ngroups * p.xsegs * p.ytiles;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set[3] = {false, false, false};
-  if (terms == 2) {
-    if (!attr_set[2]) { PCCGEO_CUDA(cudaFuncSetAttribute(zy::conv3d_umma_zy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set[2] = true; }
-    zy::conv3d_umma_zy_kernel<2><<<grid, zy::NUM_THREADS, smem, st>>>(tmap, p);
-  } else {
-    if (!attr_set[1]) { PCCGEO_CUDA(cudaFuncSetAttribute(zy::conv3d_umma_zy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set[1] = true; }
-    zy::conv3d_umma_zy_kernel<1><<<grid, zy::NUM_THREADS, smem, st>>>(tmap, p);
-  }
+  auto launch = [&](auto kern, int ng) -> int {
+    PCCGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<grid, zy::num_threads(ng), smem, st>>>(tmap, p);
+    return PCCGEO_OK;
+  };
+  int lrc;
+  if (zy::g_zy_groups == 2) lrc = terms == 2 ? launch(zy::conv3d_umma_zy_kernel<2, 2>, 2) : launch(zy::conv3d_umma_zy_kernel<1, 2>, 2);
+  else lrc = terms == 2 ? launch(zy::conv3d_umma_zy_kernel<2, 3>, 3) : launch(zy::conv3d_umma_zy_kernel<1, 3>, 3);
+  if (lrc) return lrc;
   return check_launch("conv3d_umma_zy_kernel");
 }

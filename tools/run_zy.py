@@ -9,6 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pcc_geo_cnn_v2_b200 import ops  # noqa: E402
 
 B, S, reps = [int(a) for a in (sys.argv[1:] + ['32', '64', '5'][len(sys.argv) - 1:])]
+if os.environ.get('PCCGEO_ZY_GROUPS'):
+    from pcc_geo_cnn_v2_b200 import _lib
+    _lib.check(_lib.lib().pccgeo_set_option(b'zy_groups', int(os.environ['PCCGEO_ZY_GROUPS'])), 'set_option')
 rng = np.random.default_rng(0)
 x = torch.randn(B, 16, S, S, S, device='cuda').relu_()
 w = (rng.normal(size=(27, 16, 16)) / np.sqrt(27 * 16)).astype(np.float32)
@@ -25,4 +28,4 @@ for _ in range(reps):
     ops.conv3d_umma_zy(xb, tuple(x.shape), wzy, bias, 16, True, 2, None, yb)
 e1.record()
 torch.cuda.synchronize()
-print(f'zy B={B} S={S}: {e0.elapsed_time(e1) / reps:.4f} ms/launch')
+print(f"zy groups={os.environ.get('PCCGEO_ZY_GROUPS', 'default')} B={B} S={S}: {e0.elapsed_time(e1) / reps:.4f} ms/launch")
