@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libpccgeo.so')
-SOURCES = ['common.cu', 'conv3d_direct.cu', 'conv3d_first.cu', 'conv3d_umma.cu', 'conv3d_umma_ys.cu', 'conv3d_umma_zy.cu', 'conv3d_out1.cu', 'conv3d_gemm.cu', 'train.cu','entropy.cu', 'voxel.cu', 'threshold_opt.cu', 'octree.cu', 'rc_device.cu', 'range_coder.cpp']
+SOURCES = ['common.cu', 'conv3d_direct.cu', 'conv3d_first.cu', 'conv3d_umma.cu', 'conv3d_umma_ys.cu', 'conv3d_umma_zy.cu', 'conv3d_out1.cu', 'conv3d_gemm.cu', 'train.cu', 'conv3d_wgrad_umma.cu', 'entropy.cu', 'voxel.cu', 'threshold_opt.cu', 'octree.cu', 'rc_device.cu', 'range_coder.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC,-O3,-pthread', '--threads', '8']
 

@@ -388,6 +388,28 @@ def eb_likelihood_bwd(values, eb_params, c):
     return dv, dp
 
 
+def wgrad_umma_eligible(n, cin, cout, k, stride, d, h, w, terms=2):
+    """True when the tcgen05 weight-gradient kernel covers this layer (3x3x3, stride 1, 16/32/64 channels in == out, W in 16/32/64)"""
+    if k != 3 or stride != 1 or cin != cout:
+        return False
+    return int(L.lib().pccgeo_wgrad_umma_ws_floats(cin, n, d, h, w, terms)) > 0
+
+
+def conv3d_wgrad_umma(xb, gb, shape, transposed, terms):
+    """-> dW tap-major (27, C, C) from the blocked bf16 input xb and pre-activation gradient gb (both `terms` terms) of a
+    3x3x3 stride-1 'same' conv / transposed conv with C channels in and out; shape = (N, C, D, H, W)"""
+    L.require_cuda()
+    n, c, d, h, w = shape
+    nws = int(L.lib().pccgeo_wgrad_umma_ws_floats(c, n, d, h, w, terms))
+    if nws <= 0:
+        raise ValueError(f'conv3d_wgrad_umma: unsupported geometry {shape}')
+    dw = torch.empty((27, c, c), device=xb.device, dtype=torch.float32)
+    ws = torch.empty(nws, device=xb.device, dtype=torch.float32)
+    L.check(L.lib().pccgeo_conv3d_wgrad_umma(L.ptr(xb), L.ptr(gb), L.ptr(dw), L.ptr(ws), n, c, d, h, w, int(transposed), terms,
+                                             L.stream_ptr()), 'conv3d_wgrad_umma')
+    return dw
+
+
 def conv3d_wgrad_f32(x, g, cout, k, stride, transposed):
     """-> dW tap-major (k^3, Cin, Cout) of a 'same' conv / transposed conv with input x and pre-activation gradient g"""
     _f32c(x)

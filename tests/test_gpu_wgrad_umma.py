@@ -1,0 +1,66 @@
+"""tcgen05 weight gradient (conv3d_wgrad_umma.cu) of the stride-1 3x3x3 layers against float64 autograd on the oracle's
+convolutions (small volumes) and against the fp32 CUDA-core kernel -- itself within 1e-5 of the oracle, test_gpu_train.py -- at the
+sizes of the c3p training step (reference src/model_types.py:364-369: what Adam.minimize differentiates).
+
+Tolerances: bf16x3 operands carry ~2^-16 relative error per product and the sum runs in fp32 inside TMEM: 2e-4 of the gradient's
+scale; single bf16 (terms = 1): 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import transforms as T
+from pcc_geo_cnn_v2_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DT = torch.float64
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def _umma(xd, gd, transposed, terms):
+    n, c, d, h, w = xd.shape
+    assert ops.wgrad_umma_eligible(n, c, c, 3, 1, d, h, w, terms)
+    xb, gb = ops.f32_to_blocked(xd, terms), ops.f32_to_blocked(gd, terms)
+    return ops.conv3d_wgrad_umma(xb, gb, tuple(xd.shape), transposed, terms)
+
+
+@pytest.mark.parametrize('c,shape,n', [(16, (16, 16, 16), 2), (16, (5, 7, 16), 3), (32, (6, 16, 16), 2), (64, (4, 5, 16), 2), (16, (3, 4, 32), 1)])
+@pytest.mark.parametrize('transposed', [False, True])
+def test_wgrad_umma_matches_float64_autograd(c, shape, n, transposed):
+    rng = np.random.default_rng(c + 7 * int(transposed) + shape[0])
+    x = torch.tensor(rng.normal(size=(n, c) + shape), dtype=DT, requires_grad=True)
+    kern = torch.tensor(rng.normal(size=(3, 3, 3, c, c)) / np.sqrt(27 * c), dtype=DT, requires_grad=True)
+    y = (T.conv3d_transpose_same if transposed else T.conv3d_same)(x, kern, None, 1, False)
+    gy = rng.normal(size=tuple(y.shape)).astype(np.float32)
+    y.backward(torch.tensor(gy, dtype=DT))
+    want = kern.grad.numpy().transpose(0, 1, 2, 4, 3) if transposed else kern.grad.numpy()
+    xd, gd = x.detach().float().cuda(), torch.from_numpy(gy).cuda()
+    got = _umma(xd, gd, transposed, 2).cpu().numpy().reshape(3, 3, 3, c, c)
+    assert _rel(got, want) < 2e-4, _rel(got, want)
+    got1 = _umma(xd, gd, transposed, 1).cpu().numpy().reshape(3, 3, 3, c, c)
+    assert _rel(got1, want) < 2e-2, _rel(got1, want)
+
+
+@pytest.mark.parametrize('c,s,n', [(16, 64, 32), (16, 32, 32), (32, 32, 32), (32, 16, 32), (64, 16, 32), (16, 64, 5)])
+def test_wgrad_umma_matches_fp32_kernel_at_training_sizes(c, s, n):
+    g = torch.Generator(device='cuda').manual_seed(c * 100 + s)
+    xd = torch.relu(torch.randn((n, c, s, s, s), device='cuda', generator=g))        # post-ReLU activations: non-negative, sparse
+    gd = torch.randn((n, c, s, s, s), device='cuda', generator=g) * 1e-3
+    want = ops.conv3d_wgrad_f32(xd, gd, c, 3, 1, False).cpu().numpy()
+    got = _umma(xd, gd, False, 2).cpu().numpy()
+    assert _rel(got, want) < 2e-4, _rel(got, want)
+    again = _umma(xd, gd, False, 2).cpu().numpy()
+    assert np.array_equal(got, again)            # deterministic: fixed reduction order
+
+
+def test_wgrad_umma_rejects_unsupported_geometry():
+    assert not ops.wgrad_umma_eligible(2, 16, 32, 3, 1, 16, 16, 16)
+    assert not ops.wgrad_umma_eligible(2, 16, 16, 3, 2, 16, 16, 16)
+    assert not ops.wgrad_umma_eligible(2, 64, 64, 3, 1, 8, 8, 8)
+    assert not ops.wgrad_umma_eligible(2, 8, 8, 3, 1, 16, 16, 16)
+    with pytest.raises(ValueError):
+        ops.conv3d_wgrad_umma(torch.zeros(8, device='cuda', dtype=torch.bfloat16), torch.zeros(8, device='cuda', dtype=torch.bfloat16),
+                              (1, 64, 8, 8, 8), False, 2)
