@@ -375,15 +375,101 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ partial, int split
   }
 }
 
+// One-channel ends of the V2 transforms (first layer 1 -> C, stride 2; last layer C -> 1, transposed): Cin*Cout = C pairs only, so
+// the tap-per-block kernels above re-read the activations 27 times (10 ms for 16 -> 1 at 64^3 x 32).  Here a lane owns one base
+// voxel of a row: the 27 neighbours of the one-channel tensor go to registers once, then every channel of the other tensor at
+// that voxel (read exactly once, coalesced) feeds 27 FMAs.  A thread keeps 4 channels x 27 taps of fp32 sums over its ~100
+// voxels; lanes are added by shuffles, warps / blocks by the finish kernel in double, in a fixed order.
+constexpr int NARROW_BLOCKS = 592, NARROW_WARPS = 4, NARROW_CPT = 4;
+struct NarrowParams {
+  const float* multi;    // (N, C, Bd, Bh, Bw): indexed at the base voxel
+  const float* single;   // (N, 1, Sd, Sh, Sw): indexed at base * ss + tap - pb
+  float* partial;        // (blocks * warps, C, 27)
+  int N, C, Bd, Bh, Bw, Sd, Sh, Sw, ss, pb;
+};
+__global__ void __launch_bounds__(NARROW_WARPS * 32) wgrad_narrow_kernel(const NarrowParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = blockIdx.y;
+  const int xsegs = (p.Bw + 31) / 32;
+  const long long rows = (long long)p.N * p.Bd * p.Bh * xsegs;
+  float acc[NARROW_CPT][27];
+#pragma unroll
+  for (int c = 0; c < NARROW_CPT; ++c)
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc[c][t] = 0.f;
+  const long long BHW = (long long)p.Bh * p.Bw, BDHW = BHW * p.Bd, SHW = (long long)p.Sh * p.Sw, SDHW = SHW * p.Sd;
+  for (long long row = (long long)blockIdx.x * NARROW_WARPS + warp; row < rows; row += (long long)gridDim.x * NARROW_WARPS) {
+    const int xs = (int)(row % xsegs);
+    long long r = row / xsegs;
+    const int by = (int)(r % p.Bh); r /= p.Bh;
+    const int bz = (int)(r % p.Bd);
+    const int n = (int)(r / p.Bd);
+    const int bx = xs * 32 + lane;
+    const bool live = bx < p.Bw;
+    float s[27];
+    const float* sp = p.single + (long long)n * SDHW;
+#pragma unroll
+    for (int tz = 0; tz < 3; ++tz)
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) {
+          const int z = bz * p.ss + tz - p.pb, y = by * p.ss + ty - p.pb, x = bx * p.ss + tx - p.pb;
+          const bool ok = live && z >= 0 && z < p.Sd && y >= 0 && y < p.Sh && x >= 0 && x < p.Sw;
+          s[(tz * 3 + ty) * 3 + tx] = ok ? __ldg(sp + z * SHW + (long long)y * p.Sw + x) : 0.f;
+        }
+    const float* mp = p.multi + ((long long)n * p.C + cg * NARROW_CPT) * BDHW + bz * BHW + (long long)by * p.Bw + bx;
+#pragma unroll
+    for (int c = 0; c < NARROW_CPT; ++c) {
+      const float m = live ? __ldg(mp + c * BDHW) : 0.f;
+#pragma unroll
+      for (int t = 0; t < 27; ++t) acc[c][t] = fmaf(m, s[t], acc[c][t]);
+    }
+  }
+  float* out = p.partial + ((long long)(blockIdx.x * NARROW_WARPS + warp) * p.C + cg * NARROW_CPT) * 27;
+#pragma unroll
+  for (int c = 0; c < NARROW_CPT; ++c)
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      float v = acc[c][t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) out[c * 27 + t] = v;
+    }
+}
+// dw[t][c] = sum over the per-warp partials (warps, C, 27), in order, in double
+__global__ void wgrad_narrow_finish_kernel(const float* __restrict__ partial, int nwarps, int C, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 27) return;
+  const int c = i / 27, t = i % 27;
+  double s = 0.0;
+  for (int j = 0; j < nwarps; ++j) s += (double)partial[((long long)j * C + c) * 27 + t];
+  dw[t * C + c] = (float)s;
+}
+
 // db[c] = sum_{n,v} g[n,c,v]; grid (chunks, C) -> partials[c*chunks + chunk]; finish adds in order
 __global__ void bias_grad_kernel(const float* __restrict__ g, double* __restrict__ partials, int N, int C, long long S) {
   __shared__ double sm[32];
   const int c = blockIdx.y;
   double acc = 0.0;
-  const long long total = (long long)N * S;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long n = e / S, i = e % S;
-    acc += (double)g[(n * C + c) * S + i];
+  if ((S & 3) == 0) {
+    // 128-bit loads; fp32 inside one pass over a channel volume, double across passes
+    const long long S4 = S >> 2;
+    for (int n = 0; n < N; ++n) {
+      const float4* row = reinterpret_cast<const float4*>(g + ((long long)n * C + c) * S);
+      float a = 0.f;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(row + i);
+        a += (v.x + v.y) + (v.z + v.w);
+      }
+      acc += (double)a;
+    }
+  } else {
+    const long long total = (long long)N * S;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const long long n = e / S, i = e % S;
+      acc += (double)g[(n * C + c) * S + i];
+    }
   }
   acc = block_sum(acc, sm);
   if (threadIdx.x == 0) partials[(long long)c * gridDim.x + blockIdx.x] = acc;
@@ -468,7 +554,12 @@ extern "C" int pccgeo_eb_likelihood_bwd(const float* values, const float* eb_par
 extern "C" size_t pccgeo_wgrad_ws_floats(int cin, int cout, int k) {
   const int taps = k * k * k;
   int splits = (592 + taps - 1) / taps;
-  return (size_t)taps * splits * cin * cout;
+  size_t need = (size_t)taps * splits * cin * cout;
+  if (k == 3 && (cin == 1 || cout == 1)) {
+    const size_t narrow = (size_t)NARROW_BLOCKS * NARROW_WARPS * (cin * cout) * 27;
+    if (narrow > need) need = narrow;
+  }
+  return need;
 }
 
 extern "C" int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw, float* ws, int n, int cin, int d, int h, int wd,
@@ -493,6 +584,24 @@ extern "C" int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw
   p.splits = (592 + taps - 1) / taps;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  {
+    const int C = cin * cout;
+    if (k == 3 && ((!transposed && cin == 1) || (transposed && cout == 1)) && C % NARROW_CPT == 0 && C >= NARROW_CPT) {
+      NarrowParams q{};
+      q.multi = transposed ? x : g; q.single = transposed ? g : x; q.partial = ws;
+      q.N = n; q.C = C; q.Bd = p.Bd; q.Bh = p.Bh; q.Bw = p.Bw;
+      q.Sd = transposed ? p.Gd : p.Xd; q.Sh = transposed ? p.Gh : p.Xh; q.Sw = transposed ? p.Gw : p.Xw;
+      q.ss = stride; q.pb = p.pb;
+      const long long rows = (long long)n * p.Bd * p.Bh * ((p.Bw + 31) / 32);
+      int blocks = (int)((rows + NARROW_WARPS - 1) / NARROW_WARPS);
+      if (blocks > NARROW_BLOCKS) blocks = NARROW_BLOCKS;
+      wgrad_narrow_kernel<<<dim3(blocks, C / NARROW_CPT), NARROW_WARPS * 32, 0, st>>>(q);
+      rc = check_launch("wgrad_narrow_kernel");
+      if (rc) return rc;
+      wgrad_narrow_finish_kernel<<<(C * 27 + 127) / 128, 128, 0, st>>>(ws, blocks * NARROW_WARPS, C, dw);
+      return check_launch("wgrad_narrow_finish_kernel");
+    }
+  }
   const int tp = ((cin + 3) / 4) * ((cout + 3) / 4);
   if (tp <= WG_THREADS && WG_THREADS % tp == 0) {
     const int c4 = (cin + 3) / 4 + (cout + 3) / 4;
@@ -525,8 +634,11 @@ extern "C" int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw
 extern "C" int pccgeo_bias_grad_f32(const float* g, float* db, double* ws, int n, int c, long long spatial, void* stream) {
   PCCGEO_REQUIRE(g && db && ws && n > 0 && c > 0 && spatial > 0, "bias_grad: bad argument");
   int chunks = kReduceBlocks / c;
-  if (chunks > 16) chunks = 16;
   PCCGEO_REQUIRE(chunks >= 1, "bias_grad: too many channels");
+  {
+    const long long want = (spatial / 4 + 255) / 256;   // blocks that still get a full 128-bit pass
+    if (chunks > want) chunks = want < 1 ? 1 : (int)want;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   bias_grad_kernel<<<dim3(chunks, c), 256, 0, st>>>(g, ws, n, c, spatial);
   int rc = check_launch("bias_grad_kernel");

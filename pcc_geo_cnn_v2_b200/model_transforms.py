@@ -159,9 +159,9 @@ class _ConvBase(Layer):
         """Device-resident derived parameters (cached)."""
         if key not in self._dev:
             if key == 'w_tap':
-                self._dev[key] = torch.from_numpy(self.tap_major()).cuda()
+                self._dev[key] = ops.upload(self.tap_major())
             elif key == 'bias':
-                self._dev[key] = None if self.bias is None else torch.from_numpy(self.bias).cuda()
+                self._dev[key] = None if self.bias is None else ops.upload(self.bias)
             elif key.startswith('w_gemm'):
                 terms = int(key[-1])
                 self._dev[key] = ops.gemm_pack_weights(self.tap_major(), self.in_channels, self.filters, self.k, self.stride,

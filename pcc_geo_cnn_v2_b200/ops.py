@@ -43,6 +43,17 @@ def blocked_numel(n, c, d, h, w, terms):
     return terms * n * round_up(c, 16) * d * h * w
 
 
+def upload(arr):
+    """numpy -> device through pinned staging, without blocking the host: a pageable `.cuda()` copy first waits for everything queued
+    on the stream, which stalls a training step once per packed weight image.  torch's pinned-memory cache recycles the
+    staging block after the copy has run."""
+    L.require_cuda()
+    src = torch.from_numpy(np.ascontiguousarray(arr))
+    pin = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    pin.copy_(src)
+    return pin.to('cuda', non_blocking=True)
+
+
 def f32_to_blocked(x, terms, out=None):
     L.require_cuda()
     _f32c(x)
@@ -86,7 +97,7 @@ def umma_pack_weights(w_tap_host, cin, cout, stride, transposed, terms):
     rc = L.lib().pccgeo_umma_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, stride, int(transposed), terms)
     if rc < 0:
         L.check(int(rc), 'umma_pack_weights')
-    return torch.from_numpy(img).cuda()
+    return upload(img)
 
 
 def conv3d_umma(xb, in_shape, wpacked, bias, cout, stride, transposed, relu, terms, residual_b=None, out=None):
@@ -112,7 +123,7 @@ def umma_hl_pack_weights(w_tap_host, cin, cout, transposed):
     rc = L.lib().pccgeo_umma_hl_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, int(transposed))
     if rc < 0:
         L.check(int(rc), 'umma_hl_pack_weights')
-    return torch.from_numpy(img).cuda()
+    return upload(img)
 
 
 def conv3d_umma_hl(xb, in_shape, wpacked, bias, cout, transposed, relu, residual_b=None, out=None):
@@ -137,7 +148,7 @@ def umma_zy_pack_weights(w_tap_host, cin, cout, transposed, terms):
     rc = L.lib().pccgeo_umma_zy_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, int(transposed), terms)
     if rc < 0:
         L.check(int(rc), 'umma_zy_pack_weights')
-    return torch.from_numpy(img).cuda()
+    return upload(img)
 
 
 def conv3d_umma_zy(xb, in_shape, wpacked, bias, cout, relu, terms, residual_b=None, out=None):
@@ -162,7 +173,7 @@ def umma_ys_pack_weights(w_tap_host, cin, cout, transposed, terms):
     rc = L.lib().pccgeo_umma_ys_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, int(transposed), terms)
     if rc < 0:
         L.check(int(rc), 'umma_ys_pack_weights')
-    return torch.from_numpy(img).cuda()
+    return upload(img)
 
 
 def conv3d_umma_ys(xb, in_shape, wpacked, bias, cout, relu, terms, residual_b=None, out=None):
@@ -187,7 +198,7 @@ def out1_pack_weights(w_tap_host, cin, transposed, terms):
     rc = L.lib().pccgeo_out1_pack_weights_host(L.ptr(w), L.ptr(img), cin, int(transposed), terms)
     if rc < 0:
         L.check(int(rc), 'out1_pack_weights')
-    return torch.from_numpy(img).cuda()
+    return upload(img)
 
 
 def conv3d_out1(xb, in_shape, wpacked, bias, relu, terms, want_f32=True, thresholds=None):
@@ -216,7 +227,7 @@ def gemm_pack_weights(w_tap_host, cin, cout, k, stride, transposed, terms):
     rc = L.lib().pccgeo_gemm_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, k, stride, int(transposed), terms)
     if rc < 0:
         L.check(int(rc), 'gemm_pack_weights')
-    return torch.from_numpy(img).cuda(), np.ascontiguousarray(img[:128].copy())
+    return upload(img), np.ascontiguousarray(img[:128].copy())
 
 
 def conv3d_gemm(xb, in_shape, wimg, bias, cout, stride, transposed, relu, terms, residual_b=None, out=None):

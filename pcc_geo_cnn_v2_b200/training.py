@@ -75,6 +75,7 @@ class Trainer:
         self.eb_adam = None
         self.aux_adam = None
         self.aux_lr = aux_lr
+        self.marks = []     # (label, host seconds) of the last step: where the host thread was when (tools/train_profile.py)
 
     # -- parameters ------------------------------------------------------------------------------------
     def _p(self, layer, in_channels):
@@ -88,26 +89,48 @@ class Trainer:
             self.params[layer] = p
         return self.params[layer]
 
+    def _params_to_host(self):
+        """{layer: (w numpy, b numpy | None)} with ONE device-to-host copy (a .cpu() per tensor is a stream sync per tensor)."""
+        parts = []
+        for p in self.params.values():
+            parts.append(p['w'].reshape(-1))
+            if p['b'] is not None:
+                parts.append(p['b'].reshape(-1))
+        flat = torch.cat(parts).cpu().numpy()
+        out, pos = {}, 0
+        for layer, p in self.params.items():
+            nw = p['w'].numel()
+            w = flat[pos:pos + nw].reshape(tuple(p['w'].shape))
+            pos += nw
+            b = None
+            if p['b'] is not None:
+                b = flat[pos:pos + p['b'].numel()].copy()
+                pos += p['b'].numel()
+            out[layer] = (w, b)
+        return out
+
     def sync_to_model(self):
         """Copy the trained device parameters back into the layers (Keras layouts) so that the model's own forward
         (validation `train()`), `get_weights()` and the codec path see them.  The model calls this lazily whenever it is used
         after a step (CompressionModel._sync_trainer), the way the reference's variables are simply shared by every graph."""
         self.dirty = False
+        host = self._params_to_host() if self.params else {}
         for layer, p in self.params.items():
-            w = p['w'].cpu().numpy().reshape(layer.k, layer.k, layer.k, layer.in_channels, layer.filters)
+            w = host[layer][0].reshape(layer.k, layer.k, layer.k, layer.in_channels, layer.filters)
             if layer.transposed:
                 w = w.transpose(0, 1, 2, 4, 3)
-            layer.set_weights(np.ascontiguousarray(w), None if p['b'] is None else p['b'].cpu().numpy())
+            layer.set_weights(np.ascontiguousarray(w), host[layer][1])
         self.model.entropy_bottleneck._invalidate()
 
     # -- tensor-core path: layers carry the current master weights ----------------------------------------
     def _refresh_layers(self):
         """Write the fp32 master weights into the layer objects (and their adjoint twins) so that the kernel dispatch packs
         this step's weights; one D2H per layer, packing happens lazily per kernel format."""
+        host = self._params_to_host()
         for layer, p in self.params.items():
-            w = p['w'].cpu().numpy().reshape(layer.k, layer.k, layer.k, layer.in_channels, layer.filters)
+            w = host[layer][0].reshape(layer.k, layer.k, layer.k, layer.in_channels, layer.filters)
             kern = np.ascontiguousarray(w.transpose(0, 1, 2, 4, 3)) if layer.transposed else w
-            layer.set_weights(kern, None if p['b'] is None else p['b'].cpu().numpy())
+            layer.set_weights(kern, host[layer][1])
             twin = self.twins.get(layer)
             if twin is None:
                 cls = MT.Conv3D if layer.transposed else MT.Conv3DTranspose
@@ -138,6 +161,18 @@ class Trainer:
                 raise NotImplementedError("residual_mode='concat' is not used by any reference config; training supports 'add'")
         return vals[out_id], (steps, out_id, vals)
 
+    def _wgrad(self, layer, x_in, gd):
+        """Weight gradient, tap-major (k^3, Cin, Cout).  Tensor-core mode: the stride-1 3x3x3 layers with 16 / 32 / 64 channels (85 % of
+        the weight-gradient FLOPs of c3p) run on the tcgen05 kernel in the active precision (bf16x3 by default); the rest -- stride-2
+        layers, the one-channel ends, the 8^3 and smaller volumes -- on the fp32 kernel."""
+        n, cin, d, h, w = x_in.shape
+        if self.tensor_cores:
+            terms = {'bf16x3': 2, 'bf16': 1, 'fp32': 0}[MT.get_precision()]
+            if terms and ops.wgrad_umma_eligible(n, cin, layer.filters, layer.k, layer.stride, d, h, w, terms):
+                return ops.conv3d_wgrad_umma(ops.f32_to_blocked(x_in, terms), ops.f32_to_blocked(gd, terms), tuple(x_in.shape),
+                                             layer.transposed, terms)
+        return ops.conv3d_wgrad_f32(x_in, gd, layer.filters, layer.k, layer.stride, layer.transposed)
+
     def _backward(self, tape, g_out, grads, need_input_grad=True):
         steps, out_id, vals = tape
         g = {out_id: g_out}
@@ -157,8 +192,7 @@ class Trainer:
                 gd = ops.relu_bwd(gd, vals[dst])
             p = self.params[layer]
             x_in = vals[src]
-            grads[layer] = {'w': ops.conv3d_wgrad_f32(x_in, gd, layer.filters, layer.k, layer.stride, layer.transposed),
-                            'b': ops.bias_grad_f32(gd) if p['b'] is not None else None}
+            grads[layer] = {'w': self._wgrad(layer, x_in, gd), 'b': ops.bias_grad_f32(gd) if p['b'] is not None else None}
             if src != 0 or need_input_grad:
                 # data gradient = the adjoint layer: conv <-> transposed conv, tap-major weights with the channel axes swapped
                 if self.tensor_cores:
@@ -220,10 +254,13 @@ class Trainer:
     def forward_backward(self, x, noise_y=None, noise_z=None):
         """Returns (values dict, grads dict): loss / fl / mbpov as python floats; grads[layer] = {'w','b'} (tap-major),
         grads['entropy_bottleneck'] = list of raw-variable gradients (matrices, biases, factors)."""
+        import time
         m = self.model
         x = x.contiguous().float()
         eb = m.entropy_bottleneck
         grads = {}
+        self.marks = [('start', time.perf_counter())]
+        mark = lambda label: self.marks.append((label, time.perf_counter()))
         if self.tensor_cores:
             if not self.params:   # first step: materialise the master weights (layers are built by the model's train())
                 for name, (steps, _) in self.traces.items():
@@ -231,6 +268,7 @@ class Trainer:
                         if s[0] == 'conv':
                             self._p(s[1], s[1].in_channels)
             self._refresh_layers()
+        mark('weights refreshed')
         y, tape_a = self._forward('analysis', x)
         dist = self._world()
         n_occ = float(x.sum(dtype=torch.float64))
@@ -253,14 +291,9 @@ class Trainer:
         else:
             _, sum_y = ops.eb_likelihood(y_tilde, ebp, want_likelihood=False)
         x_tilde, tape_s = self._forward('synthesis', y_tilde)
-        fl = float(ops.focal_loss_sum(x, x_tilde, self.gamma, self.alpha)[0])
-        ly, lz = float(sum_y[0]), float(sum_z[0]) if self.v2 else 0.0
-        if dist is not None:
-            fl, ly, lz = self._allreduce_scalars(dist, fl, ly, lz)   # reported values are those of the global batch
-        mb_y = ly * c
-        mb_z = lz * c if self.v2 else 0.0
-        values = {'fl': fl, 'mbpov_y': mb_y, 'mbpov_z': mb_z, 'mbpov': mb_y + mb_z, 'loss': self.lmbda * fl + mb_y + mb_z,
-                  'num_occupied_voxels': n_occ, 'x_tilde': x_tilde, 'y': y}
+        # the reported scalars are read back after the backward pass has been queued: a float() here would drain the GPU mid-step
+        fl_t = ops.focal_loss_sum(x, x_tilde, self.gamma, self.alpha)
+        mark('forward queued')
         # ---- backward
         g_xt = ops.focal_loss_bwd(x, x_tilde, self.gamma, self.alpha, self.lmbda)
         g_y = self._backward(tape_s, g_xt, grads)
@@ -275,6 +308,16 @@ class Trainer:
             dv, dpar = ops.eb_likelihood_bwd(y_tilde, ebp, c)
             g_y = ops.axpby(g_y, dv, 1.0, 1.0)
         self._backward(tape_a, g_y, grads, need_input_grad=False)
+        mark('backward queued')
+        fl = float(fl_t[0])
+        mark('backward done')
+        ly, lz = float(sum_y[0]), float(sum_z[0]) if self.v2 else 0.0
+        if dist is not None:
+            fl, ly, lz = self._allreduce_scalars(dist, fl, ly, lz)   # reported values are those of the global batch
+        mb_y = ly * c
+        mb_z = lz * c if self.v2 else 0.0
+        values = {'fl': fl, 'mbpov_y': mb_y, 'mbpov_z': mb_z, 'mbpov': mb_y + mb_z, 'loss': self.lmbda * fl + mb_y + mb_z,
+                  'num_occupied_voxels': n_occ, 'x_tilde': x_tilde, 'y': y}
         if dist is not None:
             # one flat all-reduce (sum) of every gradient: conv kernels, biases and the entropy bottleneck's (C,44) block
             parts = [dpar.reshape(-1)]
@@ -312,5 +355,6 @@ class Trainer:
         eb.updates[0]()                                   # entropy_bottleneck.updates[0]: refresh the quantised CDFs
         values['aux_loss'] = aux
         values['step'] = self.t
+        self.marks.append(('optimisers done', __import__('time').perf_counter()))
         self.dirty = True
         return values

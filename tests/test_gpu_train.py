@@ -137,7 +137,7 @@ def test_backward_kernels_on_identical_inputs():
         assert _rel(a, b) < 2e-5
     # ---- weight / bias / data gradients of the convolutions
     for transposed, k, s, cin, cout, shape in [(False, 3, 1, 16, 16, (8, 8, 8)), (False, 3, 2, 16, 32, (8, 8, 8)), (True, 3, 2, 32, 16, (4, 4, 4)),
-                                               (True, 3, 1, 16, 1, (8, 8, 8)), (False, 9, 2, 1, 8, (8, 8, 8)), (True, 5, 2, 8, 8, (4, 4, 4))]:
+                                               (True, 3, 1, 16, 1, (8, 8, 8)), (False, 3, 2, 1, 16, (8, 8, 8)), (True, 3, 1, 16, 1, (5, 6, 40)), (False, 9, 2, 1, 8, (8, 8, 8)), (True, 5, 2, 8, 8, (4, 4, 4))]:
         x = torch.tensor(rng.normal(size=(2, cin) + shape), dtype=DT, requires_grad=True)
         kshape = (k, k, k, cout, cin) if transposed else (k, k, k, cin, cout)
         kern = torch.tensor(rng.normal(size=kshape) / np.sqrt(k ** 3 * cin), dtype=DT, requires_grad=True)

@@ -31,6 +31,8 @@ for _ in range(N):
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / N
 print(f'train step: {dt * 1e3:.1f} ms for batch {B} -> {B / dt:.1f} blocks/s; loss {out["loss"]:.4f}')
+mk = m.trainer.marks
+print('host marks (ms):', ', '.join(f'{a}: {(t - mk[0][1]) * 1e3:.1f}' for a, t in mk[1:]))
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     m.train_op(x)
     torch.cuda.synchronize()
@@ -44,3 +46,15 @@ tot = sum(v for v, _ in agg.values())
 print(f'kernel time {tot / 1e3:.1f} ms')
 for k, (v, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]:
     print(f'{v / 1e3:9.2f} ms {100 * v / tot:5.1f}%  n={n:3d}  {k}')
+print('-- wgrad launches in order')
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA and ('wgrad' in e.name and 'finish' not in e.name):
+        print(f'{(e.time_range.end - e.time_range.start) / 1e3:8.3f} ms  {e.name.split("(")[0][:60]}')
+import cProfile, pstats
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(3):
+    m.train_op(x)
+torch.cuda.synchronize()
+pr.disable()
+pstats.Stats(pr).sort_stats('cumulative').print_stats(35)
