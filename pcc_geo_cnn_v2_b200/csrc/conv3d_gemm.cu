@@ -483,15 +483,19 @@ extern "C" long long pccgeo_gemm_pack_weights_host(const float* w, void* out, in
     for (size_t slot = 0; slot < T.kernels[i].size(); ++slot) {
       const int kidx = T.kernels[i][slot];
       uint16_t* o = (uint16_t*)(img + chunks_off + wchunk * ((long long)i * T.nacc + (long long)slot));
-      for (int co = 0; co < cout; ++co)
-        for (int ci = 0; ci < cin; ++ci) {
-          const float val = w[((long long)kidx * cin + ci) * cout + co];
-          const int kc = ci / 16, kk = ci % 16, kcore = kk >> 3, ki = kk & 7;
-          const long long idx = ((((long long)kc * 2 + kcore) * (cop / 8) + (co >> 3)) * 8 + (co & 7)) * 8 + ki;
+      // runs once per layer and training step: walk the source contiguously
+      for (int ci = 0; ci < cin; ++ci) {
+        const float* wr = w + ((long long)kidx * cin + ci) * cout;
+        const int kc = ci / 16, kk = ci % 16, kcore = kk >> 3, ki = kk & 7;
+        uint16_t* orow = o + ((long long)kc * 2 + kcore) * (cop / 8) * 64 + ki;
+        uint16_t* lrow = orow + per_term / 2;
+        for (int co = 0; co < cout; ++co) {
+          const float val = wr[co];
           const uint16_t hi = f2bf(val);
-          o[idx] = hi;
-          if (terms == 2) o[per_term / 2 + idx] = f2bf(val - bf2f(hi));
+          orow[co * 8] = hi;
+          if (terms == 2) lrow[co * 8] = f2bf(val - bf2f(hi));
         }
+      }
     }
   }
   return total;

@@ -103,7 +103,7 @@ class EntropyBottleneck:
             for i in range(3):
                 p[:, 34 + 3 * i:37 + 3 * i] = np.tanh(self.factors[i].astype(np.float64)).astype(np.float32)[:, :, 0]
             p[:, 43] = self.medians
-            self._dev_params = torch.from_numpy(p).cuda()
+            self._dev_params = ops.upload(p)
         return self._dev_params
 
     # -- host-side table construction (float64) ------------------------------------------------------

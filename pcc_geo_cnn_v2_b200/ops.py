@@ -217,13 +217,20 @@ def conv3d_out1(xb, in_shape, wpacked, bias, relu, terms, want_f32=True, thresho
     return xh, bits, counts
 
 
+_gemm_img_size = {}
+
+
 def gemm_pack_weights(w_tap_host, cin, cout, k, stride, transposed, terms):
     """numpy fp32 (k^3, Cin, Cout) -> (device uint8 image, host header bytes) for pccgeo_conv3d_gemm."""
     w = np.ascontiguousarray(w_tap_host, np.float32)
-    size = L.lib().pccgeo_gemm_pack_weights_host(L.ptr(w), None, cin, cout, k, stride, int(transposed), terms)
-    if size <= 0:
-        L.check(int(size) if size < 0 else -1, 'gemm_pack_weights')
-    img = np.zeros(size, np.uint8)
+    geo = (cin, cout, k, stride, int(transposed), terms)
+    size = _gemm_img_size.get(geo)
+    if size is None:
+        size = L.lib().pccgeo_gemm_pack_weights_host(L.ptr(w), None, cin, cout, k, stride, int(transposed), terms)
+        if size <= 0:
+            L.check(int(size) if size < 0 else -1, 'gemm_pack_weights')
+        _gemm_img_size[geo] = size
+    img = np.empty(size, np.uint8)   # the packer clears the image itself
     rc = L.lib().pccgeo_gemm_pack_weights_host(L.ptr(w), L.ptr(img), cin, cout, k, stride, int(transposed), terms)
     if rc < 0:
         L.check(int(rc), 'gemm_pack_weights')

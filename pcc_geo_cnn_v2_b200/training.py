@@ -351,8 +351,8 @@ class Trainer:
         aux, gq = self._aux_loss_and_grad()
         self.eb_adam.step(arrays, grads['entropy_bottleneck'])
         self.aux_adam.step([eb.quantiles], [gq])
-        eb._invalidate()
-        eb.updates[0]()                                   # entropy_bottleneck.updates[0]: refresh the quantised CDFs
+        eb._invalidate()    # entropy_bottleneck.updates[0] (the quantised-CDF refresh) is lazy here: `tables` rebuilds them from the
+                            # current variables on their next use (compress / decompress), not 64 host CDF quantisations per step
         values['aux_loss'] = aux
         values['step'] = self.t
         self.marks.append(('optimisers done', __import__('time').perf_counter()))
