@@ -234,21 +234,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_umma_kernel(const __grid
   }
 }
 
-// dw[tap][ci][co] = sum over the CTAs of the tap's kx class and over r, in a fixed order; taps mirrored for the transposed conv
-__global__ void wgrad_umma_finish_kernel(const float* __restrict__ partial, float* __restrict__ dw, int C, int R, int KXC, int ctas,
-                                         int transposed) {
+// dw[tap][ci][co] = sum over the CTAs of the tap's kx class and over r; taps mirrored for the transposed conv.  Eight threads share an
+// output (interleaved slices of the (cta, r) list, double sums) and are combined by shuffles in a fixed order: deterministic.
+__global__ void __launch_bounds__(256) wgrad_umma_finish_kernel(const float* __restrict__ partial, float* __restrict__ dw, int C, int R,
+                                                                int KXC, int ctas, int transposed) {
   const int total = 27 * C * C;
   const int KXS = 3 / KXC;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int tap = i / (C * C), pr = i % (C * C);
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sl = threadIdx.x & 7;
+  double s = 0.0;
+  int tap = 0, pr = 0;
+  if (i < total) {
+    tap = i / (C * C); pr = i % (C * C);
     const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
     const int kxl = KXC == 3 ? kx : 0, cls = KXC == 3 ? 0 : kx;
-    double s = 0.0;
-    for (int cta = cls; cta < ctas; cta += KXS)
-      for (int r = 0; r < R; ++r)
-        s += (double)partial[(size_t)cta * (R * 9 * KXC * C * C) + ((((size_t)r * 3 + kz) * 3 + ky) * KXC + kxl) * (C * C) + pr];
-    dw[(size_t)(transposed ? 26 - tap : tap) * (C * C) + pr] = (float)s;
+    const int nsrc = ((ctas - cls + KXS - 1) / KXS) * R;
+    for (int q = sl; q < nsrc; q += 8) {
+      const int cta = cls + (q / R) * KXS, r = q % R;
+      s += (double)partial[(size_t)cta * (R * 9 * KXC * C * C) + ((((size_t)r * 3 + kz) * 3 + ky) * KXC + kxl) * (C * C) + pr];
+    }
   }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (i < total && sl == 0) dw[(size_t)(transposed ? 26 - tap : tap) * (C * C) + pr] = (float)s;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -339,7 +346,7 @@ static int launch(const void* xb, const void* gb, float* dw, float* ws, int n, i
   if (lrc) return lrc;
   const int rc = check_launch("wgrad_umma_kernel");
   if (rc) return rc;
-  wgrad_umma_finish_kernel<<<(27 * C * C + 255) / 256, 256, 0, st>>>(ws, dw, C, R, KXC, pl.ctas, transposed);
+  wgrad_umma_finish_kernel<<<(27 * C * C * 8 + 255) / 256, 256, 0, st>>>(ws, dw, C, R, KXC, pl.ctas, transposed);
   return check_launch("wgrad_umma_finish_kernel");
 }
 

@@ -474,14 +474,14 @@ class _Val:
         return self.blk
 
 
-def run_steps(steps, out_id, x, pack=None, keep=None, extra=None):
+def run_steps(steps, out_id, x, pack=None, keep=None, extra=None, keep_vals=None):
     """Execute traced steps on a channels_first fp32 CUDA tensor.  pack = {'thresholds', 'want_f32'}: also return the
     packed thresholded occupancy of the (single-channel) output -> (y or None, bits, counts).  keep: dict that receives every
-    value (id -> fp32 tensor; the training path saves activations this way); extra: {id: fp32 tensor} of additional inputs
-    (e.g. a residual operand)."""
+    value (id -> fp32 tensor; the training path saves activations this way; keep_vals: the same ids -> _Val with the blocked form
+    when one exists); extra: {id: fp32 tensor} of additional inputs (e.g. a residual operand).  x may be a _Val."""
     mode = _precision['mode']
     terms = {'bf16x3': 2, 'bf16': 1, 'fp32': 0}[mode]
-    vals = {0: _Val(f32=x, shape=tuple(x.shape))}
+    vals = {0: x if isinstance(x, _Val) else _Val(f32=x, shape=tuple(x.shape))}   # a _Val input brings its blocked form along
     for vid, t in (extra or {}).items():
         vals[vid] = _Val(f32=t, shape=tuple(t.shape))
     last_use = {}
@@ -544,6 +544,8 @@ def run_steps(steps, out_id, x, pack=None, keep=None, extra=None):
             vals[s[3]] = _Val(f32=y, shape=tuple(y.shape))
         if keep is not None:
             keep[s[3]] = vals[s[3]].as_f32()
+            if keep_vals is not None:
+                keep_vals[s[3]] = vals[s[3]]      # both representations (the tcgen05 weight gradient reads the blocked one)
             continue
         for vid in [k for k, li in last_use.items() if li == i and k != out_id]:
             vals.pop(vid, None)

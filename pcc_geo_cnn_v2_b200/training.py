@@ -96,7 +96,11 @@ class Trainer:
             parts.append(p['w'].reshape(-1))
             if p['b'] is not None:
                 parts.append(p['b'].reshape(-1))
-        flat = torch.cat(parts).cpu().numpy()
+        dev = torch.cat(parts)
+        pin = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)     # pageable D2H runs at ~3 GB/s: 2.3 ms for c3p's 6.4 MB
+        pin.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        flat = pin.numpy()
         out, pos = {}, 0
         for layer, p in self.params.items():
             nw = p['w'].numel()
@@ -145,10 +149,10 @@ class Trainer:
             for s in steps:
                 if s[0] not in ('conv', 'add'):
                     raise NotImplementedError("residual_mode='concat' is not used by any reference config; training supports 'add'")
-            keep = {}
-            MT.run_steps([tuple(s) for s in steps], out_id, x, keep=keep)
+            keep, kv = {}, {}
+            MT.run_steps([tuple(s) for s in steps], out_id, x, keep=keep, keep_vals=kv)
             keep[0] = x
-            return keep[out_id], (steps, out_id, keep)
+            return keep[out_id], (steps, out_id, keep, kv)
         vals = {0: x}
         for s in steps:
             if s[0] == 'conv':
@@ -159,9 +163,9 @@ class Trainer:
                 vals[s[3]] = ops.axpby(vals[s[1]], vals[s[2]], 1.0, 1.0)
             else:
                 raise NotImplementedError("residual_mode='concat' is not used by any reference config; training supports 'add'")
-        return vals[out_id], (steps, out_id, vals)
+        return vals[out_id], (steps, out_id, vals, {})
 
-    def _wgrad(self, layer, x_in, gd):
+    def _wgrad(self, layer, x_in, gd, x_val=None, g_val=None):
         """Weight gradient, tap-major (k^3, Cin, Cout).  Tensor-core mode: the stride-1 3x3x3 layers with 16 / 32 / 64 channels (85 % of
         the weight-gradient FLOPs of c3p) run on the tcgen05 kernel in the active precision (bf16x3 by default); the rest -- stride-2
         layers, the one-channel ends, the 8^3 and smaller volumes -- on the fp32 kernel."""
@@ -169,12 +173,47 @@ class Trainer:
         if self.tensor_cores:
             terms = {'bf16x3': 2, 'bf16': 1, 'fp32': 0}[MT.get_precision()]
             if terms and ops.wgrad_umma_eligible(n, cin, layer.filters, layer.k, layer.stride, d, h, w, terms):
-                return ops.conv3d_wgrad_umma(ops.f32_to_blocked(x_in, terms), ops.f32_to_blocked(gd, terms), tuple(x_in.shape),
-                                             layer.transposed, terms)
+                # x_val / g_val: the forward pass' blocked activation and the gradient's blocked form, shared with the data-gradient conv
+                xb = x_val.as_blk(terms) if x_val is not None else ops.f32_to_blocked(x_in, terms)
+                gb = g_val.as_blk(terms) if g_val is not None else ops.f32_to_blocked(gd, terms)
+                return ops.conv3d_wgrad_umma(xb, gb, tuple(x_in.shape), layer.transposed, terms)
+            if terms and layer.k == 3 and layer.stride == 2:
+                dw = self._wgrad_stride2(layer, x_in, gd, terms)
+                if dw is not None:
+                    return dw
         return ops.conv3d_wgrad_f32(x_in, gd, layer.filters, layer.k, layer.stride, layer.transposed)
 
+    @staticmethod
+    def _wgrad_stride2(layer, x_in, gd, terms):
+        """Stride-2 layers on the stride-1 tcgen05 kernel by phase decomposition.  Both the stride-2 conv and the stride-2 transposed
+        conv read their large tensor L (the conv's input / the transposed conv's output gradient) at 2b + t, t in {0, 1, 2} per axis,
+        against the small tensor S at b:  dW[t] = sum_b L[2b + t] * S[b].  With the eight phase volumes L_p[b] = L[2b + p] stacked as
+        channels this is a stride-1 correlation: t = 0 -> (phase 0, offset 0), t = 1 -> (phase 1, offset 0), t = 2 -> (phase 0, offset
+        +1).  The phase channels are cut into chunks of C = channels of S (the kernel wants C in == C out); each chunk is one launch
+        and the (phase, offset) blocks that exist are picked from its 27 x C x C result."""
+        large, small = (gd, x_in) if layer.transposed else (x_in, gd)
+        n, c, sd, sh, sw = small.shape
+        cb = large.shape[1]
+        if c % cb or (8 * cb) % c or tuple(large.shape[2:]) != (2 * sd, 2 * sh, 2 * sw):
+            return None
+        if not ops.wgrad_umma_eligible(n, c, c, 3, 1, sd, sh, sw, terms):
+            return None
+        ppc, nch = c // cb, 8 * cb // c          # phases per chunk, chunks
+        ph = large.contiguous().view(n, cb, sd, 2, sh, 2, sw, 2).permute(3, 5, 7, 0, 1, 2, 4, 6).reshape(nch, ppc, n, cb, sd, sh, sw)
+        ph = ph.permute(0, 2, 1, 3, 4, 5, 6).reshape(nch, n, c, sd, sh, sw).contiguous()
+        sb = ops.f32_to_blocked(small, terms)
+        outs = [ops.conv3d_wgrad_umma(ops.f32_to_blocked(ph[j], terms), sb, (n, c, sd, sh, sw), False, terms) for j in range(nch)]
+        dw = torch.empty((27, x_in.shape[1], layer.filters), device=x_in.device, dtype=torch.float32)
+        for t in range(27):
+            tz, ty, tx = t // 9, (t // 3) % 3, t % 3
+            phase = (int(tz == 1) * 2 + int(ty == 1)) * 2 + int(tx == 1)
+            k = ((int(tz == 2) + 1) * 3 + int(ty == 2) + 1) * 3 + int(tx == 2) + 1
+            blk = outs[phase // ppc][k, (phase % ppc) * cb:(phase % ppc + 1) * cb, :]      # (channels of L, channels of S)
+            dw[t] = blk.t() if layer.transposed else blk
+        return dw
+
     def _backward(self, tape, g_out, grads, need_input_grad=True):
-        steps, out_id, vals = tape
+        steps, out_id, vals, kv = tape
         g = {out_id: g_out}
 
         def accumulate(vid, t):
@@ -192,11 +231,12 @@ class Trainer:
                 gd = ops.relu_bwd(gd, vals[dst])
             p = self.params[layer]
             x_in = vals[src]
-            grads[layer] = {'w': self._wgrad(layer, x_in, gd), 'b': ops.bias_grad_f32(gd) if p['b'] is not None else None}
+            g_val = MT._Val(f32=gd, shape=tuple(gd.shape)) if self.tensor_cores else None
+            grads[layer] = {'w': self._wgrad(layer, x_in, gd, kv.get(src), g_val), 'b': ops.bias_grad_f32(gd) if p['b'] is not None else None}
             if src != 0 or need_input_grad:
                 # data gradient = the adjoint layer: conv <-> transposed conv, tap-major weights with the channel axes swapped
                 if self.tensor_cores:
-                    gx = MT.run_layer(self.twins[layer], gd, g.pop(src, None))
+                    gx = MT.run_layer(self.twins[layer], g_val, g.pop(src, None))
                 else:
                     w_t = p['w'].transpose(1, 2).contiguous()
                     gx = ops.conv3d_f32(gd, w_t, None, layer.in_channels, layer.k, layer.stride, not layer.transposed, False, g.pop(src, None))

@@ -56,6 +56,24 @@ def test_wgrad_umma_matches_fp32_kernel_at_training_sizes(c, s, n):
     assert np.array_equal(got, again)            # deterministic: fixed reduction order
 
 
+@pytest.mark.parametrize('transposed,cin,cout,s_small,n', [(True, 32, 16, 16, 3), (False, 16, 32, 16, 2), (True, 64, 32, 16, 2), (True, 32, 16, 32, 32)])
+def test_stride2_layers_by_phase_decomposition(transposed, cin, cout, s_small, n):
+    """the trainer's stride-2 weight gradient (eight phase volumes of the large tensor as channels -> stride-1 tcgen05 launches) against
+    the fp32 kernel, which test_gpu_train.py pins to float64 autograd"""
+    from types import SimpleNamespace
+    from pcc_geo_cnn_v2_b200.training import Trainer
+    g = torch.Generator(device='cuda').manual_seed(cin + cout + s_small)
+    s_in = s_small if transposed else 2 * s_small
+    s_out = 2 * s_small if transposed else s_small
+    xd = torch.relu(torch.randn((n, cin, s_in, s_in, s_in), device='cuda', generator=g))
+    gd = torch.randn((n, cout, s_out, s_out, s_out), device='cuda', generator=g) * 1e-3
+    layer = SimpleNamespace(transposed=transposed, filters=cout, k=3, stride=2)
+    got = Trainer._wgrad_stride2(layer, xd, gd, 2)
+    assert got is not None
+    want = ops.conv3d_wgrad_f32(xd, gd, cout, 3, 2, transposed).cpu().numpy()
+    assert _rel(got.cpu().numpy(), want) < 2e-4, _rel(got.cpu().numpy(), want)
+
+
 def test_wgrad_umma_rejects_unsupported_geometry():
     assert not ops.wgrad_umma_eligible(2, 16, 32, 3, 1, 16, 16, 16)
     assert not ops.wgrad_umma_eligible(2, 16, 16, 3, 2, 16, 16, 16)
