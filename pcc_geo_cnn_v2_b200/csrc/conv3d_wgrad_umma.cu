@@ -5,8 +5,8 @@
 // SynthesisBlock and the hyper transforms (reference src/model_types.py:364-369 over src/model_transforms.py:62-81): the
 // backward-filter contraction
 //     dW[kz,ky,kx,ci,co] = sum_{n,z,y,x} X[n,ci,z+kz-1,y+ky-1,x+kx-1] * G[n,co,z,y,x]
-// which is 85 % of the weight-gradient FLOPs of a c3p training step (the stride-2 layers and the 8^3 / 4^3 / 2^3 volumes stay on
-// the fp32 kernel of train.cu).
+// which is 85 % of the weight-gradient FLOPs of a c3p training step; the stride-2 layers reach this kernel through a phase
+// decomposition of their large tensor (training.py::_wgrad_stride2), the 8^3 / 4^3 / 2^3 volumes stay on the fp32 kernel of train.cu.
 //
 // Formulation.  The contraction index is the voxel, so both operands are "MN-major" for the tensor core: in the blocked bf16
 // layout (term, N, C/8, D, H, W, 8) a row of voxels is a run of 16-byte items (8 channels each), which read as K = voxel,

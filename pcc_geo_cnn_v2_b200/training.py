@@ -7,11 +7,12 @@
 Forward and backward run as libpccgeo kernels with saved activations (no autograd).  The convolutions of the forward pass
 and the data gradients (the adjoint layer: conv <-> transposed conv with the same kernel array) go through the same
 kernel dispatch as the codec -- the tcgen05 kernels in the active precision mode (bf16x3 by default, fp32-class) -- with
-the packed weight images rebuilt from the fp32 master weights every step; weight / bias gradients, ReLU masks, focal-loss
-and likelihood backward are the fp32 kernels of csrc/train.cu.  That is `Trainer(..., tensor_cores=True)`
-(`model.train_tensor_cores = True`): 155 -> 99 ms per batch-32 c3p step, conv-kernel gradients within 1e-2 of float64
-autograd (the focal loss amplifies the 1e-5 forward differences).  The default keeps every conv on the fp32 CUDA-core
-kernel (gradients within 2e-3).  Both optimisers follow TF1's AdamOptimizer
+the packed weight images rebuilt from the fp32 master weights every step; the weight gradients of the 3x3x3 layers with 16 / 32 / 64
+channels run on the tcgen05 weight-gradient kernel (csrc/conv3d_wgrad_umma.cu; stride-2 layers by phase decomposition), bias
+gradients, ReLU masks, focal-loss and likelihood backward are the fp32 kernels of csrc/train.cu.  That is
+`Trainer(..., tensor_cores=True)` (`model.train_tensor_cores = True`): 155 -> 29 ms per batch-32 c3p step, conv-kernel gradients
+within 1e-2 of float64 autograd (the focal loss amplifies the 1e-5 forward differences).  The default keeps every conv on the fp32
+CUDA-core kernel (gradients within 2e-3).  Both optimisers follow TF1's AdamOptimizer
 (lr_t = lr*sqrt(1-b2^t)/(1-b1^t), theta -= lr_t*m/(sqrt(v)+eps)): Adam(1e-4) on every trainable of the main loss, Adam(1e-3)
 on the entropy bottleneck's quantiles (auxiliary loss).  Whole-batch sums everywhere (FL is sum-reduced and mbpov divides
 by the batch's occupied-voxel count), so data-parallel training all-reduces SUMS, not averages: with torch.distributed
