@@ -56,6 +56,7 @@ struct Params {
   int N, D, H, W;
   int terms, relu, cout_real;
   int ngroups, xsegs, ytiles;
+  int xch;                 // x chunks of 8 voxels per block in an M tile: the tile is (16 / xch) blocks x (8 * xch) x-voxels
   int nstage;
   long long term_stride;   // elements between precision terms of y / res
 };
@@ -196,8 +197,9 @@ __global__ void __launch_bounds__(NGROUPS * 128 + 96, 1) conv3d_umma_zy_kernel(c
           mbar_expect_tx(full, (uint32_t)STAGE_BYTES);
 #pragma unroll
           for (int t = 0; t < TERMS; ++t)
-            tma_load_5d(smem_u32(stages + (size_t)s * STAGE_BYTES + (size_t)t * TERM_BYTES), &tmap_x, full, (xs * TX - 1) * 8, yi, z, 0,
-                        t * p.N + ng * UNITS);
+            for (int c = 0; c < p.xch; ++c)   // one box per x chunk: (16 / xch) blocks x 10 voxels (its own halo)
+              tma_load_5d(smem_u32(stages + (size_t)s * STAGE_BYTES + (size_t)t * TERM_BYTES + (size_t)c * (UNITS / p.xch) * UNIT_BYTES), &tmap_x, full,
+                          ((xs * p.xch + c) * TX - 1) * 8, yi, z, 0, t * p.N + ng * (UNITS / p.xch));
           if (++s == (uint32_t)p.nstage) { s = 0; phase ^= 1; }
         }
     }
@@ -283,7 +285,9 @@ __global__ void __launch_bounds__(NGROUPS * 128 + 96, 1) conv3d_umma_zy_kernel(c
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access (warp id % 4)
     const int grp = ew >> 2;
     const int row = quad * 32 + lane; // M row = TMEM lane
-    const int n = ng * UNITS + (row >> 3), x = xs * TX + (row & 7);
+    // M row -> (block, x): unit u = row / 8 is x chunk u / (16 / xch) of block u % (16 / xch) of the tile
+    const int upc = UNITS / p.xch, unit = row >> 3;
+    const int n = ng * upc + unit % upc, x = (xs * p.xch + unit / upc) * TX + (row & 7);
     const bool live = n < p.N;
     float bias_r[COUT];
 #pragma unroll
@@ -472,8 +476,11 @@ extern "C" int pccgeo_conv3d_umma_zy(const void* xb, const void* wpacked, const 
   zy::Params p{};
   p.bias = bias; p.res = (const __nv_bfloat16*)residual_b; p.y = (__nv_bfloat16*)yb; p.wimg = (const uint8_t*)wpacked;
   p.N = n; p.D = d; p.H = h; p.W = wd; p.terms = terms; p.relu = relu; p.cout_real = cout;
-  p.ngroups = (n + zy::UNITS - 1) / zy::UNITS;
-  p.xsegs = wd / zy::TX;
+  // small batches: fill the 16 units of the M tile with several x chunks of fewer blocks
+  p.xch = 1;
+  while (p.xch < 4 && n % (zy::UNITS / p.xch) != 0 && wd % (zy::TX * p.xch * 2) == 0) p.xch *= 2;
+  p.ngroups = (n + zy::UNITS / p.xch - 1) / (zy::UNITS / p.xch);
+  p.xsegs = wd / (zy::TX * p.xch);
   p.ytiles = zy::choose_ytiles(p.ngroups * p.xsegs, h);
   p.term_stride = (long long)n * 16 * d * h * wd;
   const int wbytes = 3 * 3 * terms * zy::BT_BYTES, stage_bytes = terms * zy::TERM_BYTES;
@@ -485,7 +492,7 @@ extern "C" int pccgeo_conv3d_umma_zy(const void* xb, const void* wpacked, const 
   // blocked layout (term, N, C/8, D, H, W, 8): {x*8ch, y, z, channel group, term*N + block}
   const cuuint64_t gdim[5] = {(cuuint64_t)wd * 8, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)zy::CGI, (cuuint64_t)terms * n};
   const cuuint64_t gstr[4] = {(cuuint64_t)wd * 16, (cuuint64_t)wd * h * 16, (cuuint64_t)wd * h * d * 16, (cuuint64_t)zy::CGI * wd * h * d * 16};
-  const cuuint32_t box[5] = {zy::PX * 8, 1, 1, zy::CGI, zy::UNITS};
+  const cuuint32_t box[5] = {zy::PX * 8, 1, 1, zy::CGI, (cuuint32_t)(zy::UNITS / p.xch)};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xb), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -202,11 +202,13 @@ class _ConvBase(Layer):
                 and d % 2 == 0 and h % 2 == 0 and w % 2 == 0)
 
     def zy_eligible(self, in_shape, terms):
-        """zy-ring kernel: stride-1 3x3x3 layers with 9..16 channels in and out, batches that fill its 16-block M tiles and
-        volumes large enough for its (16 blocks x 8 x x <= 10 rows) work items to occupy the GPU."""
+        """zy-ring kernel: stride-1 3x3x3 layers with 9..16 channels in and out, batches that fill its M tiles (16 blocks x 8 x-voxels,
+        or 8 x 16 / 4 x 32 for batches of 8 / 4 blocks -- the 128^3 blocks run at batch 4) and volumes large enough for its work items
+        (one M tile x <= 10 rows) to occupy the GPU."""
         n, c, d, h, w = in_shape
-        return (_zy_enabled[0] and terms and self.k == 3 and self.stride == 1 and 8 <= c <= 16 and 8 < self.filters <= 16 and w % 8 == 0
-                and n % 16 == 0 and (n // 16) * (w // 8) * h >= 148 * 4)
+        xch = 1 if n % 16 == 0 else 2 if n % 8 == 0 else 4
+        return (_zy_enabled[0] and terms and self.k == 3 and self.stride == 1 and 8 <= c <= 16 and 8 < self.filters <= 16
+                and n % (16 // xch) == 0 and w % (8 * xch) == 0 and (n * w // 128) * h >= 148 * 4)
 
     def hl_eligible(self, in_shape, terms):
         """hi/lo-stacked form of the TMA kernel: two-term precision, stride 1, <= 16 channels in and out."""

@@ -153,6 +153,8 @@ ZY_CASES = [
     (False, 16, 16, (4, 16, 8), 1), (True, 16, 16, (16, 16, 16), 2), (False, 12, 9, (3, 5, 8), 3), (True, 16, 16, (1, 1, 8), 1),
     (False, 16, 16, (2, 23, 16), 17), (True, 16, 16, (7, 64, 24), 16), (True, 16, 16, (20, 16, 24), 3), (False, 16, 16, (64, 64, 64), 32),
     (True, 16, 16, (5, 3, 8), 33),
+    # small batches: M tiles of 8 blocks x 16 x / 4 blocks x 32 x (the 128^3 blocks run at batch 4)
+    (False, 16, 16, (4, 12, 32), 4), (True, 16, 16, (3, 8, 64), 5), (False, 16, 16, (2, 10, 128), 4), (True, 16, 16, (3, 9, 32), 8),
 ]
 
 
