@@ -556,7 +556,7 @@ def train_step(P, args, peak_tf):
     best = min(out, key=lambda k: out[k]['ms_per_step'])
     return {'ms_per_step': out[best]['ms_per_step'], 'mode': best, 'batch': B, 'config': 'c3p, 64^3, gamma 2, alpha 0.75, lambda 1e-4',
             'gflop_per_step_algorithmic': GFLOP_TRAIN * B, 'modes': out,
-            'what': 'forward + backward (data and weight gradients) + 2 Adam steps + CDF-table refresh, CUDA events around 3 steps'}
+            'what': 'forward + backward (data and weight gradients, all convs on tcgen05 in tensor_cores mode) + 2 Adam steps, CUDA events around 3 steps'}
 
 
 if __name__ == '__main__':
