@@ -425,7 +425,7 @@ class CompressionModel:
         if self._graph_epoch != _mt.params_epoch[0]:  # parameters changed: packed weights were re-uploaded
             self._graphs.clear()
             self._graph_epoch = _mt.params_epoch[0]
-        key = (name, n, tuple(dims), _mt.get_precision(), torch.cuda.current_device())
+        key = (name, n, tuple(dims), _mt.get_precision(), torch.cuda.current_device(), getattr(self, 'lane', 0))
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = _StageGraph(fn)
@@ -433,7 +433,8 @@ class CompressionModel:
 
     def _static(self, n, dims):
         """Static device buffers the stage graphs of (n, dims) read their per-batch inputs from."""
-        key = (n, tuple(dims), torch.cuda.current_device())
+        # `lane`: independent sets of static buffers / stage graphs, so that two chains of batches can be in flight on two streams
+        key = (n, tuple(dims), torch.cuda.current_device(), getattr(self, 'lane', 0))
         st = self._statics.get(key)
         if st is None:
             st = self._statics[key] = {'x': torch.zeros((n, 1) + tuple(dims), device='cuda'),

@@ -39,6 +39,22 @@ def test_indexed_tables_roundtrip_and_bytes(ns, per, spread):
     assert np.array_equal(ops.range_decode(ref, offs, t, indexes=idx.reshape(-1)).reshape(ns, per), sym)
 
 
+@pytest.mark.parametrize('ns,per,spread', [(3, 2000, 1.0), (2, 257, 40.0), (4, 64, 0.05)])
+def test_device_coder_against_the_oracle_coder_directly(ns, per, spread):
+    """the device coder's bytes are the ORACLE's bytes (oracle/range_coder_c.c, no product code on the checking side), and the
+    oracle decodes them back; round 1 only had this transitively (device == product host coder == Python oracle)"""
+    from oracle import range_coder as RC
+    t = gaussian_tables(make_scale_table())
+    rng = np.random.default_rng(ns + per)
+    idx = rng.integers(0, 64, (ns, per)).astype(np.int32)
+    sym = np.round(rng.standard_normal((ns, per)) * make_scale_table()[idx] * spread).astype(np.int32)
+    got, packed, boffs = _device_strings(sym, t, idx)
+    for i in range(ns):
+        want = RC.encode_c(sym[i], idx[i], t['cdf'], t['cdf_length'], t['offset'])
+        assert got[i] == bytes(want)
+        assert np.array_equal(RC.decode_c(got[i], idx[i], t['cdf'], t['cdf_length'], t['offset']), sym[i])
+
+
 def test_per_channel_tables_and_empty_strings():
     t = gaussian_tables(make_scale_table())
     rows = 8
