@@ -32,7 +32,8 @@ def compress_point_cloud(model, points, resolution, octree_level, opt_metrics=('
     data_list, data, _ = model.compress_blocks(None, blocks, binstr, points, resolution, octree_level, with_normals=with_normals,
                                                opt_metrics=tuple(opt_metrics), max_deltas=tuple(max_deltas),
                                                fixed_threshold=fixed_threshold)
-    blobs = [gzip.compress(save_compressed_file(binstr, cur, resolution, octree_level)) for cur in data_list]
+    # mtime=0: the gzip header otherwise carries the wall-clock second, and two runs on the same input differ in four bytes
+    blobs = [gzip.compress(save_compressed_file(binstr, cur, resolution, octree_level), mtime=0) for cur in data_list]
     return blobs, data
 
 

@@ -12,6 +12,7 @@ int32 symbols / indexes and packed occupancy bits cross PCIe; the range coder ru
 independent stream per block and latent.
 """
 import logging
+import os
 from enum import Enum
 
 import numpy as np
@@ -565,7 +566,7 @@ class CompressionModel:
                 self._release(pend['bits'])
             return strings, pts
 
-        post_f, xs, devs = [], [], []
+        post_f, xs, devs, copy_evs = [], [], [], []
         graphs = self.use_graphs and thr_idx is not None and not keep_x_hat and debug_out is None
         if graphs and self.device_coder:
             return self._encode_blocks_device_coder(spans, coords_f, dims, thr_idx)
@@ -573,9 +574,33 @@ class CompressionModel:
             if len(post_f) >= self.pipeline_depth + 4:  # bound the driver's run-ahead (staging memory in flight)
                 post_f[len(post_f) - self.pipeline_depth - 4].result()
             if graphs:
-                lat, st = self.device_encode(self._h2d_staged(cf.result()), b - a, dims, None, block0=getattr(cf, 'block0', None))
-                pend = {'sym': self._d2h(*self._latent_tensors(lat))}
-                pend['bits'] = self._d2h(self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b])))
+                # copies run on their own streams (copy engines): on the compute stream a batch's 7 MB of coordinates and 8 MB of
+                # symbols would sit between two stage graphs -- 0.4 ms of idle SMs per batch (tools/e2e_gpu_busy.py)
+                main = torch.cuda.current_stream()
+                hs, ds = self._copy_streams()
+                staged = cf.result()
+                with torch.cuda.stream(hs):
+                    coords = self._h2d_staged(staged)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record()
+                if torch.is_tensor(coords):
+                    coords.record_stream(main)
+                main.wait_event(ev_in)
+                for ev in copy_evs:            # the previous batch's copies read the stage graphs' static outputs
+                    main.wait_event(ev)
+                lat, st = self.device_encode(coords, b - a, dims, None, block0=getattr(cf, 'block0', None))
+                ev_lat = torch.cuda.Event()
+                ev_lat.record()
+                ds.wait_event(ev_lat)
+                with torch.cuda.stream(ds):
+                    pend = {'sym': self._d2h(*self._latent_tensors(lat))}
+                bits = self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b]))
+                ev_bits = torch.cuda.Event()
+                ev_bits.record()
+                ds.wait_event(ev_bits)
+                with torch.cuda.stream(ds):
+                    pend['bits'] = self._d2h(bits)
+                copy_evs = [pend['sym'][1], pend['bits'][1]]
                 xs.append(None)
                 post_f.append(pool.submit(post, lat, pend))
                 continue
@@ -697,9 +722,12 @@ class CompressionModel:
         nb, lag, ahead = len(chunks), 2, 2
         f0 = {i: pool.submit(self._decode_host0, strings[i], dims) for i in range(min(ahead, nb))}
         ctxs, f2, f4, dbgs = {}, {}, [], []
+        # graphs: the batches alternate between two lanes (two sets of static buffers / stage graphs), so that a batch's symbols can
+        # be copied in (and its scale indexes / occupancy bits copied out) on the copy streams while the other lane's graph runs
+        self._pipe_evs = {}
         for i in range(nb + lag):
             if i < nb:
-                ctxs[i] = self._graph_dev1(f0.pop(i).result(), len(strings[i]), dims) if graphs else self._decode_dev1(f0.pop(i).result(), dims)
+                ctxs[i] = self._graph_dev1(f0.pop(i).result(), len(strings[i]), dims, lane=i % 2) if graphs else self._decode_dev1(f0.pop(i).result(), dims)
                 f2[i] = pool.submit(self._decode_host1, ctxs[i], strings[i])
                 if i + ahead < nb:
                     f0[i + ahead] = pool.submit(self._decode_host0, strings[i + ahead], dims)
@@ -709,10 +737,11 @@ class CompressionModel:
                 chunk, ctx = chunks[j], ctxs.pop(j)
                 idx = np.asarray([int(c[1]) for c in chunk], np.int64)
                 if graphs:
-                    dbg = {'bits': self._graph_dev2(ctx, len(chunk), dims, threshold_f32(self.thresholds, idx))}
+                    dbg = {'bits': self._graph_dev2(ctx, len(chunk), dims, threshold_f32(self.thresholds, idx), lane=j % 2)}
+                    pend = self._d2h_side(dbg['bits'], ('dec2', j % 2, len(chunk)))
                 else:
                     x_hat, dbg = self._decode_dev2(ctx, self._h2d(threshold_f32(self.thresholds, idx)), debug)
-                pend = self._d2h(dbg['bits'])
+                    pend = self._d2h(dbg['bits'])
                 f4.append(pool.submit(self._points_task, pend, dims))
                 dbgs.append(split_debug(self._debug_batch(dbg), [c[0] for c in chunk], self._debug_static()) if debug
                             else [None] * len(chunk))
@@ -731,6 +760,16 @@ class CompressionModel:
     def _groups(self, spans):
         per = max(1, self.coder_group_blocks // self.batch_size)
         return [spans[i:i + per] for i in range(0, len(spans), per)]
+
+    def _copy_streams(self, who='enc'):
+        """(host-to-device, device-to-host) side streams of this model on the current device; the compute stream itself when
+        PCCGEO_SIDE_COPIES=0 (every copy then sits between the stage graphs again: for A/B measurements and bisecting)"""
+        if os.environ.get('PCCGEO_SIDE_COPIES', '1') in ('0', 'dec' if who == 'enc' else 'enc'):
+            return torch.cuda.current_stream(), torch.cuda.current_stream()
+        key = ('copy_streams', torch.cuda.current_device())
+        if key not in self.__dict__:
+            self.__dict__[key] = (torch.cuda.Stream(), torch.cuda.Stream())
+        return self.__dict__[key]
 
     def _coder_stream(self):
         """The stream of the device coder: the current one, or with coder_overlap a side stream (one per model and device)."""
@@ -927,28 +966,77 @@ class CompressionModel:
         self._release(pend)
         return pts
 
-    def _graph_dev1(self, sym0_host, n, dims):
-        """decode stage 1 as a graph: first latent's symbols (host) -> static buffer -> _dec1_compute."""
-        st = self._static(n, dims)
-        self._copy_in(st['sym0'], sym0_host)
-        ctx = dict(self._stage('dec1', n, dims, lambda: self._dec1_compute(st['sym0'])))
-        if 'indexes' in ctx:
-            ctx['idx_pending'] = self._d2h(ctx['indexes'])
-        return ctx
-
-    def _graph_dev2(self, ctx, n, dims, thr):
-        """decode stage 3 as a graph: [second latent's symbols ->] synthesis + threshold + pack -> bits."""
-        st = self._static(n, dims)
-        if 'ysym_staged' in ctx:
-            host, buf = ctx.pop('ysym_staged')
-            st['sym1'].copy_(host.view(st['sym1'].shape), non_blocking=True)
+    # Stage graphs of the decode pipeline with their copies on the copy streams.  self._pipe_evs[(stage, lane, batch size)] -- the key of
+    # a set of static buffers -- holds what the next user of those buffers has to wait for: 'graph' = the last replay (it reads the static inputs), 'out' = the
+    # device-to-host copy of its static outputs.
+    def _lane_in(self, key, fill):
+        """Run `fill()` (host-to-device copies into this lane's static inputs) on the H2D stream, after the lane's previous graph;
+        make the compute stream wait for it and for the lane's previous output copy."""
+        main = torch.cuda.current_stream()
+        hs, _ = self._copy_streams('dec')
+        prev = self._pipe_evs.get(key, {})
+        with torch.cuda.stream(hs):
+            if 'graph' in prev:
+                hs.wait_event(prev['graph'])
+            else:
+                hs.wait_stream(main)   # first use of the lane: its static buffers were just allocated and zero-filled on the compute stream
+            fill()
             ev = torch.cuda.Event()
             ev.record()
-            _pinned.put_after(buf, ev)
-        elif 'ysym' in ctx:
-            st['sym1'].copy_(ctx['ysym']) if torch.is_tensor(ctx['ysym']) else self._copy_in(st['sym1'], ctx['ysym'])
-        st['thr'].copy_(thr) if torch.is_tensor(thr) else self._copy_in(st['thr'], thr)
-        return self._stage('dec2', n, dims, lambda: self._dec2_compute(ctx, st))
+        main.wait_event(ev)
+        if 'out' in prev:
+            main.wait_event(prev['out'])
+
+    def _lane_done(self, key):
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pipe_evs.setdefault(key, {})['graph'] = ev
+
+    def _d2h_side(self, tensor, key):
+        """_d2h of a stage graph's static output on the D2H stream, after the graph recorded by _lane_done(key)."""
+        _, ds = self._copy_streams('dec')
+        ds.wait_event(self._pipe_evs[key]['graph'])
+        with torch.cuda.stream(ds):
+            pend = self._d2h(tensor)
+        self._pipe_evs[key]['out'] = pend[1]
+        return pend
+
+    def _graph_dev1(self, sym0_host, n, dims, lane=0):
+        """decode stage 1 as a graph: first latent's symbols (host) -> static buffer -> _dec1_compute."""
+        self.lane = lane
+        try:
+            st = self._static(n, dims)
+            self._lane_in(('dec1', lane, n), lambda: self._copy_in(st['sym0'], sym0_host))
+            ctx = dict(self._stage('dec1', n, dims, lambda: self._dec1_compute(st['sym0'])))
+            self._lane_done(('dec1', lane, n))
+            if 'indexes' in ctx:
+                ctx['idx_pending'] = self._d2h_side(ctx['indexes'], ('dec1', lane, n))
+            return ctx
+        finally:
+            self.lane = 0
+
+    def _graph_dev2(self, ctx, n, dims, thr, lane=0):
+        """decode stage 3 as a graph: [second latent's symbols ->] synthesis + threshold + pack -> bits."""
+        self.lane = lane
+        try:
+            st = self._static(n, dims)
+
+            def fill():
+                if 'ysym_staged' in ctx:
+                    host, buf = ctx.pop('ysym_staged')
+                    st['sym1'].copy_(host.view(st['sym1'].shape), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    _pinned.put_after(buf, ev)
+                elif 'ysym' in ctx:
+                    st['sym1'].copy_(ctx['ysym']) if torch.is_tensor(ctx['ysym']) else self._copy_in(st['sym1'], ctx['ysym'])
+                st['thr'].copy_(thr) if torch.is_tensor(thr) else self._copy_in(st['thr'], thr)
+            self._lane_in(('dec2', lane, n), fill)
+            bits = self._stage('dec2', n, dims, lambda: self._dec2_compute(ctx, st))
+            self._lane_done(('dec2', lane, n))
+            return bits
+        finally:
+            self.lane = 0
 
     def _decode_batch(self, strings_list, dims, thresholds=None, want_x_hat=True):
         """One batch through the four decode stages, sequentially."""
@@ -1027,7 +1115,7 @@ class CompressionModelV1(CompressionModel):
     # one latent: nothing on the GPU between the two host stages, so the decode graph is a single stage (dequantise +
     # synthesis + threshold + pack) fed from the static symbol buffer right before its replay -- a 'dec1' graph would
     # leave its output in a static tensor that the next batch's replay overwrites before this batch's synthesis runs
-    def _graph_dev1(self, sym0_host, n, dims):
+    def _graph_dev1(self, sym0_host, n, dims, lane=0):
         return {'ysym': sym0_host}
 
     def _dec2_compute(self, ctx, st):

@@ -13,7 +13,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 NB = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 B = 32
 m = P.ModelConfigType['c3p'].build(batch_size=B)
-m.set_weights(synthetic.trained_like_weights(m, seed=42))
+m.set_weights((synthetic.trained_like_weights if os.environ.get("E2E_STRESS") else synthetic.codec_like_weights)(m, seed=42))
 m.compress((1, 1, 64, 64, 64))
 uniq = synthetic.surface_blocks(8, size=64, seed=100)
 blocks = [uniq[i % 8] for i in range(B * NB)]
