@@ -785,7 +785,7 @@ class CompressionModel:
         lats = self._coder_latents(dims)
         cf_of = dict(zip(spans, coords_f))
         main, side = torch.cuda.current_stream(), self._coder_stream()
-        str_f, pts_f = [], []
+        str_f, pts_f, bits_ev = [], [], None
         for group in self._groups(spans):
             g0, g1 = group[0][0], group[-1][1]
             big = {}
@@ -796,10 +796,28 @@ class CompressionModel:
                         big[k].record_stream(side)
             for a, b in group:
                 cf = cf_of[(a, b)]
-                lat, st = self.device_encode(self._h2d_staged(cf.result()), b - a, dims, None, block0=getattr(cf, 'block0', None))
+                # coordinates in / occupancy bits out on the copy streams (see encode_blocks)
+                hs, ds = self._copy_streams()
+                staged = cf.result()
+                with torch.cuda.stream(hs):
+                    coords = self._h2d_staged(staged)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record()
+                if torch.is_tensor(coords):
+                    coords.record_stream(main)
+                main.wait_event(ev_in)
+                if bits_ev is not None:
+                    main.wait_event(bits_ev)     # the previous batch's bits (a static output of the synthesis graph) are still being copied
+                lat, st = self.device_encode(coords, b - a, dims, None, block0=getattr(cf, 'block0', None))
                 for k, t in big.items():
                     t[a - g0:b - g0].copy_(lat[k].view(t[a - g0:b - g0].shape))
-                pend = self._d2h(self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b])))
+                bits = self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b]))
+                ev_bits = torch.cuda.Event()
+                ev_bits.record()
+                ds.wait_event(ev_bits)
+                with torch.cuda.stream(ds):
+                    pend = self._d2h(bits)
+                bits_ev = pend[1]
                 pts_f.append(pool.submit(self._points_task, pend, dims))
             # the group's streams are coded on the side stream, under the next group's transforms
             side.wait_stream(main)
@@ -927,6 +945,9 @@ class CompressionModel:
             ev.record(side)
             return sym[lats[0]['sym']], ev
 
+        bits_ev = [None]
+        _, ds = self._copy_streams('dec')
+
         def synthesize_group(group, ysym, ev):
             g0 = group[0][0]
             main.wait_event(ev)
@@ -935,8 +956,16 @@ class CompressionModel:
                 st['sym1'].copy_(ysym[a - g0:b - g0].view(st['sym1'].shape))
                 thr = threshold_f32(self.thresholds, np.asarray([int(c[1]) for c in flat[a:b]], np.int64))
                 self._copy_in(st['thr'], thr)
+                if bits_ev[0] is not None:
+                    main.wait_event(bits_ev[0])   # the previous batch's bits (static output of this graph) are copied on the D2H stream
                 bits = self._stage('dec2', b - a, dims, lambda: self._dec2_compute(None, st))
-                f4.append(pool.submit(self._points_task, self._d2h(bits), dims))
+                done = torch.cuda.Event()
+                done.record()
+                ds.wait_event(done)
+                with torch.cuda.stream(ds):
+                    pend = self._d2h(bits)
+                bits_ev[0] = pend[1]
+                f4.append(pool.submit(self._points_task, pend, dims))
 
         # software pipeline with a lag of one group: the side stream decodes group g+1 under the synthesis of group g
         prev = None
