@@ -15,6 +15,10 @@ B = 32
 m = P.ModelConfigType['c3p'].build(batch_size=B)
 m.set_weights((synthetic.trained_like_weights if os.environ.get("E2E_STRESS") else synthetic.codec_like_weights)(m, seed=42))
 m.compress((1, 1, 64, 64, 64))
+if os.environ.get('E2E_GROUP'):
+    m.coder_group_blocks = int(os.environ['E2E_GROUP'])
+if os.environ.get('E2E_OVERLAP'):
+    m.coder_overlap = os.environ['E2E_OVERLAP'] == '1'
 uniq = synthetic.surface_blocks(8, size=64, seed=100)
 blocks = [uniq[i % 8] for i in range(B * NB)]
 import gc  # noqa: E402
