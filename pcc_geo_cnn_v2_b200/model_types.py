@@ -440,6 +440,9 @@ class CompressionModel:
         if st is None:
             st = self._statics[key] = {'x': torch.zeros((n, 1) + tuple(dims), device='cuda'),
                                        'thr': torch.zeros(n, device='cuda'), **self._static_latents(n, dims)}
+            # the zero fills run on the stream that is current NOW: whoever writes these buffers from another stream first waits here
+            st['ready'] = torch.cuda.Event()
+            st['ready'].record()
         return st
 
     def device_encode(self, coords_dev, n, dims, thr, block0=None):
@@ -566,7 +569,7 @@ class CompressionModel:
                 self._release(pend['bits'])
             return strings, pts
 
-        post_f, xs, devs, copy_evs = [], [], [], []
+        post_f, xs, devs, lane_evs = [], [], [], {}
         graphs = self.use_graphs and thr_idx is not None and not keep_x_hat and debug_out is None
         if graphs and self.device_coder:
             return self._encode_blocks_device_coder(spans, coords_f, dims, thr_idx)
@@ -574,33 +577,46 @@ class CompressionModel:
             if len(post_f) >= self.pipeline_depth + 4:  # bound the driver's run-ahead (staging memory in flight)
                 post_f[len(post_f) - self.pipeline_depth - 4].result()
             if graphs:
-                # copies run on their own streams (copy engines): on the compute stream a batch's 7 MB of coordinates and 8 MB of
-                # symbols would sit between two stage graphs -- 0.4 ms of idle SMs per batch (tools/e2e_gpu_busy.py)
+                # Two compute streams and two lanes (sets of static buffers / stage graphs): batch i+1's analysis + hyper transforms --
+                # small volumes that leave most SMs idle -- run on the front stream beside batch i's synthesis on the main stream.
+                # Copies run on their own streams (copy engines): on a compute stream a batch's 7 MB of coordinates and 8 MB of
+                # symbols would sit between two stage graphs, 0.4 ms of idle SMs per batch (tools/e2e_gpu_busy.py).  Every hand-over
+                # is an event; lane_evs[(lane, n)] = what the next user of that lane's buffers waits for.
                 main = torch.cuda.current_stream()
                 hs, ds = self._copy_streams()
+                front = self._front_stream()
+                if not lane_evs:
+                    front.wait_stream(main)       # whatever produced the inputs (e.g. the octree partition kernels)
+                lane, n = len(post_f) % 2, b - a
                 staged = cf.result()
                 with torch.cuda.stream(hs):
                     coords = self._h2d_staged(staged)
                     ev_in = torch.cuda.Event()
                     ev_in.record()
                 if torch.is_tensor(coords):
-                    coords.record_stream(main)
-                main.wait_event(ev_in)
-                for ev in copy_evs:            # the previous batch's copies read the stage graphs' static outputs
-                    main.wait_event(ev)
-                lat, st = self.device_encode(coords, b - a, dims, None, block0=getattr(cf, 'block0', None))
-                ev_lat = torch.cuda.Event()
-                ev_lat.record()
-                ds.wait_event(ev_lat)
-                with torch.cuda.stream(ds):
-                    pend = {'sym': self._d2h(*self._latent_tensors(lat))}
-                bits = self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b]))
+                    coords.record_stream(front)
+                self.lane = lane
+                try:
+                    with torch.cuda.stream(front):
+                        front.wait_event(ev_in)
+                        for ev in lane_evs.get((lane, n), ()):
+                            front.wait_event(ev)
+                        lat, st = self.device_encode(coords, n, dims, None, block0=getattr(cf, 'block0', None))
+                        ev_lat = torch.cuda.Event()
+                        ev_lat.record()
+                    ds.wait_event(ev_lat)
+                    with torch.cuda.stream(ds):
+                        pend = {'sym': self._d2h(*self._latent_tensors(lat))}
+                    main.wait_event(ev_lat)
+                    bits = self.device_synthesis(lat, st, n, dims, threshold_f32(self.thresholds, thr_idx[a:b]))
+                finally:
+                    self.lane = 0
                 ev_bits = torch.cuda.Event()
                 ev_bits.record()
                 ds.wait_event(ev_bits)
                 with torch.cuda.stream(ds):
                     pend['bits'] = self._d2h(bits)
-                copy_evs = [pend['sym'][1], pend['bits'][1]]
+                lane_evs[(lane, n)] = [ev_bits, pend['sym'][1], pend['bits'][1]]
                 xs.append(None)
                 post_f.append(pool.submit(post, lat, pend))
                 continue
@@ -771,6 +787,15 @@ class CompressionModel:
             self.__dict__[key] = (torch.cuda.Stream(), torch.cuda.Stream())
         return self.__dict__[key]
 
+    def _front_stream(self, who='enc'):
+        """second compute stream of the block loops (the main stream itself when PCCGEO_SIDE_COPIES switches the side streams off)"""
+        if os.environ.get('PCCGEO_SIDE_COPIES', '1') in ('0', 'dec' if who == 'enc' else 'enc'):
+            return torch.cuda.current_stream()
+        key = ('front_stream', torch.cuda.current_device())
+        if key not in self.__dict__:
+            self.__dict__[key] = torch.cuda.Stream()
+        return self.__dict__[key]
+
     def _coder_stream(self):
         """The stream of the device coder: the current one, or with coder_overlap a side stream (one per model and device)."""
         if not self.coder_overlap:
@@ -785,7 +810,10 @@ class CompressionModel:
         lats = self._coder_latents(dims)
         cf_of = dict(zip(spans, coords_f))
         main, side = torch.cuda.current_stream(), self._coder_stream()
-        str_f, pts_f, bits_ev = [], [], None
+        front = self._front_stream()
+        front.wait_stream(main)
+        hs, ds = self._copy_streams()
+        str_f, pts_f, lane_evs, nbatch = [], [], {}, 0
         for group in self._groups(spans):
             g0, g1 = group[0][0], group[-1][1]
             big = {}
@@ -794,30 +822,41 @@ class CompressionModel:
                     if k is not None and k not in big:
                         big[k] = torch.empty((g1 - g0,) + tuple(l['shape']), dtype=torch.int32, device='cuda')
                         big[k].record_stream(side)
+                        big[k].record_stream(front)
             for a, b in group:
                 cf = cf_of[(a, b)]
-                # coordinates in / occupancy bits out on the copy streams (see encode_blocks)
-                hs, ds = self._copy_streams()
+                # as in encode_blocks: coordinates in / bits out on the copy streams, analysis + hyper transforms of a batch on the
+                # front stream beside the previous batch's synthesis, two lanes of static buffers / stage graphs
+                lane, n = nbatch % 2, b - a
+                nbatch += 1
                 staged = cf.result()
                 with torch.cuda.stream(hs):
                     coords = self._h2d_staged(staged)
                     ev_in = torch.cuda.Event()
                     ev_in.record()
                 if torch.is_tensor(coords):
-                    coords.record_stream(main)
-                main.wait_event(ev_in)
-                if bits_ev is not None:
-                    main.wait_event(bits_ev)     # the previous batch's bits (a static output of the synthesis graph) are still being copied
-                lat, st = self.device_encode(coords, b - a, dims, None, block0=getattr(cf, 'block0', None))
-                for k, t in big.items():
-                    t[a - g0:b - g0].copy_(lat[k].view(t[a - g0:b - g0].shape))
-                bits = self.device_synthesis(lat, st, b - a, dims, threshold_f32(self.thresholds, thr_idx[a:b]))
+                    coords.record_stream(front)
+                self.lane = lane
+                try:
+                    with torch.cuda.stream(front):
+                        front.wait_event(ev_in)
+                        for ev in lane_evs.get((lane, n), ()):
+                            front.wait_event(ev)
+                        lat, st = self.device_encode(coords, n, dims, None, block0=getattr(cf, 'block0', None))
+                        for k, t in big.items():
+                            t[a - g0:b - g0].copy_(lat[k].view(t[a - g0:b - g0].shape))
+                        ev_lat = torch.cuda.Event()
+                        ev_lat.record()
+                    main.wait_event(ev_lat)
+                    bits = self.device_synthesis(lat, st, n, dims, threshold_f32(self.thresholds, thr_idx[a:b]))
+                finally:
+                    self.lane = 0
                 ev_bits = torch.cuda.Event()
                 ev_bits.record()
                 ds.wait_event(ev_bits)
                 with torch.cuda.stream(ds):
                     pend = self._d2h(bits)
-                bits_ev = pend[1]
+                lane_evs[(lane, n)] = [ev_bits, pend[1]]
                 pts_f.append(pool.submit(self._points_task, pend, dims))
             # the group's streams are coded on the side stream, under the next group's transforms
             side.wait_stream(main)
@@ -998,17 +1037,16 @@ class CompressionModel:
     # Stage graphs of the decode pipeline with their copies on the copy streams.  self._pipe_evs[(stage, lane, batch size)] -- the key of
     # a set of static buffers -- holds what the next user of those buffers has to wait for: 'graph' = the last replay (it reads the static inputs), 'out' = the
     # device-to-host copy of its static outputs.
-    def _lane_in(self, key, fill):
+    def _lane_in(self, key, fill, st):
         """Run `fill()` (host-to-device copies into this lane's static inputs) on the H2D stream, after the lane's previous graph;
         make the compute stream wait for it and for the lane's previous output copy."""
         main = torch.cuda.current_stream()
         hs, _ = self._copy_streams('dec')
         prev = self._pipe_evs.get(key, {})
         with torch.cuda.stream(hs):
+            hs.wait_event(st['ready'])     # first use of the lane: its static buffers were just allocated and zero-filled
             if 'graph' in prev:
                 hs.wait_event(prev['graph'])
-            else:
-                hs.wait_stream(main)   # first use of the lane: its static buffers were just allocated and zero-filled on the compute stream
             fill()
             ev = torch.cuda.Event()
             ev.record()
@@ -1034,10 +1072,12 @@ class CompressionModel:
         """decode stage 1 as a graph: first latent's symbols (host) -> static buffer -> _dec1_compute."""
         self.lane = lane
         try:
-            st = self._static(n, dims)
-            self._lane_in(('dec1', lane, n), lambda: self._copy_in(st['sym0'], sym0_host))
-            ctx = dict(self._stage('dec1', n, dims, lambda: self._dec1_compute(st['sym0'])))
-            self._lane_done(('dec1', lane, n))
+            # on the front stream: the hyper-synthesis of a batch (2^3 .. 8^3 volumes) runs beside another batch's synthesis
+            with torch.cuda.stream(self._front_stream('dec')):
+                st = self._static(n, dims)
+                self._lane_in(('dec1', lane, n), lambda: self._copy_in(st['sym0'], sym0_host), st)
+                ctx = dict(self._stage('dec1', n, dims, lambda: self._dec1_compute(st['sym0'])))
+                self._lane_done(('dec1', lane, n))
             if 'indexes' in ctx:
                 ctx['idx_pending'] = self._d2h_side(ctx['indexes'], ('dec1', lane, n))
             return ctx
@@ -1060,7 +1100,7 @@ class CompressionModel:
                 elif 'ysym' in ctx:
                     st['sym1'].copy_(ctx['ysym']) if torch.is_tensor(ctx['ysym']) else self._copy_in(st['sym1'], ctx['ysym'])
                 st['thr'].copy_(thr) if torch.is_tensor(thr) else self._copy_in(st['thr'], thr)
-            self._lane_in(('dec2', lane, n), fill)
+            self._lane_in(('dec2', lane, n), fill, st)
             bits = self._stage('dec2', n, dims, lambda: self._dec2_compute(ctx, st))
             self._lane_done(('dec2', lane, n))
             return bits
