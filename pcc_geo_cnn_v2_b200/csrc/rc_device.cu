@@ -302,25 +302,42 @@ __global__ void __launch_bounds__(kRcDecWarps * 32) rc_decode_kernel(
   // entry k of a row with n symbols: cdf[n] = 2^16 does not fit the 16-bit table and is implied; beyond the row: "infinite"
   auto entry = [&](int start, int k, int n) -> uint32_t { return k < n ? (uint32_t)s_cdf[start + k] : (k == n ? 0x10000u : 0x7fffffffu); };
   int nrow = row_of(lane);
-  uint32_t piv_next = entry(s_start[__shfl_sync(0xffffffffu, nrow, 0)], lane * (((s_len[__shfl_sync(0xffffffffu, nrow, 0)] - 1) >> 5) + 1),
-                            s_len[__shfl_sync(0xffffffffu, nrow, 0)] - 1);
   for (long long base = 0; base < per_stream; base += 32) {
     const int my_row = nrow;
     nrow = row_of(base + 32 + lane);   // next group's table indexes fly during this group's decoding
     const int cnt_syms = (int)min(32LL, per_stream - base);
     int32_t my_out = 0;
+    // Fast path: every lane prepares, for ITS symbol of the group, the interval of the value 0 (table entry -offset: the mode of
+    // the zero-mean Gaussian rows and of a trained factorized prior) as cdf_lo | (freq - 1) << 16.  Decoding symbol j then starts
+    // with ONE shuffle and a range test; only when the value is not 0 does the lane-parallel search below run.  At codec
+    // operating points (~98 % zeros) the chain per symbol shrinks from ~120 to ~25 instructions; the result is the same
+    // symbol the search would find (it is the s with cdf[s] * r <= code < cdf[s+1] * r).
+    uint32_t my_pack = 0;
+    bool my_fast = false;
+    {
+      const int st_ = s_start[my_row], n_ = s_len[my_row] - 1, m_ = -s_off[my_row];
+      if (m_ >= 0 && m_ < n_ - 1) {   // a regular symbol (not the escape slot)
+        const uint32_t lo_ = entry(st_, m_, n_), hi_ = entry(st_, m_ + 1, n_);
+        if (hi_ > lo_) { my_pack = lo_ | (hi_ - lo_ - 1u) << 16; my_fast = true; }
+      }
+    }
+    const uint32_t fast_mask = __ballot_sync(0xffffffffu, my_fast);
     for (int j = 0; j < cnt_syms; ++j) {
+      const uint32_t r = d.range >> kRcPrecision;   // < 2^16, cdf <= 2^16: the products fit
+      if ((fast_mask >> j) & 1u) {
+        const uint32_t pk = __shfl_sync(0xffffffffu, my_pack, j);
+        const uint32_t lo_r = (pk & 0xffffu) * r, fr = ((pk >> 16) + 1u) * r;
+        if (d.code - lo_r < fr) {    // unsigned: also false when code < lo_r.  Warp-uniform: every lane carries the coder state
+          d.code -= lo_r;
+          d.range = fr;
+          rc_dec_normalize(d, bs, lane);
+          continue;                  // my_out of lane j stays 0
+        }
+      }
       const int row = __shfl_sync(0xffffffffu, my_row, j);
       const int start = s_start[row], n = s_len[row] - 1, off = s_off[row];   // n symbols incl. the escape slot; cdf[0..n]
       const int step = (n >> 5) + 1;
-      const uint32_t piv = piv_next;
-      {   // the next symbol's pivots: issued now, consumed one symbol later
-        const int r_in = __shfl_sync(0xffffffffu, my_row, (j + 1) & 31), r_nx = __shfl_sync(0xffffffffu, nrow, 0);
-        const int rn = j + 1 < 32 ? r_in : r_nx;
-        const int nn = s_len[rn] - 1;
-        piv_next = entry(s_start[rn], lane * ((nn >> 5) + 1), nn);
-      }
-      const uint32_t r = d.range >> kRcPrecision;   // < 2^16, cdf <= 2^16: the products fit
+      const uint32_t piv = entry(start, lane * step, n);
       const int seg = __popc(__ballot_sync(0xffffffffu, lane >= 1 && lane * step < n && piv * r <= d.code));
       int lo = seg * step;
       uint32_t c_lo, c_hi;
