@@ -112,6 +112,18 @@ struct Decoder {
   }
   // lut (optional, 256 entries): lut[b] = largest symbol s with cdf[s] <= (b << (precision-8)); the search then scans
   // forward from there -- for the peaked tables of this codec that is 0-2 steps instead of an 11-step binary search.
+  // Try ONE candidate symbol m (the callers pass the table entry of the value 0, the mode of this codec's tables: ~98 % of the
+  // latents at its operating points): cdf[m] * r <= code < cdf[m+1] * r is exactly "decode() would return m", without the
+  // division and the search.  Returns false (state untouched) when the symbol is another one.
+  inline bool try_symbol(const int32_t* cdf, int m, int precision) {
+    const uint32_t r = range >> precision;
+    const uint32_t lo = r * (uint32_t)cdf[m], fr = r * (uint32_t)(cdf[m + 1] - cdf[m]);
+    if (code - lo >= fr) return false;   // unsigned: also when code < lo
+    code -= lo;
+    range = fr;
+    normalize();
+    return true;
+  }
   inline int decode(const int32_t* cdf, int n, int precision, const uint16_t* lut = nullptr) {
     const uint32_t r = range >> precision;
     uint32_t value = code / r;
@@ -206,6 +218,11 @@ bool decode_stream(const Tables& t, const uint8_t* b, const uint8_t* e, const in
     if (row_i < 0 || row_i >= t.rows) return false;
     const int32_t* row = t.cdf + (long long)row_i * t.cdf_stride;
     const int32_t max_value = t.cdf_length[row_i] - 2;
+    const int32_t zero = -t.offset[row_i];    // table entry of the value 0
+    if (zero >= 0 && zero < max_value && dec.try_symbol(row, zero, kPrecision)) {
+      out[i] = 0;
+      continue;
+    }
     long long value = dec.decode(row, max_value + 1, kPrecision, t.lut ? t.lut + (long long)row_i * 256 : nullptr);
     if (value == max_value) {
       int widths = 0;
@@ -256,10 +273,14 @@ bool decode_stream_x2(const Tables& t, const uint8_t* b0, const uint8_t* e0, con
     const int32_t* row0 = t.cdf + (long long)r0 * t.cdf_stride;
     const int32_t* row1 = t.cdf + (long long)r1 * t.cdf_stride;
     const int32_t m0 = t.cdf_length[r0] - 2, m1 = t.cdf_length[r1] - 2;
-    long long v0 = d0.decode(row0, m0 + 1, kPrecision, t.lut ? t.lut + (long long)r0 * 256 : nullptr);
-    long long v1 = d1.decode(row1, m1 + 1, kPrecision, t.lut ? t.lut + (long long)r1 * 256 : nullptr);
-    if (v0 == m0 && !escape(d0, v0, m0)) return false;
-    if (v1 == m1 && !escape(d1, v1, m1)) return false;
+    const int32_t z0 = -t.offset[r0], z1 = -t.offset[r1];
+    const bool hit0 = z0 >= 0 && z0 < m0 && d0.try_symbol(row0, z0, kPrecision);
+    const bool hit1 = z1 >= 0 && z1 < m1 && d1.try_symbol(row1, z1, kPrecision);
+    long long v0 = z0, v1 = z1;
+    if (!hit0) v0 = d0.decode(row0, m0 + 1, kPrecision, t.lut ? t.lut + (long long)r0 * 256 : nullptr);
+    if (!hit1) v1 = d1.decode(row1, m1 + 1, kPrecision, t.lut ? t.lut + (long long)r1 * 256 : nullptr);
+    if (!hit0 && v0 == m0 && !escape(d0, v0, m0)) return false;
+    if (!hit1 && v1 == m1 && !escape(d1, v1, m1)) return false;
     out0[i] = (int32_t)(v0 + t.offset[r0]);
     out1[i] = (int32_t)(v1 + t.offset[r1]);
   }
