@@ -192,6 +192,9 @@ conv3d_out1_kernel(const __grid_constant__ CUtensorMap tmap_x, const out1::Param
           Scur[k] = (z == 0 ? 0.f : Scur[k]) + __uint_as_float(r[9 + k]);              // dz = 1 -> output plane z
           Snext[k] = __uint_as_float(r[k]);                                            // dz = 0 -> output plane z+1 (first term)
         }
+        // The last plane also publishes its own sums, into the buffer that the OTHER group may still be reading for plane z-2 (it was
+        // filled one plane ago): wait for those readers first (racecheck: write-after-read hazard without this barrier).
+        if (last) named_bar_sync(1, 256);
         if (f < NFP) {
           if (z > 0) {
             float* dst = Ps + (size_t)((z - 1) & 1) * 9 * NFP + f;
