@@ -34,7 +34,8 @@ def fresh():
 
 sl = slice(rank * B // world, (rank + 1) * B // world)
 m = fresh()
-tr = Trainer(m, gamma=2, alpha=0.75, lmbda=3e-3)
+TC = bool(os.environ.get('TRAIN_TC'))   # TRAIN_TC=1: forward, data and weight gradients on the tcgen05 kernels
+tr = Trainer(m, gamma=2, alpha=0.75, lmbda=3e-3, tensor_cores=TC)
 vals, grads = tr.forward_backward(x[sl].contiguous(), ny[sl].contiguous(), nz[sl].contiguous())
 for _ in range(2):
     tr.step(x[sl].contiguous(), ny[sl].contiguous(), nz[sl].contiguous())
@@ -44,7 +45,7 @@ dist.all_gather(gathered, flat)
 same = all(torch.equal(gathered[0], t) for t in gathered)
 if rank == 0:
     m1 = fresh()
-    t1 = Trainer(m1, gamma=2, alpha=0.75, lmbda=3e-3)
+    t1 = Trainer(m1, gamma=2, alpha=0.75, lmbda=3e-3, tensor_cores=TC)
     t1.distributed = False
     v1, g1 = t1.forward_backward(x, ny, nz)
     worst = 0.0
@@ -54,7 +55,8 @@ if rank == 0:
     eb = max(float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30)) for a, b in zip(grads['entropy_bottleneck'], g1['entropy_bottleneck']))
     print(f'world {world}: loss {vals["loss"]:.6f} vs single-process {v1["loss"]:.6f}; worst conv-gradient difference {worst:.2e}, '
           f'entropy-bottleneck gradients {eb:.2e}; replicas bit-identical after 2 steps: {same}', flush=True)
-    assert abs(vals['loss'] - v1['loss']) < 1e-5 * abs(v1['loss']) and worst < 1e-4 and eb < 1e-4 and same
+    tol = 2e-3 if TC else 1e-4   # bf16x3: the weight gradient of a slice and of the whole batch differ by its operand rounding
+    assert abs(vals['loss'] - v1['loss']) < 1e-5 * abs(v1['loss']) and worst < tol and eb < tol and same
     print('DDP CHECK OK', flush=True)
 dist.barrier()
 dist.destroy_process_group()
