@@ -210,7 +210,7 @@ size_t pccgeo_wgrad_ws_floats(int cin, int cout, int k);
 int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw, float* ws, int n, int cin, int d, int h, int wd,
                             int cout, int k, int stride, int transposed, void* stream);
 /* The same weight gradient on the tensor cores (tcgen05, bf16 or bf16x3 operands, fp32 accumulation in TMEM) for the 3x3x3 stride-1
- * layers with c channels in and out, c in {16, 32, 64}, W in {16, 32, 64} -- the backward-filter pass of the Conv3D /
+ * layers with c channels in and out, c in {16, 32, 64}, W in {16, 32, 64} (and 8 for c >= 32) -- the backward-filter pass of the Conv3D /
  * Conv3DTranspose layers that tf.train.AdamOptimizer.minimize differentiates (reference src/model_types.py:364-369).
  * xb, gb: layer input and pre-activation output gradient in the blocked bf16 layout (pccgeo_f32_to_blocked, `terms` terms).
  * pccgeo_wgrad_umma_ws_floats() returns 0 when the geometry is not supported (use pccgeo_conv3d_wgrad_f32). */

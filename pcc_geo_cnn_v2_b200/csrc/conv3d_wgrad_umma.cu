@@ -6,7 +6,8 @@
 // backward-filter contraction
 //     dW[kz,ky,kx,ci,co] = sum_{n,z,y,x} X[n,ci,z+kz-1,y+ky-1,x+kx-1] * G[n,co,z,y,x]
 // which is 85 % of the weight-gradient FLOPs of a c3p training step; the stride-2 layers reach this kernel through a phase
-// decomposition of their large tensor (training.py::_wgrad_stride2), the 8^3 / 4^3 / 2^3 volumes stay on the fp32 kernel of train.cu.
+// decomposition of their large tensor (training.py::_wgrad_stride2), W = 8 volumes with K chunks that span two rows (rk = 2 below);
+// the 4^3 / 2^3 volumes stay on the fp32 kernel of train.cu.
 //
 // Formulation.  The contraction index is the voxel, so both operands are "MN-major" for the tensor core: in the blocked bf16
 // layout (term, N, C/8, D, H, W, 8) a row of voxels is a run of 16-byte items (8 channels each), which read as K = voxel,
@@ -50,6 +51,7 @@ struct Params {
   int N, D, H, W;
   int ytiles, zsegs, nitems;
   int xs;          // X stages
+  int rk;          // y rows per K chunk (1; 2 for W = 8)
   int workers;     // CTAs per kx class
 };
 
@@ -81,9 +83,12 @@ struct Geo {
   static constexpr int NACC = MG * KXC;
   static_assert(N <= 256 && N % 16 == 0, "bad N");
   static_assert(NACC * N <= 512, "accumulators exceed TMEM");
-  __host__ __device__ static constexpr int x_term_bytes(int w) { return ((XROWS * CG * (w + 2) * 16) + 127) / 128 * 128; }
-  __host__ __device__ static constexpr int x_load_bytes(int w) { return XROWS * CG * (w + 2) * 16; }
-  __host__ __device__ static constexpr int slot_bytes(int w) { return R * CG * w * 16; }
+  // rk = y rows per K chunk: 1 (K = 16 voxels of one row), or 2 for W = 8 (K = 8 voxels of row y + 8 of row y+1; R = 1 only): a tile
+  // then covers 2 gradient rows and needs 4 input rows
+  __host__ __device__ static constexpr int x_rows(int rk) { return R * rk + 2; }
+  __host__ __device__ static constexpr int x_term_bytes(int w, int rk) { return ((x_rows(rk) * CG * (w + 2) * 16) + 127) / 128 * 128; }
+  __host__ __device__ static constexpr int x_load_bytes(int w, int rk) { return x_rows(rk) * CG * (w + 2) * 16; }
+  __host__ __device__ static constexpr int slot_bytes(int w) { return R * CG * w * 16; }   // ONE row set of a plane (per K half when rk = 2)
 };
 
 template <int C, int R, int KXC, int TERMS>
@@ -97,8 +102,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_umma_kernel(const __grid
   constexpr uint32_t TMEM_COLS = 512;
   constexpr int KXS = 3 / KXC;   // kx classes of CTAs
   const int W = p.W, PXW = W + 2;
-  const int XT = G::x_term_bytes(W), XSTAGE = TERMS * XT;
-  const int SLOT = G::slot_bytes(W), GT = S_SLOTS * SLOT;   // one precision term of the gradient ring
+  const int RK = p.rk;
+  const int XT = G::x_term_bytes(W, RK), XSTAGE = TERMS * XT;
+  const int SLOT = G::slot_bytes(W), GH = S_SLOTS * SLOT, GT = RK * GH;   // gradient ring: [term][K half][slot]
   uint8_t* xst = smem + HEADER_BYTES;
   uint8_t* gring = xst + (size_t)p.xs * XSTAGE;
   const int kxclass = (int)blockIdx.x % KXS, worker = (int)blockIdx.x / KXS;
@@ -129,26 +135,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_umma_kernel(const __grid
       for (int item = worker; item < p.nitems; item += p.workers) {
         const int zs = item % p.zsegs, col = item / p.zsegs, yt = col % p.ytiles, n = col / p.ytiles;
         const int z0 = (int)((long long)zs * p.D / p.zsegs), z1 = (int)((long long)(zs + 1) * p.D / p.zsegs);
-        const int y0 = yt * R;
+        const int y0 = yt * R * RK;
         for (int z = z0; z < z1; ++z) {
           mbar_wait(smem_u32(&hdr->empty[s]), phase ^ 1);
           const uint32_t full = smem_u32(&hdr->full[s]);
           const int pfirst = z == z0 ? z0 - 1 : z + 1, pcount = z == z0 ? 3 : 1;
           uint32_t copies = 0;
           for (int k = 0; k < pcount; ++k) copies += ((q + k) % S_RING < 2u) ? 2u : 1u;
-          mbar_expect_tx(full, (uint32_t)(TERMS * G::x_load_bytes(W)) + copies * (uint32_t)(TERMS * SLOT));
+          mbar_expect_tx(full, (uint32_t)(TERMS * G::x_load_bytes(W, RK)) + copies * (uint32_t)(TERMS * SLOT * RK));
 #pragma unroll
           for (int t = 0; t < TERMS; ++t)
             tma_load_5d(smem_u32(xst + (size_t)s * XSTAGE + (size_t)t * XT), &tmap_x, full, 0, -1, (t * p.N + n) * G::CG, y0 - 1, z);
           for (int k = 0; k < pcount; ++k, ++q) {
             const uint32_t slot = q % S_RING;
 #pragma unroll
-            for (int t = 0; t < TERMS; ++t) {
-              tma_load_5d(smem_u32(gring + (size_t)t * GT + (size_t)slot * SLOT), &tmap_g, full, 0, 0, (t * p.N + n) * G::CG, y0, pfirst + k);
-              if (slot < 2u)
-                tma_load_5d(smem_u32(gring + (size_t)t * GT + (size_t)(slot + S_RING) * SLOT), &tmap_g, full, 0, 0, (t * p.N + n) * G::CG, y0,
-                            pfirst + k);
-            }
+            for (int t = 0; t < TERMS; ++t)
+              for (int kk = 0; kk < RK; ++kk) {   // rk = 2: row y0 feeds the first K half, row y0 + 1 the second (boxes of one row each)
+                uint8_t* dst = gring + (size_t)t * GT + (size_t)kk * GH;
+                tma_load_5d(smem_u32(dst + (size_t)slot * SLOT), &tmap_g, full, 0, 0, (t * p.N + n) * G::CG, y0 + kk, pfirst + k);
+                if (slot < 2u)
+                  tma_load_5d(smem_u32(dst + (size_t)(slot + S_RING) * SLOT), &tmap_g, full, 0, 0, (t * p.N + n) * G::CG, y0 + kk, pfirst + k);
+              }
           }
           if (++s == (uint32_t)p.xs) { s = 0; phase ^= 1; }
         }
@@ -160,9 +167,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_umma_kernel(const __grid
       constexpr int NPROD = TERMS == 2 ? 3 : 1;
       // descriptor words: lo = start address / 16 | LBO (K direction: 8 voxels = 128 B) << 16; hi = SBO (next 8-channel group) | version
       const uint32_t a_hi = (uint32_t)((PXW * 16) >> 4) | (1u << 14), b_hi = (uint32_t)((W * 16) >> 4) | (1u << 14);
-      const uint32_t lo_proto = (128u >> 4) << 16;
+      // K direction (LBO): the next 8 voxels of the row (128 B), or with rk = 2 the same 8 voxels of the next row
+      const uint32_t lo_proto_a = (uint32_t)((RK == 2 ? G::CG * PXW * 16 : 128) >> 4) << 16;
+      const uint32_t lo_proto_b = (uint32_t)((RK == 2 ? GH : 128) >> 4) << 16;
       const uint32_t xst16 = smem_u32(xst) >> 4, g16 = smem_u32(gring) >> 4;
-      const int kchunks = W / 16;
+      const int kchunks = RK == 2 ? 1 : W / 16;
       const uint32_t rowgroup16 = (uint32_t)(G::JR * G::CG * PXW);   // JR rows of the X tile, in 16-byte units
       uint32_t s = 0, phase = 0, qw = 0, started = 0;
       for (int item = worker; item < p.nitems; item += p.workers) {
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_umma_kernel(const __grid
                   const int ta = pr == 2 ? 1 : 0, tb = pr == 1 ? 1 : 0;
                   const uint32_t a = a0 + (uint32_t)(ta * XT >> 4) + g * rowgroup16 + (uint32_t)(16 * c) + shift;
                   const uint32_t b = b0 + (uint32_t)(tb * GT >> 4) + (uint32_t)(16 * c);
-                  umma_bf16_lh(d, (a & 0x3FFFu) | lo_proto, a_hi, (b & 0x3FFFu) | lo_proto, b_hi, IDESC, started | (uint32_t)(c | pr));
+                  umma_bf16_lh(d, (a & 0x3FFFu) | lo_proto_a, a_hi, (b & 0x3FFFu) | lo_proto_b, b_hi, IDESC, started | (uint32_t)(c | pr));
                 }
             }
           umma_commit(smem_u32(&hdr->empty[s]));
@@ -272,7 +281,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 struct Plan {
-  int r, kxc, ctas, workers, ytiles, zsegs, nitems, xs;
+  int r, kxc, ctas, workers, ytiles, zsegs, nitems, xs, rk;
   size_t smem, partial_floats;
 };
 
@@ -280,8 +289,10 @@ template <int C, int R, int KXC>
 static bool make_plan(int n, int d, int h, int w, int terms, Plan& pl) {
   using G = Geo<C, R, KXC>;
   pl.r = R; pl.kxc = KXC;
+  pl.rk = w == 8 ? 2 : 1;
+  if (pl.rk == 2 && R != 1) return false;
   const int kxs = 3 / KXC;
-  pl.ytiles = (h + R - 1) / R;
+  pl.ytiles = (h + R * pl.rk - 1) / (R * pl.rk);
   const int cols = n * pl.ytiles;
   const int max_workers = 148 / kxs;
   // z segments: balance the persistent CTAs against the two extra gradient planes every item loads
@@ -297,7 +308,7 @@ static bool make_plan(int n, int d, int h, int w, int terms, Plan& pl) {
   pl.nitems = cols * best;
   pl.workers = pl.nitems < max_workers ? pl.nitems : max_workers;
   pl.ctas = pl.workers * kxs;
-  const size_t ring = (size_t)terms * S_SLOTS * G::slot_bytes(w), xstage = (size_t)terms * G::x_term_bytes(w);
+  const size_t ring = (size_t)terms * pl.rk * S_SLOTS * G::slot_bytes(w), xstage = (size_t)terms * G::x_term_bytes(w, pl.rk);
   const size_t room = 227 * 1024 - HEADER_BYTES - ring - 1024;   // slack: the unused M rows of the last stage read past it
   if (ring + 2 * xstage + HEADER_BYTES + 1024 > 227 * 1024) return false;
   int xs = (int)(room / xstage);
@@ -308,7 +319,7 @@ static bool make_plan(int n, int d, int h, int w, int terms, Plan& pl) {
 }
 
 static bool plan_for(int c, int n, int d, int h, int w, int terms, Plan& pl) {
-  if (n <= 0 || d <= 0 || h <= 0 || (w != 16 && w != 32 && w != 64)) return false;
+  if (n <= 0 || d <= 0 || h <= 0 || (w != 8 && w != 16 && w != 32 && w != 64)) return false;
   if (c == 16) return make_plan<16, 3, 3>(n, d, h, w, terms, pl);
   if (c == 32) return make_plan<32, 1, 3>(n, d, h, w, terms, pl);
   if (c == 64) return make_plan<64, 1, 1>(n, d, h, w, terms, pl);
@@ -325,8 +336,8 @@ static int launch(const void* xb, const void* gb, float* dw, float* ws, int n, i
   const cuuint64_t gdim[5] = {8, (cuuint64_t)w, (cuuint64_t)terms * n * G::CG, (cuuint64_t)h, (cuuint64_t)d};
   const cuuint64_t gstr[4] = {16, (cuuint64_t)d * h * w * 16, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const cuuint32_t box_x[5] = {8, (cuuint32_t)(w + 2), (cuuint32_t)G::CG, (cuuint32_t)G::XROWS, 1};
-  const cuuint32_t box_g[5] = {8, (cuuint32_t)w, (cuuint32_t)G::CG, (cuuint32_t)R, 1};
+  const cuuint32_t box_x[5] = {8, (cuuint32_t)(w + 2), (cuuint32_t)G::CG, (cuuint32_t)G::x_rows(pl.rk), 1};
+  const cuuint32_t box_g[5] = {8, (cuuint32_t)w, (cuuint32_t)G::CG, (cuuint32_t)R, 1};   // rk = 2: one box per K half (row)
   CUtensorMap tx, tg;
   CUresult cr = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(xb), gdim, gstr, box_x, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -336,7 +347,7 @@ static int launch(const void* xb, const void* gb, float* dw, float* ws, int n, i
   PCCGEO_REQUIRE(cr == CUDA_SUCCESS, "conv3d_wgrad_umma: cuTensorMapEncodeTiled (g) failed (%d)", (int)cr);
   Params p{};
   p.partial = ws; p.N = n; p.D = d; p.H = h; p.W = w;
-  p.ytiles = pl.ytiles; p.zsegs = pl.zsegs; p.nitems = pl.nitems; p.xs = pl.xs; p.workers = pl.workers;
+  p.ytiles = pl.ytiles; p.zsegs = pl.zsegs; p.nitems = pl.nitems; p.xs = pl.xs; p.workers = pl.workers; p.rk = pl.rk;
   auto run = [&](auto kern) -> int {
     PCCGEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kern<<<pl.ctas, NUM_THREADS, pl.smem + 1024, st>>>(tx, tg, p);
@@ -367,7 +378,7 @@ extern "C" int pccgeo_conv3d_wgrad_umma(const void* xb, const void* gb, float* d
   PCCGEO_REQUIRE(terms == 1 || terms == 2, "conv3d_wgrad_umma: terms must be 1 or 2");
   wg::Plan pl;
   PCCGEO_REQUIRE(wg::plan_for(c, n, d, h, wd, terms, pl),
-                 "conv3d_wgrad_umma: needs C in {16, 32, 64} (in == out) and W in {16, 32, 64} (got C=%d, %dx%dx%d)", c, d, h, wd);
+                 "conv3d_wgrad_umma: needs C in {16, 32, 64} (in == out) and W in {16, 32, 64} (8 for C >= 32) (got C=%d, %dx%dx%d)", c, d, h, wd);
   cudaStream_t st = (cudaStream_t)stream;
   if (c == 16) return wg::launch<16, 3, 3>(xb, gb, dw, ws, n, d, h, wd, transposed, terms, pl, st);
   if (c == 32) return wg::launch<32, 1, 3>(xb, gb, dw, ws, n, d, h, wd, transposed, terms, pl, st);

@@ -27,7 +27,8 @@ def _umma(xd, gd, transposed, terms):
     return ops.conv3d_wgrad_umma(xb, gb, tuple(xd.shape), transposed, terms)
 
 
-@pytest.mark.parametrize('c,shape,n', [(16, (16, 16, 16), 2), (16, (5, 7, 16), 3), (32, (6, 16, 16), 2), (64, (4, 5, 16), 2), (16, (3, 4, 32), 1)])
+@pytest.mark.parametrize('c,shape,n', [(16, (16, 16, 16), 2), (16, (5, 7, 16), 3), (32, (6, 16, 16), 2), (64, (4, 5, 16), 2), (16, (3, 4, 32), 1),
+                                       (64, (4, 5, 8), 2), (32, (3, 8, 8), 3), (64, (8, 8, 8), 2)])   # W = 8: K chunks span two rows
 @pytest.mark.parametrize('transposed', [False, True])
 def test_wgrad_umma_matches_float64_autograd(c, shape, n, transposed):
     rng = np.random.default_rng(c + 7 * int(transposed) + shape[0])
@@ -44,7 +45,7 @@ def test_wgrad_umma_matches_float64_autograd(c, shape, n, transposed):
     assert _rel(got1, want) < 2e-2, _rel(got1, want)
 
 
-@pytest.mark.parametrize('c,s,n', [(16, 64, 32), (16, 32, 32), (32, 32, 32), (32, 16, 32), (64, 16, 32), (16, 64, 5)])
+@pytest.mark.parametrize('c,s,n', [(16, 64, 32), (16, 32, 32), (32, 32, 32), (32, 16, 32), (64, 16, 32), (16, 64, 5), (64, 8, 32)])
 def test_wgrad_umma_matches_fp32_kernel_at_training_sizes(c, s, n):
     g = torch.Generator(device='cuda').manual_seed(c * 100 + s)
     xd = torch.relu(torch.randn((n, c, s, s, s), device='cuda', generator=g))        # post-ReLU activations: non-negative, sparse
@@ -56,7 +57,8 @@ def test_wgrad_umma_matches_fp32_kernel_at_training_sizes(c, s, n):
     assert np.array_equal(got, again)            # deterministic: fixed reduction order
 
 
-@pytest.mark.parametrize('transposed,cin,cout,s_small,n', [(True, 32, 16, 16, 3), (False, 16, 32, 16, 2), (True, 64, 32, 16, 2), (True, 32, 16, 32, 32)])
+@pytest.mark.parametrize('transposed,cin,cout,s_small,n', [(True, 32, 16, 16, 3), (False, 16, 32, 16, 2), (True, 64, 32, 16, 2), (True, 32, 16, 32, 32),
+                                                           (False, 32, 64, 8, 2), (True, 64, 64, 8, 3)])
 def test_stride2_layers_by_phase_decomposition(transposed, cin, cout, s_small, n):
     """the trainer's stride-2 weight gradient (eight phase volumes of the large tensor as channels -> stride-1 tcgen05 launches) against
     the fp32 kernel, which test_gpu_train.py pins to float64 autograd"""
@@ -77,8 +79,9 @@ def test_stride2_layers_by_phase_decomposition(transposed, cin, cout, s_small, n
 def test_wgrad_umma_rejects_unsupported_geometry():
     assert not ops.wgrad_umma_eligible(2, 16, 32, 3, 1, 16, 16, 16)
     assert not ops.wgrad_umma_eligible(2, 16, 16, 3, 2, 16, 16, 16)
-    assert not ops.wgrad_umma_eligible(2, 64, 64, 3, 1, 8, 8, 8)
+    assert not ops.wgrad_umma_eligible(2, 16, 16, 3, 1, 8, 8, 8)
+    assert not ops.wgrad_umma_eligible(2, 64, 64, 3, 1, 4, 4, 4)
     assert not ops.wgrad_umma_eligible(2, 8, 8, 3, 1, 16, 16, 16)
     with pytest.raises(ValueError):
         ops.conv3d_wgrad_umma(torch.zeros(8, device='cuda', dtype=torch.bfloat16), torch.zeros(8, device='cuda', dtype=torch.bfloat16),
-                              (1, 64, 8, 8, 8), False, 2)
+                              (1, 64, 4, 4, 4), False, 2)
