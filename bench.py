@@ -578,8 +578,17 @@ def train_step(P, args, peak_tf):
         del m, x
         torch.cuda.empty_cache()
     best = min(out, key=lambda k: out[k]['ms_per_step'])
+    wg = None
+    try:   # committed ncu summary of the tcgen05 weight-gradient kernel (one launch, 16 -> 16 @ 64^3, batch 32)
+        with open(os.path.join(ROOT, 'profiles', 'r02_ncu_wgrad16.json')) as f:
+            d = json.load(f)
+        wg = {'kernel': 'wgrad_umma_kernel<16,3,3,2>', 'tensor_pipe_active_pct_ncu': d.get('tensor_pipe_active_pct'),
+              'dram_bytes_per_launch_ncu': (d.get('dram_bytes_read') or 0) + (d.get('dram_bytes_write') or 0),
+              'source': 'profiles/r02_ncu_wgrad16.json (static, not from this run)'}
+    except Exception:
+        pass
     return {'ms_per_step': out[best]['ms_per_step'], 'mode': best, 'batch': B, 'config': 'c3p, 64^3, gamma 2, alpha 0.75, lambda 1e-4',
-            'gflop_per_step_algorithmic': GFLOP_TRAIN * B, 'modes': out,
+            'gflop_per_step_algorithmic': GFLOP_TRAIN * B, 'modes': out, 'weight_gradient_kernel': wg,
             'what': 'forward + backward (data and weight gradients, all convs on tcgen05 in tensor_cores mode) + 2 Adam steps, CUDA events around 3 steps'}
 
 
