@@ -298,3 +298,32 @@ def test_debug_contract_of_decompress_octree(config, size, bias):
         np.testing.assert_equal(dec[j], meta[0]['x_hat_list'][j])
         # the debug x_hat is the tensor the points come from
         assert np.array_equal(np.argwhere(np.clip(dd['x_hat'][0, 0], 0, 1) > m.thresholds[128]).astype(np.float32), dec[j])
+
+
+@pytest.mark.parametrize('config,device_coder', [('c3p', False), ('c3p', True), ('c1', False)])
+def test_block_loops_do_not_depend_on_the_stream_schedule(config, device_coder, monkeypatch):
+    """The block loops run their stage graphs on two compute streams and their copies on dedicated copy streams, with batches
+    alternating between two sets of static buffers.  The bytes and the points must be what the
+    single-stream schedule (PCCGEO_SIDE_COPIES=0) produces, over many ragged batches, on a fresh model each time (first-use
+    captures and buffer allocations are part of what is being checked), and twice in a row on the same model."""
+    size = 32
+    blocks = synthetic.surface_blocks(45, size=size, seed=21) + [np.array([[1, 2, 3]], np.float32)]
+    results = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('PCCGEO_SIDE_COPIES', mode)
+        m = _model(config, 5, output_bias={'c3p': -0.7, 'c1': 0.4}[config])
+        m.batch_size = 8                       # 46 blocks -> 5 full batches + one of 6
+        m.device_coder = device_coder
+        m.compress((1, 1, size, size, size))
+        m.decompress()
+        runs = []
+        for _ in range(2):
+            data_list, metadata, _ = m.compress_blocks(None, blocks, None, None, size, 0, fixed_threshold=True)
+            dec, _ = m.decompress_blocks(None, data_list[0], (size, size, size))
+            runs.append(([s for s, _ in data_list[0]], metadata[0]['x_hat_list'], dec))
+        assert runs[0][0] == runs[1][0]
+        assert all(np.array_equal(a, b) for a, b in zip(runs[0][2], runs[1][2]))
+        results[mode] = runs[0]
+    assert results['0'][0] == results['1'][0]                                             # strings
+    for enc0, enc1, dec0, dec1 in zip(results['0'][1], results['1'][1], results['0'][2], results['1'][2]):
+        assert np.array_equal(enc0, enc1) and np.array_equal(dec0, dec1) and np.array_equal(enc1, dec1)
