@@ -66,6 +66,11 @@ int pccgeo_conv3d_f32(const float* x, const float* w, const float* bias, const f
 
 /* fp32 (N,C,D,H,W) -> blocked bf16 (terms, N, Cp/8, D, H, W, 8), Cp = round_up(C,16), zero padded */
 int pccgeo_f32_to_blocked(const float* x, void* xb, int n, int c, int d, int h, int wd, int terms, void* stream);
+/* The eight stride-2 phase volumes x[.., 2b + p] of x (N, Cb, 2d, 2h, 2wd) stacked as channels, cut into 8*Cb/C chunks of C channels and
+ * written in the blocked layout, chunk after chunk (each chunk = one pccgeo_f32_to_blocked image of shape (N, C, d, h, wd)): what the
+ * stride-2 layers' weight gradient feeds to pccgeo_conv3d_wgrad_umma (reference src/model_types.py:364-369, the stride-2 Conv3D /
+ * Conv3DTranspose kernels of AnalysisBlock / SynthesisBlock, src/model_transforms.py:62-81). */
+int pccgeo_f32_phases_to_blocked(const float* x, void* xb, int n, int cb, int c, int d, int h, int wd, int terms, void* stream);
 /* blocked bf16 -> fp32 (N,C,D,H,W) (sums the terms) */
 int pccgeo_blocked_to_f32(const void* xb, float* x, int n, int c, int d, int h, int wd, int terms, void* stream);
 

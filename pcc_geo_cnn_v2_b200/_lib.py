@@ -21,6 +21,7 @@ SIGNATURES = {
     'pccgeo_set_option': (i32, [C.c_char_p, i64]),
     'pccgeo_conv3d_f32': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_f32_to_blocked': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_f32_phases_to_blocked': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_blocked_to_f32': (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_umma_pack_weights_host': (i64, [vp, vp, i32, i32, i32, i32, i32]),
     'pccgeo_conv3d_umma': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),

@@ -401,6 +401,43 @@ __global__ void f32_to_blocked_kernel(const float* __restrict__ x, __nv_bfloat16
   }
 }
 
+// Phase split + layout conversion in one pass (the stride-2 layers' weight gradient, training.py::_wgrad_stride2): the eight phase
+// volumes L_p[b] = L[2b + p] of x (N, Cb, 2S, 2S, 2S) stacked as channels and cut into chunks of C channels (C a multiple of Cb,
+// 8*Cb a multiple of C): out[chunk][term][n][C/8][S][S][S][8], channel c of chunk j = phase j*(C/Cb) + c / Cb, source channel c % Cb.
+__global__ void f32_phases_to_blocked_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, int N, int Cb, int C, int S0, int S1,
+                                             int S2, int nch, int terms) {
+  const int CG = C / 8, ppc = C / Cb;
+  const long long V = (long long)S0 * S1 * S2, total = (long long)nch * N * CG * V;
+  const long long term_stride = (long long)N * CG * V * 8, chunk_stride = term_stride * terms;
+  const long long LV = 8 * V, L2 = 2LL * S2, L12 = 4LL * S1 * S2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long vox = i % V;
+    const int cg = (int)((i / V) % CG);
+    const int n = (int)((i / (V * CG)) % N);
+    const int j = (int)(i / (V * CG * N));
+    const int xx = (int)(vox % S2), yy = (int)((vox / S2) % S1), zz = (int)(vox / ((long long)S1 * S2));
+    const int c0 = cg * 8, phase = j * ppc + c0 / Cb, cb0 = c0 % Cb;   // the 8 channels of a group share their phase (Cb >= 8)
+    const int pz = phase >> 2, py = (phase >> 1) & 1, px = phase & 1;
+    const float* src = x + ((long long)n * Cb + cb0) * LV + (2 * zz + pz) * L12 + (2 * yy + py) * L2 + (2 * xx + px);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(src + k * LV);
+    int4 qh, ql;
+    uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
+    uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+      __nv_bfloat162 t2 = __halves2bfloat162(h0, h1);
+      qh32[k] = *reinterpret_cast<uint32_t*>(&t2);
+      ql32[k] = pack_bf16x2(v[2 * k] - __bfloat162float(h0), v[2 * k + 1] - __bfloat162float(h1));
+    }
+    __nv_bfloat16* dst = xb + j * chunk_stride + (((long long)n * CG + cg) * V + vox) * 8;
+    *reinterpret_cast<int4*>(dst) = qh;
+    if (terms == 2) *reinterpret_cast<int4*>(dst + term_stride) = ql;
+  }
+}
+
 __global__ void blocked_to_f32_kernel(const __nv_bfloat16* __restrict__ xb, float* __restrict__ x, int N, int C, int CG,
                                       long long DHW, int terms) {
   const long long total = (long long)N * CG * DHW;
@@ -490,6 +527,18 @@ extern "C" int pccgeo_f32_to_blocked(const float* x, void* xb, int n, int c, int
   if (b > 148 * 16) b = 148 * 16;
   f32_to_blocked_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xb, n, c, CG, DHW, terms);
   return check_launch("f32_to_blocked_kernel");
+}
+
+extern "C" int pccgeo_f32_phases_to_blocked(const float* x, void* xb, int n, int cb, int c, int d, int h, int wd, int terms, void* stream) {
+  PCCGEO_REQUIRE(x && xb && n > 0 && cb >= 8 && cb % 8 == 0 && c > 0 && c % 16 == 0 && c % cb == 0 && (8 * cb) % c == 0 && d > 0 && h > 0 && wd > 0 &&
+                     (terms == 1 || terms == 2),
+                 "f32_phases_to_blocked: bad argument (Cb a multiple of 8, C a multiple of 16 and of Cb that divides 8 * Cb)");
+  const int nch = 8 * cb / c;
+  const long long total = (long long)nch * n * (c / 8) * d * h * wd;
+  long long b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  f32_phases_to_blocked_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xb, n, cb, c, d, h, wd, nch, terms);
+  return check_launch("f32_phases_to_blocked_kernel");
 }
 
 extern "C" int pccgeo_blocked_to_f32(const void* xb, float* x, int n, int c, int d, int h, int wd, int terms, void* stream) {

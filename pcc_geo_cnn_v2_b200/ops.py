@@ -64,6 +64,20 @@ def f32_to_blocked(x, terms, out=None):
     return out
 
 
+def f32_phases_to_blocked(x, c, terms):
+    """x fp32 (N, Cb, 2d, 2h, 2w) -> [blocked bf16 image of shape (N, c, d, h, w)] * (8*Cb/c): the eight stride-2 phase volumes of x as
+    channels (phase-major, then source channel), cut into chunks of c channels.  One pass, no intermediate copies."""
+    L.require_cuda()
+    _f32c(x)
+    n, cb, d2, h2, w2 = x.shape
+    d, h, w = d2 // 2, h2 // 2, w2 // 2
+    nch = 8 * cb // c
+    per = blocked_numel(n, c, d, h, w, terms)
+    out = torch.empty(nch * per, device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().pccgeo_f32_phases_to_blocked(L.ptr(x), L.ptr(out), n, cb, c, d, h, w, terms, L.stream_ptr()), 'f32_phases_to_blocked')
+    return [out[j * per:(j + 1) * per] for j in range(nch)]
+
+
 def blocked_to_f32(xb, shape, terms, out=None):
     L.require_cuda()
     n, c, d, h, w = shape

@@ -199,11 +199,12 @@ class Trainer:
             return None
         if not ops.wgrad_umma_eligible(n, c, c, 3, 1, sd, sh, sw, terms):
             return None
+        if cb % 8 or c % 16:
+            return None
         ppc, nch = c // cb, 8 * cb // c          # phases per chunk, chunks
-        ph = large.contiguous().view(n, cb, sd, 2, sh, 2, sw, 2).permute(3, 5, 7, 0, 1, 2, 4, 6).reshape(nch, ppc, n, cb, sd, sh, sw)
-        ph = ph.permute(0, 2, 1, 3, 4, 5, 6).reshape(nch, n, c, sd, sh, sw).contiguous()
+        phb = ops.f32_phases_to_blocked(large.contiguous(), c, terms)     # phase split + blocked layout in one pass
         sb = ops.f32_to_blocked(small, terms)
-        outs = [ops.conv3d_wgrad_umma(ops.f32_to_blocked(ph[j], terms), sb, (n, c, sd, sh, sw), False, terms) for j in range(nch)]
+        outs = [ops.conv3d_wgrad_umma(phb[j], sb, (n, c, sd, sh, sw), False, terms) for j in range(nch)]
         dw = torch.empty((27, x_in.shape[1], layer.filters), device=x_in.device, dtype=torch.float32)
         for t in range(27):
             tz, ty, tx = t // 9, (t // 3) % 3, t % 3
