@@ -356,14 +356,15 @@ class CompressionModel:
         self.use_graphs = True   # capture the per-batch kernel sequences of the block loops into CUDA graphs
         # entropy-code on the GPU (csrc/rc_device.cu: one warp per stream, all streams of up to `coder_group_blocks` blocks in
         # one launch) instead of in the host workers; byte-identical strings.  Used by the CUDA-graph block loops.
-        # Default: on when this rank has fewer than 16 host cores (several GPUs per host).  Measured on the rate-realistic
-        # workload (round 2, blocks/s end to end, host / device coder): 16 cores 6.73 k / 6.70 k, 12 cores (2 ranks) 6.4 k / 6.2 k
-        # per GPU, 8 cores 5.4 k / 6.8 k, 4 cores 4.6 k / 6.8 k -- the device coder does not depend on the host at all.
+        # Default: on when this rank has at most 8 host cores (several GPUs per host).  Measured on the rate-realistic
+        # workload at the end of round 2 (blocks/s end to end, host / device coder, `taskset` on one box): 16 cores 7.6 k / 7.2 k,
+        # 12 cores 7.4 k / 7.0 k, 8 cores 7.0 k / 7.1 k; 8 ranks x 4 cores 33.9 k / 52.0 k in total -- the device coder does not
+        # depend on the host at all, the host coder is free as long as cores are idle.
         # PCCGEO_DEVICE_CODER=0/1 overrides.  A group's coding costs a fixed few milliseconds (the length
         # of one stream's serial chain), so groups are large; `coder_overlap` moves it to a side stream under the next
         # group's transforms (off: its one-warp CTAs displace the persistent conv CTAs and cost more than they hide).
         env = os.environ.get('PCCGEO_DEVICE_CODER', '')
-        self.device_coder = env == '1' if env in ('0', '1') else cores < 16
+        self.device_coder = env == '1' if env in ('0', '1') else cores <= 8
         self.coder_group_blocks = 1024
         self.coder_overlap = False
         self.symbol_bytes = self.index_bytes = 4   # width of the symbols / scale indexes that cross PCIe with the host coder
