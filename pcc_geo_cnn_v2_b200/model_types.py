@@ -369,6 +369,7 @@ class CompressionModel:
         self.coder_overlap = False
         self.symbol_bytes = self.index_bytes = 4   # width of the symbols / scale indexes that cross PCIe with the host coder
         self._graphs, self._statics, self._graph_epoch = {}, {}, -1
+        self._pipe_evs = {}   # events of the decode pipeline's lanes (reset by every decompress_blocks call)
 
     # -- weights -------------------------------------------------------------------------------------
     def transforms(self):
