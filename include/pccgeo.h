@@ -222,6 +222,13 @@ int pccgeo_conv3d_wgrad_f32(const float* x, const float* g, float* dw, float* ws
 long long pccgeo_wgrad_umma_ws_floats(int c, int n, int d, int h, int wd, int terms);
 int pccgeo_conv3d_wgrad_umma(const void* xb, const void* gb, float* dw, float* ws, int n, int c, int d, int h, int wd,
                              int transposed, int terms, void* stream);
+/* The elementwise steps of the backward pass on the blocked bf16 layout (pccgeo_f32_to_blocked; `groups` = N * ceil16(C)/8 * voxels
+ * 16-byte items per term): ReLU mask from the activation's hi term (tf.nn.relu's gradient), residual add (ResidualLayer 'add',
+ * reference src/model_transforms.py:35-36), bias gradient (BiasAdd; ws: pccgeo_bias_grad_blocked_ws_doubles(c) doubles). */
+size_t pccgeo_bias_grad_blocked_ws_doubles(int c);
+int pccgeo_relu_mask_blocked(const void* gb, const void* yb, void* out, long long groups, int terms, void* stream);
+int pccgeo_add_blocked(const void* a, const void* b, void* out, long long groups, int terms, void* stream);
+int pccgeo_bias_grad_blocked(const void* gb, float* db, double* ws, int n, int c, long long spatial, int terms, void* stream);
 /* db[c] = sum over batch and voxels of g; ws: pccgeo_reduce_ws_doubles() doubles */
 int pccgeo_bias_grad_f32(const float* g, float* db, double* ws, int n, int c, long long spatial, void* stream);
 /* tf.train.AdamOptimizer step t (1-based): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps) */

@@ -56,6 +56,10 @@ SIGNATURES = {
     'pccgeo_conv3d_wgrad_f32': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     'pccgeo_wgrad_umma_ws_floats': (i64, [i32, i32, i32, i32, i32, i32]),
     'pccgeo_conv3d_wgrad_umma': (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    'pccgeo_relu_mask_blocked': (i32, [vp, vp, vp, i64, i32, vp]),
+    'pccgeo_add_blocked': (i32, [vp, vp, vp, i64, i32, vp]),
+    'pccgeo_bias_grad_blocked_ws_doubles': (C.c_size_t, [i32]),
+    'pccgeo_bias_grad_blocked': (i32, [vp, vp, vp, i32, i32, i64, i32, vp]),
     'pccgeo_bias_grad_f32': (i32, [vp, vp, vp, i32, i32, i64, vp]),
     'pccgeo_adam_step': (i32, [vp, vp, vp, vp, f32, f32, f32, f32, i64, i64, vp]),
     'pccgeo_range_encode_host': (i32, [vp, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, vp, i64, vp, i32]),

@@ -18,6 +18,78 @@ __global__ void axpby_kernel(const float* __restrict__ a, const float* __restric
     out[i] = alpha * a[i] + (b ? beta * b[i] : 0.f);
 }
 
+// ---- the same elementwise steps on the blocked bf16 hi/lo layout (term, N, C/8, voxels, 8): the tensor-core training path keeps the
+// gradients in that layout between the layers of the backward pass (every conv kernel reads and writes it), so the ReLU mask, the
+// residual adds and the bias gradients work on it directly instead of through a blocked -> fp32 -> blocked round trip per layer.
+// `groups` = N * C/8 * voxels 16-byte items per term.
+__device__ __forceinline__ uint32_t bf16x2_positive_mask(uint32_t w) {   // 0xffff per 16-bit lane that holds a value > 0
+  const uint32_t lo = w & 0xffffu, hi = w >> 16;
+  const uint32_t ml = ((lo & 0x8000u) == 0 && (lo & 0x7fffu) != 0) ? 0xffffu : 0u;
+  const uint32_t mh = ((hi & 0x8000u) == 0 && (hi & 0x7fffu) != 0) ? 0xffff0000u : 0u;
+  return ml | mh;
+}
+__global__ void relu_mask_blocked_kernel(const int4* __restrict__ g, const int4* __restrict__ y, int4* __restrict__ out, long long groups,
+                                         int terms) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (long long)gridDim.x * blockDim.x) {
+    const int4 yq = __ldg(y + i);   // the hi term of the activation decides: bf16_rn(v) > 0  <=>  v > 0
+    const uint32_t m0 = bf16x2_positive_mask((uint32_t)yq.x), m1 = bf16x2_positive_mask((uint32_t)yq.y),
+                   m2 = bf16x2_positive_mask((uint32_t)yq.z), m3 = bf16x2_positive_mask((uint32_t)yq.w);
+    for (int t = 0; t < terms; ++t) {
+      int4 q = __ldg(g + t * groups + i);
+      q.x &= (int)m0; q.y &= (int)m1; q.z &= (int)m2; q.w &= (int)m3;
+      out[t * groups + i] = q;
+    }
+  }
+}
+__device__ __forceinline__ void bf16x8_accumulate(const int4& q, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] += f.x;
+    v[2 * k + 1] += f.y;
+  }
+}
+__global__ void add_blocked_kernel(const int4* __restrict__ a, const int4* __restrict__ b, int4* __restrict__ out, long long groups, int terms) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < groups; i += (long long)gridDim.x * blockDim.x) {
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < terms; ++t) {
+      bf16x8_accumulate(__ldg(a + t * groups + i), v);
+      bf16x8_accumulate(__ldg(b + t * groups + i), v);
+    }
+    int4 qh, ql;
+    uint32_t* qh32 = reinterpret_cast<uint32_t*>(&qh);
+    uint32_t* ql32 = reinterpret_cast<uint32_t*>(&ql);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * k]), h1 = __float2bfloat16_rn(v[2 * k + 1]);
+      __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+      qh32[k] = *reinterpret_cast<uint32_t*>(&hh);
+      __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * k] - __bfloat162float(h0), v[2 * k + 1] - __bfloat162float(h1));
+      ql32[k] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    out[i] = qh;
+    if (terms == 2) out[groups + i] = ql;
+  }
+}
+// db[c] = sum over blocks and voxels of (hi + lo); grid (chunks, C/8) -> partials[c * chunks + chunk] (bias_grad_finish_kernel adds them)
+__global__ void bias_grad_blocked_kernel(const int4* __restrict__ g, double* __restrict__ partials, int N, int CG, long long V, int terms) {
+  __shared__ double sm[32];
+  const int cg = blockIdx.y;
+  const long long groups = (long long)N * CG * V;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int n = 0; n < N; ++n) {
+    const int4* row = g + ((long long)n * CG + cg) * V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x)
+      for (int t = 0; t < terms; ++t) bf16x8_accumulate(__ldg(row + t * groups + i), acc);
+  }
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const double r = block_sum((double)acc[k], sm);
+    if (threadIdx.x == 0) partials[(long long)(cg * 8 + k) * gridDim.x + blockIdx.x] = r;
+  }
+}
+
 // d focal_loss / d y_pred (src/utils/focal_loss.py:5-12); K.clip passes gradient on [1e-3, .999] only; tf.where routes it
 // through the selected branch only.  scale multiplies the result (lambda).
 __global__ void focal_bwd_kernel(const float* __restrict__ xt, const float* __restrict__ xp, float gamma, float alpha, float scale,
@@ -521,6 +593,36 @@ extern "C" int pccgeo_axpby(const float* a, const float* b, float alpha, float b
   PCCGEO_REQUIRE(a && out && n > 0, "axpby: bad argument");
   axpby_kernel<<<grid1d(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(a, b, alpha, beta, out, n);
   return check_launch("axpby_kernel");
+}
+
+extern "C" int pccgeo_relu_mask_blocked(const void* gb, const void* yb, void* out, long long groups, int terms, void* stream) {
+  PCCGEO_REQUIRE(gb && yb && out && groups > 0 && (terms == 1 || terms == 2), "relu_mask_blocked: bad argument");
+  relu_mask_blocked_kernel<<<grid1d(groups, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>((const int4*)gb, (const int4*)yb, (int4*)out, groups, terms);
+  return check_launch("relu_mask_blocked_kernel");
+}
+
+extern "C" int pccgeo_add_blocked(const void* a, const void* b, void* out, long long groups, int terms, void* stream) {
+  PCCGEO_REQUIRE(a && b && out && groups > 0 && (terms == 1 || terms == 2), "add_blocked: bad argument");
+  add_blocked_kernel<<<grid1d(groups, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>((const int4*)a, (const int4*)b, (int4*)out, groups, terms);
+  return check_launch("add_blocked_kernel");
+}
+
+constexpr int kBiasBlockedChunks = 148 * 8;
+extern "C" size_t pccgeo_bias_grad_blocked_ws_doubles(int c) { return (size_t)((c + 15) / 16) * 16 * kBiasBlockedChunks; }
+
+extern "C" int pccgeo_bias_grad_blocked(const void* gb, float* db, double* ws, int n, int c, long long spatial, int terms, void* stream) {
+  PCCGEO_REQUIRE(gb && db && ws && n > 0 && c > 0 && spatial > 0 && (terms == 1 || terms == 2), "bias_grad_blocked: bad argument");
+  const int cg = ((c + 15) / 16) * 2;   // the blocked layout pads the channels to a multiple of 16
+  int chunks = kBiasBlockedChunks / cg;   // ~ 8 CTAs per SM in total
+  const long long want = (spatial + 255) / 256;
+  if (chunks > want) chunks = (int)want;
+  if (chunks < 1) chunks = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  bias_grad_blocked_kernel<<<dim3(chunks, cg), 256, 0, st>>>((const int4*)gb, ws, n, cg, spatial, terms);
+  int rc = check_launch("bias_grad_blocked_kernel");
+  if (rc) return rc;
+  bias_grad_finish_kernel<<<1, c, 0, st>>>(ws, chunks, db);
+  return check_launch("bias_grad_finish_kernel");
 }
 
 extern "C" int pccgeo_focal_loss_bwd(const float* x_true, const float* x_pred, float gamma, float alpha, float scale, float* dx_pred,

@@ -476,7 +476,7 @@ class _Val:
         return self.blk
 
 
-def run_steps(steps, out_id, x, pack=None, keep=None, extra=None, keep_vals=None):
+def run_steps(steps, out_id, x, pack=None, keep=None, extra=None, keep_vals=None, return_val=False):
     """Execute traced steps on a channels_first fp32 CUDA tensor.  pack = {'thresholds', 'want_f32'}: also return the
     packed thresholded occupancy of the (single-channel) output -> (y or None, bits, counts).  keep: dict that receives every
     value (id -> fp32 tensor; the training path saves activations this way; keep_vals: the same ids -> _Val with the blocked form
@@ -485,7 +485,7 @@ def run_steps(steps, out_id, x, pack=None, keep=None, extra=None, keep_vals=None
     terms = {'bf16x3': 2, 'bf16': 1, 'fp32': 0}[mode]
     vals = {0: x if isinstance(x, _Val) else _Val(f32=x, shape=tuple(x.shape))}   # a _Val input brings its blocked form along
     for vid, t in (extra or {}).items():
-        vals[vid] = _Val(f32=t, shape=tuple(t.shape))
+        vals[vid] = t if isinstance(t, _Val) else _Val(f32=t, shape=tuple(t.shape))
     last_use = {}
     for i, s in enumerate(steps):
         for vid in ((s[2], s[4]) if s[0] == 'conv' else (s[1], s[2])):
@@ -551,6 +551,8 @@ def run_steps(steps, out_id, x, pack=None, keep=None, extra=None, keep_vals=None
             continue
         for vid in [k for k, li in last_use.items() if li == i and k != out_id]:
             vals.pop(vid, None)
+    if return_val:          # the value in whatever representation the last kernel produced (the training path's backward chain)
+        return vals[out_id]
     y = vals[out_id].as_f32()
     if pack:
         bits, counts = ops.threshold_pack(y, pack['thresholds'])
@@ -586,10 +588,11 @@ def layer_runner(layer, xb, in_shape, terms, residual_b=None):
     raise ValueError('layer is not served by a tensor-core kernel')
 
 
-def run_layer(layer, x, residual=None):
-    """One conv layer (fp32 in / fp32 out) through the same kernel dispatch as a transform; residual is added in the epilogue."""
+def run_layer(layer, x, residual=None, return_val=False):
+    """One conv layer (fp32 or _Val in / fp32 out, or a _Val with return_val) through the same kernel dispatch as a transform; residual
+    is added in the epilogue."""
     steps = [('conv', layer, 0, 1, 2 if residual is not None else None)]
-    return run_steps(steps, 1, x, extra={2: residual} if residual is not None else None)
+    return run_steps(steps, 1, x, extra={2: residual} if residual is not None else None, return_val=return_val)
 
 
 def _run_transform(layer, tensor, data_format, pack=None):

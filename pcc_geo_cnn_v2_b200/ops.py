@@ -463,6 +463,32 @@ def bias_grad_f32(g):
     return db
 
 
+def _groups(shape):
+    n, c, d, h, w = shape
+    return n * (round_up(c, 16) // 8) * d * h * w
+
+
+def relu_mask_blocked(gb, yb, shape, terms):
+    """blocked gradient gb masked by the blocked activation yb (> 0), out of place; shape = logical (N, C, D, H, W) of both"""
+    out = torch.empty_like(gb)
+    L.check(L.lib().pccgeo_relu_mask_blocked(L.ptr(gb), L.ptr(yb), L.ptr(out), _groups(shape), terms, L.stream_ptr()), 'relu_mask_blocked')
+    return out
+
+
+def add_blocked(ab, bb, shape, terms):
+    out = torch.empty_like(ab)
+    L.check(L.lib().pccgeo_add_blocked(L.ptr(ab), L.ptr(bb), L.ptr(out), _groups(shape), terms, L.stream_ptr()), 'add_blocked')
+    return out
+
+
+def bias_grad_blocked(gb, shape, terms):
+    n, c, d, h, w = shape
+    db = torch.empty(c, device=gb.device, dtype=torch.float32)
+    ws = torch.empty(int(L.lib().pccgeo_bias_grad_blocked_ws_doubles(c)), device=gb.device, dtype=torch.float64)
+    L.check(L.lib().pccgeo_bias_grad_blocked(L.ptr(gb), L.ptr(db), L.ptr(ws), n, c, d * h * w, terms, L.stream_ptr()), 'bias_grad_blocked')
+    return db
+
+
 def adam_step(theta, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
     L.check(L.lib().pccgeo_adam_step(L.ptr(theta), L.ptr(grad), L.ptr(m), L.ptr(v), float(lr), float(beta1), float(beta2), float(eps),
                                      int(step), theta.numel(), L.stream_ptr()), 'adam_step')

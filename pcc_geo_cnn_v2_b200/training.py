@@ -166,44 +166,48 @@ class Trainer:
                 raise NotImplementedError("residual_mode='concat' is not used by any reference config; training supports 'add'")
         return vals[out_id], (steps, out_id, vals, {})
 
-    def _wgrad(self, layer, x_in, gd, x_val=None, g_val=None):
-        """Weight gradient, tap-major (k^3, Cin, Cout).  Tensor-core mode: the stride-1 3x3x3 layers with 16 / 32 / 64 channels (85 % of
-        the weight-gradient FLOPs of c3p) run on the tcgen05 kernel in the active precision (bf16x3 by default); the rest -- stride-2
-        layers, the one-channel ends, the 8^3 and smaller volumes -- on the fp32 kernel."""
+    def _wgrad(self, layer, x_in, g_val, x_val=None):
+        """Weight gradient, tap-major (k^3, Cin, Cout).  g_val: the gradient w.r.t. the layer's pre-activation output as a _Val (fp32 and
+        / or blocked); x_val: the forward pass' input activation as a _Val when it exists in the blocked layout.  Tensor-core mode: the
+        3x3x3 layers with 16 / 32 / 64 channels run on the tcgen05 kernel in the active precision (bf16x3 by default) -- stride 1
+        directly, stride 2 by phase decomposition; the one-channel ends and the 4^3-and-smaller volumes on the fp32 kernels."""
         n, cin, d, h, w = x_in.shape
         if self.tensor_cores:
             terms = {'bf16x3': 2, 'bf16': 1, 'fp32': 0}[MT.get_precision()]
             if terms and ops.wgrad_umma_eligible(n, cin, layer.filters, layer.k, layer.stride, d, h, w, terms):
-                # x_val / g_val: the forward pass' blocked activation and the gradient's blocked form, shared with the data-gradient conv
                 xb = x_val.as_blk(terms) if x_val is not None else ops.f32_to_blocked(x_in, terms)
-                gb = g_val.as_blk(terms) if g_val is not None else ops.f32_to_blocked(gd, terms)
-                return ops.conv3d_wgrad_umma(xb, gb, tuple(x_in.shape), layer.transposed, terms)
+                return ops.conv3d_wgrad_umma(xb, g_val.as_blk(terms), tuple(x_in.shape), layer.transposed, terms)
             if terms and layer.k == 3 and layer.stride == 2:
-                dw = self._wgrad_stride2(layer, x_in, gd, terms)
+                dw = self._wgrad_stride2(layer, x_in, g_val, x_val, terms)
                 if dw is not None:
                     return dw
-        return ops.conv3d_wgrad_f32(x_in, gd, layer.filters, layer.k, layer.stride, layer.transposed)
+        return ops.conv3d_wgrad_f32(x_in, g_val.as_f32(), layer.filters, layer.k, layer.stride, layer.transposed)
 
     @staticmethod
-    def _wgrad_stride2(layer, x_in, gd, terms):
+    def _wgrad_stride2(layer, x_in, g_val, x_val, terms):
         """Stride-2 layers on the stride-1 tcgen05 kernel by phase decomposition.  Both the stride-2 conv and the stride-2 transposed
         conv read their large tensor L (the conv's input / the transposed conv's output gradient) at 2b + t, t in {0, 1, 2} per axis,
         against the small tensor S at b:  dW[t] = sum_b L[2b + t] * S[b].  With the eight phase volumes L_p[b] = L[2b + p] stacked as
         channels this is a stride-1 correlation: t = 0 -> (phase 0, offset 0), t = 1 -> (phase 1, offset 0), t = 2 -> (phase 0, offset
         +1).  The phase channels are cut into chunks of C = channels of S (the kernel wants C in == C out); each chunk is one launch
         and the (phase, offset) blocks that exist are picked from its 27 x C x C result."""
-        large, small = (gd, x_in) if layer.transposed else (x_in, gd)
-        n, c, sd, sh, sw = small.shape
-        cb = large.shape[1]
-        if c % cb or (8 * cb) % c or tuple(large.shape[2:]) != (2 * sd, 2 * sh, 2 * sw):
+        if isinstance(g_val, torch.Tensor):
+            g_val = MT._Val(f32=g_val, shape=tuple(g_val.shape))
+        small_shape = tuple(x_in.shape) if layer.transposed else g_val.shape
+        large_shape = g_val.shape if layer.transposed else tuple(x_in.shape)
+        n, c, sd, sh, sw = small_shape
+        cb = large_shape[1]
+        if c % cb or (8 * cb) % c or tuple(large_shape[2:]) != (2 * sd, 2 * sh, 2 * sw) or cb % 8 or c % 16:
             return None
         if not ops.wgrad_umma_eligible(n, c, c, 3, 1, sd, sh, sw, terms):
             return None
-        if cb % 8 or c % 16:
-            return None
         ppc, nch = c // cb, 8 * cb // c          # phases per chunk, chunks
+        large = g_val.as_f32() if layer.transposed else x_in
         phb = ops.f32_phases_to_blocked(large.contiguous(), c, terms)     # phase split + blocked layout in one pass
-        sb = ops.f32_to_blocked(small, terms)
+        if layer.transposed:
+            sb = x_val.as_blk(terms) if x_val is not None else ops.f32_to_blocked(x_in, terms)
+        else:
+            sb = g_val.as_blk(terms)
         outs = [ops.conv3d_wgrad_umma(phb[j], sb, (n, c, sd, sh, sw), False, terms) for j in range(nch)]
         dw = torch.empty((27, x_in.shape[1], layer.filters), device=x_in.device, dtype=torch.float32)
         for t in range(27):
@@ -215,11 +219,24 @@ class Trainer:
         return dw
 
     def _backward(self, tape, g_out, grads, need_input_grad=True):
+        """Backward pass of one transform.  The gradients travel as _Val: in tensor-core mode they stay in the blocked bf16 layout
+        between the layers (the data-gradient conv writes it, the ReLU mask / residual add / bias gradient / weight gradient read
+        it); an fp32 copy is made only where an fp32 kernel needs one."""
         steps, out_id, vals, kv = tape
-        g = {out_id: g_out}
+        V = MT._Val
+        terms = {'bf16x3': 2, 'bf16': 1, 'fp32': 0}[MT.get_precision()] if self.tensor_cores else 0
+        g = {out_id: V(f32=g_out, shape=tuple(g_out.shape))}
+
+        def blocked(v):
+            return terms and v.blk is not None and v.terms == terms
 
         def accumulate(vid, t):
-            g[vid] = t if vid not in g else ops.axpby(g[vid], t, 1.0, 1.0)
+            if vid not in g:
+                g[vid] = t
+            elif blocked(g[vid]) and blocked(t):
+                g[vid] = V(blk=ops.add_blocked(g[vid].blk, t.blk, t.shape, terms), shape=t.shape, terms=terms)
+            else:
+                g[vid] = V(f32=ops.axpby(g[vid].as_f32(), t.as_f32(), 1.0, 1.0), shape=t.shape)
 
         for s in reversed(steps):
             if s[0] == 'add':
@@ -228,22 +245,33 @@ class Trainer:
                 accumulate(s[2], gd)
                 continue
             _, layer, src, dst, _ = s
-            gd = g.pop(dst)
+            gv = g.pop(dst)
             if layer.relu:
-                gd = ops.relu_bwd(gd, vals[dst])
+                yv = kv.get(dst)
+                if yv is not None and blocked(yv) and (blocked(gv) or terms):
+                    gv = V(blk=ops.relu_mask_blocked(gv.as_blk(terms), yv.blk, gv.shape, terms), shape=gv.shape, terms=terms)
+                else:
+                    gv = V(f32=ops.relu_bwd(gv.as_f32(), vals[dst]), shape=gv.shape)
             p = self.params[layer]
             x_in = vals[src]
-            g_val = MT._Val(f32=gd, shape=tuple(gd.shape)) if self.tensor_cores else None
-            grads[layer] = {'w': self._wgrad(layer, x_in, gd, kv.get(src), g_val), 'b': ops.bias_grad_f32(gd) if p['b'] is not None else None}
+            if p['b'] is None:
+                db = None
+            elif blocked(gv):
+                db = ops.bias_grad_blocked(gv.blk, gv.shape, terms)
+            else:
+                db = ops.bias_grad_f32(gv.as_f32())
+            grads[layer] = {'w': self._wgrad(layer, x_in, gv, kv.get(src)), 'b': db}
             if src != 0 or need_input_grad:
                 # data gradient = the adjoint layer: conv <-> transposed conv, tap-major weights with the channel axes swapped
                 if self.tensor_cores:
-                    gx = MT.run_layer(self.twins[layer], g_val, g.pop(src, None))
+                    g[src] = MT.run_layer(self.twins[layer], gv, g.pop(src, None), return_val=True)
                 else:
                     w_t = p['w'].transpose(1, 2).contiguous()
-                    gx = ops.conv3d_f32(gd, w_t, None, layer.in_channels, layer.k, layer.stride, not layer.transposed, False, g.pop(src, None))
-                g[src] = gx
-        return g.get(0)
+                    res = g.pop(src, None)
+                    gx = ops.conv3d_f32(gv.as_f32(), w_t, None, layer.in_channels, layer.k, layer.stride, not layer.transposed, False,
+                                        None if res is None else res.as_f32())
+                    g[src] = V(f32=gx, shape=tuple(gx.shape))
+        return g[0].as_f32() if 0 in g else None
 
     # -- entropy bottleneck helpers (host float64; C x 3 values) ----------------------------------------
     def _aux_loss_and_grad(self):

@@ -70,7 +70,7 @@ def test_stride2_layers_by_phase_decomposition(transposed, cin, cout, s_small, n
     xd = torch.relu(torch.randn((n, cin, s_in, s_in, s_in), device='cuda', generator=g))
     gd = torch.randn((n, cout, s_out, s_out, s_out), device='cuda', generator=g) * 1e-3
     layer = SimpleNamespace(transposed=transposed, filters=cout, k=3, stride=2)
-    got = Trainer._wgrad_stride2(layer, xd, gd, 2)
+    got = Trainer._wgrad_stride2(layer, xd, gd, None, 2)
     assert got is not None
     want = ops.conv3d_wgrad_f32(xd, gd, cout, 3, 2, transposed).cpu().numpy()
     assert _rel(got.cpu().numpy(), want) < 2e-4, _rel(got.cpu().numpy(), want)
@@ -85,3 +85,28 @@ def test_wgrad_umma_rejects_unsupported_geometry():
     with pytest.raises(ValueError):
         ops.conv3d_wgrad_umma(torch.zeros(8, device='cuda', dtype=torch.bfloat16), torch.zeros(8, device='cuda', dtype=torch.bfloat16),
                               (1, 64, 4, 4, 4), False, 2)
+
+
+@pytest.mark.parametrize('shape', [(3, 16, 5, 6, 8), (2, 12, 4, 4, 4), (32, 64, 8, 8, 8)])
+@pytest.mark.parametrize('terms', [2, 1])
+def test_blocked_backward_helpers(shape, terms):
+    """ReLU mask, residual add and bias gradient on the blocked bf16 layout (what the tensor-core training path uses between the layers of
+    its backward pass) against the fp32 kernels of the same steps"""
+    g = torch.Generator(device='cuda').manual_seed(shape[1])
+    gd = torch.randn(shape, device='cuda', generator=g)
+    y = torch.relu(torch.randn(shape, device='cuda', generator=g))
+    y[0, 0].zero_()
+    gb, yb = ops.f32_to_blocked(gd, terms), ops.f32_to_blocked(y, terms)
+    masked = ops.relu_mask_blocked(gb, yb, shape, terms)
+    want = ops.f32_to_blocked(ops.relu_bwd(gd, y), terms)
+    assert torch.equal(ops.blocked_to_f32(masked, shape, terms), ops.blocked_to_f32(want, shape, terms))
+    other = torch.randn(shape, device='cuda', generator=g)
+    ob = ops.f32_to_blocked(other, terms)
+    tol = 2e-5 if terms == 2 else 2e-2
+    s = ops.blocked_to_f32(ops.add_blocked(gb, ob, shape, terms), shape, terms)
+    ref = ops.blocked_to_f32(gb, shape, terms) + ops.blocked_to_f32(ob, shape, terms)
+    assert float((s - ref).abs().max()) <= tol * float(ref.abs().max())
+    db = ops.bias_grad_blocked(gb, shape, terms).cpu().numpy()
+    ref_db = ops.blocked_to_f32(gb, shape, terms).double().sum((0, 2, 3, 4)).cpu().numpy()
+    assert db.shape == (shape[1],)
+    assert np.abs(db - ref_db).max() <= 1e-5 * max(1.0, np.abs(ref_db).max())
